@@ -1,0 +1,146 @@
+/* zenflow_b200 — C ABI of the B200-native spline-coupling hot path.
+ *
+ * The reference (HDembinski/zenflow) is pure Python/JAX and has no FFI of its own; this
+ * header is the boundary a `jax.ffi` / XLA custom-call adapter (or the ctypes host layer
+ * in zenflow_b200/_lib.py) binds.  Every entry point names the reference function it
+ * replaces (paths relative to the reference's src/zenflow/).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes and small POD structs; no C++/torch/XLA types;
+ *  - `stream` is a cudaStream_t passed as void*; work is only enqueued on it, the
+ *    library never synchronises, allocates, frees or retains device pointers;
+ *  - all tensors are DEVICE pointers, fp32 row-major unless stated; descriptor structs
+ *    (zf_chain, zf_op, zf_coupling, zf_shift_bounds) live in HOST memory and hold
+ *    device pointers to the unmodified FLAX variable leaves;
+ *  - scratch is supplied by the caller (`workspace`), sized by zf_*_workspace_bytes;
+ *  - return value: ZF_OK (0) or a zf_status error; zf_last_error() returns a
+ *    thread-local message.  Nothing throws across the ABI;
+ *  - entry points are re-entrant; the only global state is a per-device cache of
+ *    device attributes and cudaFuncSetAttribute calls.
+ */
+#ifndef ZENFLOW_B200_H
+#define ZENFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZF_ABI_VERSION 1
+#define ZF_MAX_LAYERS 8   /* hidden layers per conditioner */
+#define ZF_MAX_DIM 64     /* columns of x */
+
+typedef enum zf_status {
+    ZF_OK = 0,
+    ZF_ERR_INVALID = 1,      /* bad argument (shape, null pointer, alignment)            */
+    ZF_ERR_UNSUPPORTED = 2,  /* valid but outside what the kernels are built for         */
+    ZF_ERR_CUDA = 3,         /* a CUDA runtime call failed; message has the CUDA error   */
+    ZF_ERR_WORKSPACE = 4     /* workspace too small                                       */
+} zf_status;
+
+typedef enum zf_op_kind { ZF_OP_SHIFT_BOUNDS = 0, ZF_OP_ROLL = 1, ZF_OP_COUPLING = 2 } zf_op_kind;
+
+/* distributions.py:50-126 */
+typedef enum zf_latent_kind {
+    ZF_LATENT_BETA = 0,       /* Beta(peakness, peakness), distributions.py:81-116 */
+    ZF_LATENT_NORMAL = 1,     /* Normal(0.5, 0.1),         distributions.py:50-62  */
+    ZF_LATENT_TRUNCNORMAL = 2,/* truncnorm(-5,5,0.5,0.1),  distributions.py:65-78  */
+    ZF_LATENT_UNIFORM = 3     /* Uniform(0,1),             distributions.py:119-126 */
+} zf_latent_kind;
+
+/* ShiftBounds column treatment, bijectors.py:183-205 */
+typedef enum zf_bound_kind {
+    ZF_BOUND_NONE = 0,   /* unit-interval map from running min/max            */
+    ZF_BOUND_BOTH = 1,   /* (x-a)/(b-a)                                         */
+    ZF_BOUND_LOWER = 2,  /* t = log(x-a+tiny), then unit-interval map of t     */
+    ZF_BOUND_UPPER = 3   /* t = log(b-x+tiny), then unit-interval map of t     */
+} zf_bound_kind;
+
+/* bijectors.py:132-273 ShiftBounds.  xmin/xmax: DEVICE arrays of `dim` floats packing the
+ * batch_stats leaves xmin_i/xmax_i (entries of ZF_BOUND_BOTH columns are ignored). */
+typedef struct zf_shift_bounds {
+    int32_t kind[ZF_MAX_DIM];
+    double lo[ZF_MAX_DIM];   /* a (Python double in the reference, bijectors.py:185-192) */
+    double hi[ZF_MAX_DIM];   /* b */
+    double margin;
+    float* xmin;
+    float* xmax;
+} zf_shift_bounds;
+
+/* bijectors.py:300-371 NeuralSplineCoupling.  Leaves exactly as FLAX stores them:
+ * BatchNorm_0 scale/bias (params), mean/var (batch_stats), all (F,), F = dim - dim/2 + cdim;
+ * Dense_j kernel (in,out) row-major and bias (out,), j = 0..n_hidden (the last one has
+ * out = (dim/2)*(3*knots-1), column index = j_dim*(3*knots-1) + p, bijectors.py:346-347). */
+typedef struct zf_coupling {
+    int32_t knots;
+    int32_t n_hidden;
+    int32_t hidden[ZF_MAX_LAYERS];
+    const float* bn_scale;
+    const float* bn_bias;
+    float* bn_mean;
+    float* bn_var;
+    const float* kernel[ZF_MAX_LAYERS + 1];
+    const float* bias[ZF_MAX_LAYERS + 1];
+} zf_coupling;
+
+typedef struct zf_op {
+    int32_t kind;   /* zf_op_kind */
+    int32_t shift;  /* ZF_OP_ROLL: jnp.roll shift, bijectors.py:286-297 */
+    const zf_shift_bounds* shift_bounds;
+    const zf_coupling* coupling;
+} zf_op;
+
+/* bijectors.py:90-124 Chain (a single bijector is a chain of one op). */
+typedef struct zf_chain {
+    int32_t dim;    /* D, columns of x                      */
+    int32_t cdim;   /* C, columns of c (0: unconditional)   */
+    int32_t n_ops;
+    const zf_op* ops;
+} zf_chain;
+
+int32_t zf_abi_version(void);
+const char* zf_last_error(void);
+/* Number of kernels this library has launched on the calling thread (bench bookkeeping). */
+int64_t zf_launch_count(void);
+
+/* ---- spline stage on raw conditioner output --------------------------------------------
+ * theta (M, d, 3K-1): raw widths | heights | slopes per transformed dim (bijectors.py:347-355).
+ * Replaces utils.py:37-62 normalize_spline_params + :65-141 rational_quadratic_spline_forward
+ * (+ :205-250 _compute_rqs_input/_knots/_index).  x, y (M, d); log_det (M,);
+ * idx (M, d) int32 bin indices in [0, K] (may be NULL). */
+int zf_rqs_forward(void* stream, const float* theta, const float* x, int64_t M, int32_t d,
+                   int32_t K, float* y, float* log_det, int32_t* idx);
+/* utils.py:144-202 rational_quadratic_spline_inverse on raw theta (bins searched in yk). */
+int zf_rqs_inverse(void* stream, const float* theta, const float* y, int64_t M, int32_t d,
+                   int32_t K, float* x, int32_t* idx);
+
+/* Exhaustive device self-test of the exact-arithmetic fast paths the bin search relies on
+ * (zf_math.cuh): mismatches[0] = sqrt fast path vs sqrt.rn over every float in [2^-100, 2^100],
+ * [1] = squareplus fast vs IEEE over |x| < 2^40, [2] = reciprocal-form division vs div.rn.
+ * mismatches: DEVICE array of 3 uint64; all must be 0. */
+int zf_selftest_exact_math(void* stream, uint64_t* mismatches);
+
+/* ---- whole-chain eval passes -------------------------------------------------------------
+ * One fused pass per call: ShiftBounds, conditioner MLP (eval-mode BatchNorm), spline,
+ * Roll (as column renaming) and, for log_prob, the latent log-pdf + nan_to_num. */
+size_t zf_chain_workspace_bytes(const zf_chain* chain, int64_t M);
+
+/* Chain.__call__(x, c, train=False), bijectors.py:104-111.  y (M,D) and/or log_det (M,)
+ * may be NULL.  c is (M,C) or NULL when cdim == 0. */
+int zf_chain_forward(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                     float* y, float* log_det, void* workspace, size_t workspace_bytes);
+/* Chain.inverse(z, c), bijectors.py:113-116. */
+int zf_chain_inverse(void* stream, const zf_chain* chain, const float* z, const float* c, int64_t M,
+                     float* x, void* workspace, size_t workspace_bytes);
+/* Flow.__call__(x, c, train=False), flow.py:22-48: latent.log_prob(bijector(x)) + log_det,
+ * nan_to_num(nan=-inf). */
+int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness,
+                     const float* x, const float* c, int64_t M, float* log_prob, void* workspace,
+                     size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZENFLOW_B200_H */

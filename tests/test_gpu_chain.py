@@ -1,0 +1,170 @@
+"""GPU parity of the fused whole-chain passes (zf_chain_forward / zf_chain_inverse /
+zf_flow_log_prob) through the host API, against the oracle in fp32 and fp64."""
+import numpy as np
+import pytest
+
+from oracle import zenflow_oracle as zo
+from tests.helpers import errs, product_chain, to64, trained_variables
+
+pytestmark = pytest.mark.gpu
+
+# north_star: log_prob within rel 1e-5; the absolute floor covers |lp| ~ 0 and the summed
+# fp32 rounding of D latent terms and up to 8x8 log-det terms.
+LP_RTOL, LP_ATOL = 1e-5, 5e-5
+Y_ATOL = 5e-6
+
+
+def _data(M, D, C, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0.3, 1.2, (M, D)).astype(np.float32)
+    c = rng.uniform(0, 1, (M, C)).astype(np.float32) if C else None
+    return x, c
+
+
+CONFIGS = [
+    # name, D, C, K, layers, n_couplings, roll shift, M
+    ("two_moons", 2, 0, 16, (128, 128), None, 1, 10_000),
+    ("two_moons_conditional", 2, 1, 16, (128, 128), None, 1, 20_011),
+    ("deep_set_flow", 2, 8, 16, (128,) * 6, None, 1, 1000),
+    ("bounded16", 16, 0, 32, (128, 128), 8, 2, 3001),
+    ("cond16", 16, 4, 32, (128, 128), 8, 2, 1500),
+    ("odd", 5, 3, 7, (64, 48), None, 1, 2000),
+    ("wide", 3, 0, 4, (200,), None, 1, 333),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_chain_forward_logprob_inverse(cfg):
+    from zenflow_b200 import Flow
+
+    name, D, C, K, layers, ncoup, shift, M = cfg
+    ops = zo.make_chain(D, K, layers, n_couplings=ncoup, roll_shift=shift)
+    x, c = _data(M, D, C, seed=len(name))
+    v = trained_variables(ops, x, c, seed=1)
+    chain = product_chain(ops)
+
+    # --- Chain.__call__ eval
+    y, ld = chain.apply(v, x, c, train=False)
+    yo, ldo, _ = zo.chain_forward(ops, v, x, c)
+    y64, ld64, _ = zo.chain_forward(ops, to64(v), x.astype(np.float64), None if c is None else c.astype(np.float64))
+    e_or = errs(yo, y64)
+    e_gpu = errs(y, y64)
+    print(f"\n[{name}] y err gpu={e_gpu:.2e} oracle32={e_or:.2e}; ld err gpu={errs(ld, ld64):.2e} "
+          f"oracle32={errs(ldo, ld64):.2e}")
+    np.testing.assert_allclose(y, y64, atol=Y_ATOL, rtol=0)
+    np.testing.assert_allclose(ld, ld64, rtol=LP_RTOL, atol=LP_ATOL)
+
+    # --- Flow.__call__ (log_prob)
+    flow = Flow(chain)
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    lp = flow.apply(fv, x, c)
+    lp64, _ = zo.flow_log_prob(ops, to64(v), x.astype(np.float64), None if c is None else c.astype(np.float64))
+    lpo, _ = zo.flow_log_prob(ops, v, x, c)
+    print(f"[{name}] lp err gpu={errs(lp, lp64):.2e} oracle32={errs(lpo, lp64):.2e} |lp|max={np.abs(lp64).max():.1f}")
+    assert lp.shape == (M,) and lp.dtype == np.float32
+    np.testing.assert_allclose(lp, lp64, rtol=LP_RTOL, atol=LP_ATOL)
+
+    # --- Chain.inverse on a given latent draw (parity mode of Flow.sample)
+    u = np.random.default_rng(3).beta(12, 12, (M, D)).astype(np.float32)
+    xi = chain.apply(v, u, c, method="inverse")
+    xi64 = zo.chain_inverse(ops, to64(v), u.astype(np.float64), None if c is None else c.astype(np.float64))
+    xio = zo.chain_inverse(ops, v, u, c)
+    scale = np.abs(xi64).max()
+    print(f"[{name}] inverse err gpu={errs(xi, xi64):.2e} oracle32={errs(xio, xi64):.2e} scale={scale:.1f}")
+    np.testing.assert_allclose(xi, xi64, atol=2e-5 * max(1.0, scale), rtol=0)
+
+
+def test_reference_kats_through_host_api():
+    """tests/test_bijectors.py:168-206 (Roll / Chain golden vectors) on the CUDA path."""
+    from zenflow_b200 import bijectors as bi
+
+    x = np.array([[1, 5], [3, 4], [6, 2]])
+    roll = bi.Roll()
+    z, ld = roll.apply(roll.init(0, x, None), x, None, train=True)
+    np.testing.assert_array_equal(z, [[5, 1], [4, 3], [2, 6]])
+    np.testing.assert_array_equal(ld, np.zeros(3))
+    np.testing.assert_array_equal(roll.apply({}, z, None, method="inverse"), x)
+
+    x = np.array([[1, 2, 3], [4, 5, 6]])
+    ch = bi.Chain([bi.Roll(), bi.Roll()])
+    z, ld = ch.apply({}, x, None, train=False)
+    np.testing.assert_array_equal(z, [[2, 3, 1], [5, 6, 4]])
+    np.testing.assert_array_equal(ch.apply({}, z, None, method="inverse"), x)
+
+    # ShiftBounds eval with the reference's golden statistics (test_ShiftBounds_1)
+    sb = bi.ShiftBounds(margin=0.01)
+    stats = {"batch_stats": {"xmin_0": np.array([0.975], np.float32), "xmax_0": np.array([6.025], np.float32),
+                             "xmin_1": np.array([1.985], np.float32), "xmax_1": np.array([5.015], np.float32)}}
+    x = np.array([[1, 5], [3, 4], [6, 2]])
+    y, ld = sb.apply(stats, x, None)
+    y_ref = np.column_stack([(x[:, 0] - 0.975) / (6.025 - 0.975), (x[:, 1] - 1.985) / (5.015 - 1.985)])
+    np.testing.assert_allclose(y, y_ref, atol=5e-6)
+    np.testing.assert_allclose(ld, np.log(1 / 5.05) + np.log(1 / 3.03), atol=5e-6)
+    np.testing.assert_allclose(sb.apply(stats, y, None, method="inverse"), x, atol=6e-6)
+
+
+def test_shift_bounds_bounded_variants_eval():
+    """tests/test_bijectors.py:61-92 formulas, eval mode with oracle statistics."""
+    from zenflow_b200 import bijectors as bi
+
+    rng = np.random.default_rng(0)
+    x = np.column_stack([2 * rng.uniform(size=50) - 1, rng.exponential(size=50) * 10 + 10,
+                         1 - rng.exponential(size=50)]).astype(np.float32)
+    bounds = [(0, -1, 1), (1, 10, None), (2, None, 1)]
+    st = {}
+    yo, ldo = zo.shift_bounds_forward(x, st, margin=0.0, bounds=bounds, train=True)
+    sb = bi.ShiftBounds(margin=0.0, bounds=bounds)
+    y, ld = sb.apply({"batch_stats": st}, x, None)
+    np.testing.assert_allclose(y, yo, atol=2e-6)
+    np.testing.assert_allclose(ld, ldo, rtol=1e-5, atol=1e-5)
+    x2 = sb.apply({"batch_stats": st}, y, None, method="inverse")
+    np.testing.assert_allclose(x2, zo.shift_bounds_inverse(yo, st, bounds=bounds), rtol=1e-5, atol=1e-5)
+
+
+def test_latent_log_probs_on_device():
+    """tests/test_distributions.py:11-74 through the latent kernel."""
+    from zenflow_b200 import distributions as dist
+
+    rng = np.random.default_rng(1)
+    x = rng.uniform(size=(1000, 3)).astype(np.float32)
+    x[0] = [0.0, 0.5, 1.0]
+    x[1] = [-0.1, 0.5, 0.5]
+    for d, kind in [(dist.Beta(), "beta"), (dist.Normal(), "normal"), (dist.TruncatedNormal(), "truncnorm"),
+                    (dist.Uniform(), "uniform"), (dist.Beta(3.5), "beta")]:
+        lp = d.log_prob(x)
+        ref = zo.latent_log_prob(x.astype(np.float64), kind, getattr(d, "peakness", 12.0))
+        fin = np.isfinite(ref)
+        np.testing.assert_allclose(lp[fin], ref[fin], rtol=2e-5, atol=2e-5)
+        # flow.py:47 is applied by the kernel: -inf -> finfo.min
+        assert (lp[~fin] == np.finfo(np.float32).min).all()
+        assert d.dim == 3
+
+
+def test_batch_permutation_is_bit_exact_at_full_size():
+    """Samples are independent in eval mode: lp(x[perm]) == lp(x)[perm] bit-for-bit, at the
+    two_moons_conditional bench size (1M) — catches any tile-boundary or scheduling bug."""
+    import torch
+    from zenflow_b200 import Flow
+
+    D, C, M = 2, 1, 1_000_000
+    ops = zo.make_chain(D)
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 1, (M, D)).astype(np.float32)
+    c = rng.integers(0, 2, (M, 1)).astype(np.float32)
+    v = trained_variables(ops, x[:5000], c[:5000])
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    xt, ct = torch.from_numpy(x).cuda(), torch.from_numpy(c).cuda()
+    lp = flow.apply(fv, xt, ct)
+    perm = torch.randperm(M, device="cuda")
+    lp2 = flow.apply(fv, xt[perm], ct[perm])
+    assert torch.equal(lp[perm], lp2)
+    sub = np.r_[0:2048, M - 2048:M]
+    lp64, _ = zo.flow_log_prob(ops, to64(v), x[sub].astype(np.float64), c[sub].astype(np.float64))
+    np.testing.assert_allclose(lp[sub].cpu().numpy(), lp64, rtol=LP_RTOL, atol=LP_ATOL)
+    # round trip inverse(forward(x)) ~ x (structural EPS mismatch allows ~1e-4)
+    chain = flow.bijector
+    y, _ = chain.apply(v, xt, ct)
+    x2 = chain.apply(v, y, ct, method="inverse")
+    inside = (y > 1e-3).all(1) & (y < 1 - 1e-3).all(1)
+    assert float((x2 - xt)[inside].abs().max()) < 5e-4 * float(xt.abs().max())

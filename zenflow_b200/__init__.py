@@ -1,0 +1,15 @@
+"""zenflow_b200 — the spline-coupling hot path of zenflow as hand-written sm_100a CUDA
+behind the reference's FLAX-module API (``Flow``, the bijectors, the latent distributions,
+``train``).  CUDA only: there is no CPU fallback."""
+
+from .flow import Flow
+
+__all__ = ("Flow", "train")
+
+
+def __getattr__(name):
+    if name == "train":
+        from .train import train
+
+        return train
+    raise AttributeError(name)

@@ -1,0 +1,46 @@
+"""Device-memory plumbing (PyTorch owns HBM buffers and streams; nothing else).
+
+The product needs a CUDA device: every helper here raises if none is present.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("zenflow_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device_f32(a, device: Optional[torch.device] = None) -> torch.Tensor:
+    """numpy / torch / list -> contiguous float32 CUDA tensor (ints are cast like the
+    reference does, bijectors.py:178-179)."""
+    device = device or require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def like_input(t: torch.Tensor, template):
+    """Return results in the caller's currency: numpy in -> numpy out, torch in -> torch out."""
+    if isinstance(template, torch.Tensor):
+        return t
+    return t.cpu().numpy()

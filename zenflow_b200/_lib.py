@@ -1,0 +1,135 @@
+"""ctypes binding of libzenflow_b200.so (the C ABI in include/zenflow_b200.h).
+
+There is no CPU fallback: if the shared library is missing and cannot be built, or a call
+returns a non-zero status, this module raises.  PyTorch is used by the callers only to own
+device memory and streams; no torch type crosses this boundary (pointers and sizes only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+ZF_MAX_LAYERS = 8
+ZF_MAX_DIM = 64
+
+OP_SHIFT_BOUNDS, OP_ROLL, OP_COUPLING = 0, 1, 2
+LATENT_KINDS = {"beta": 0, "normal": 1, "truncnorm": 2, "uniform": 3}
+BOUND_NONE, BOUND_BOTH, BOUND_LOWER, BOUND_UPPER = 0, 1, 2, 3
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class ZfShiftBounds(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32 * ZF_MAX_DIM),
+        ("lo", C.c_double * ZF_MAX_DIM),
+        ("hi", C.c_double * ZF_MAX_DIM),
+        ("margin", C.c_double),
+        ("xmin", C.c_void_p),
+        ("xmax", C.c_void_p),
+    ]
+
+
+class ZfCoupling(C.Structure):
+    _fields_ = [
+        ("knots", C.c_int32),
+        ("n_hidden", C.c_int32),
+        ("hidden", C.c_int32 * ZF_MAX_LAYERS),
+        ("bn_scale", C.c_void_p),
+        ("bn_bias", C.c_void_p),
+        ("bn_mean", C.c_void_p),
+        ("bn_var", C.c_void_p),
+        ("kernel", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+        ("bias", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+    ]
+
+
+class ZfOp(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("shift", C.c_int32),
+        ("shift_bounds", C.POINTER(ZfShiftBounds)),
+        ("coupling", C.POINTER(ZfCoupling)),
+    ]
+
+
+class ZfChain(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("cdim", C.c_int32),
+        ("n_ops", C.c_int32),
+        ("ops", C.POINTER(ZfOp)),
+    ]
+
+
+class ZenflowNativeError(RuntimeError):
+    """A C-ABI call returned a non-zero zf_status."""
+
+
+_lock = threading.Lock()
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/zenflow_b200.h declares
+SIGNATURES = {
+    "zf_abi_version": (C.c_int32, []),
+    "zf_last_error": (C.c_char_p, []),
+    "zf_launch_count": (C.c_int64, []),
+    "zf_rqs_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zf_rqs_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p]),
+    "zf_selftest_exact_math": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zf_chain_workspace_bytes": (C.c_size_t, [C.POINTER(ZfChain), C.c_int64]),
+    "zf_chain_forward": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_chain_inverse": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_flow_log_prob": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_int32, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t]),
+}
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the in-tree .so is absent or stale and nvcc exists)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if os.environ.get("ZENFLOW_B200_NO_BUILD") != "1":
+            try:
+                path = _build.build()
+            except Exception as e:  # no nvcc on the box: use the prebuilt library if present
+                if not os.path.exists(path):
+                    raise ImportError(
+                        f"zenflow_b200: native library {path} is missing and could not be built: {e}"
+                    ) from e
+        if not os.path.exists(path):
+            raise ImportError(f"zenflow_b200: native library {path} is missing (run python -m zenflow_b200.build)")
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        ver = lib.zf_abi_version()
+        if ver != 1:
+            raise ImportError(f"zenflow_b200: ABI version {ver} != 1")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().zf_last_error().decode(errors="replace")
+        raise ZenflowNativeError(f"{what or 'zenflow_b200'} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().zf_launch_count())

@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the spline-coupling hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload two_moons_conditional|bounded16]
+  python bench.py --impl reference ...        # the reference's CPU implementation of the path
+
+One step = one ``Flow.__call__`` (log-prob) pass over one batch of synthetic events.  At N=1
+the workload is BASELINE.json configs[1] (two_moons_conditional: 2-D flow, 1-D condition,
+default rolling_spline_coupling chain, batch 1M).  With N>1 (torchrun, one rank per GPU) every
+rank evaluates its own batch - the eval path shards over events with no data-path collective,
+so scaling is "weak" - and the time is the max over ranks.
+
+Printed JSON (one line, rank 0): value = events/s with inputs resident in HBM; e2e = the same
+metric through the public API from pinned HOST buffers (H2D of x and c, D2H of log_prob inside
+the timed region); roofline for the dominant kernel; cpu_baseline = the numpy oracle ("port",
+NOT the reference: JAX is not installable in this image) on a bounded sample of the same
+workload.  ``--impl reference`` times that CPU port with all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "two_moons_conditional": dict(D=2, C=1, K=16, layers=(128, 128), n_couplings=None, roll=1, M=1_000_000),
+    # BASELINE.json configs[3] (16-D bounded flow, 8 couplings, K=32); M reduced by --batch
+    "bounded16": dict(D=16, C=0, K=32, layers=(128, 128), n_couplings=8, roll=2, M=16 * 2 ** 20),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def chain_flops_per_event(w):
+    d = w["D"] // 2
+    F = w["D"] - d + w["C"]
+    widths = [F] + list(w["layers"]) + [d * (3 * w["K"] - 1)]
+    per = 2 * sum(a * b for a, b in zip(widths[:-1], widths[1:]))
+    n = w["D"] if w["n_couplings"] is None else w["n_couplings"]
+    return per * n
+
+
+def default_cpu_sample(w):
+    """Bounded CPU sample: about 2e11 conditioner flops (~10-30 s on 8 host cores)."""
+    return int(max(20_000, min(4_000_000, 2e11 // chain_flops_per_event(w))))
+
+
+def synth(w, M, seed):
+    """Synthetic events of the workload's shape (two_moons_conditional: two noisy half circles
+    with the class label as condition, as examples/two_moons_conditional.ipynb builds them)."""
+    rng = np.random.default_rng(seed)
+    if w["D"] == 2 and w["C"] == 1:
+        lab = rng.integers(0, 2, M)
+        t = rng.uniform(0, np.pi, M)
+        x = np.where(lab == 0, np.cos(t), 1 - np.cos(t)) + 0.1 * rng.standard_normal(M)
+        y = np.where(lab == 0, np.sin(t), 0.5 - np.sin(t)) + 0.1 * rng.standard_normal(M)
+        return np.column_stack([x, y]).astype(np.float32), lab.astype(np.float32).reshape(-1, 1)
+    x = rng.uniform(0, 1, (M, w["D"])).astype(np.float32)
+    c = rng.uniform(0, 1, (M, w["C"])).astype(np.float32) if w["C"] else None
+    return x, c
+
+
+def oracle_ops(w):
+    from oracle import zenflow_oracle as zo
+
+    return zo.make_chain(w["D"], w["K"], w["layers"], n_couplings=w["n_couplings"], roll_shift=w["roll"])
+
+
+def make_variables(w, seed=0):
+    """Fixed-seed variables shared by both arms: LeCun-normal kernels, small random biases and
+    BatchNorm statistics, ShiftBounds statistics from a 4096-event sample."""
+    from oracle import zenflow_oracle as zo
+
+    ops = oracle_ops(w)
+    v = zo.init_variables(ops, w["D"], w["C"], seed, randomize_bn=True)
+    xs, cs = synth(w, 4096, seed + 1)
+    _, _, stats = zo.chain_forward(ops, v, xs, cs, train=True)
+    v["batch_stats"]["bijectors_0"] = stats["bijectors_0"]
+    return ops, v
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle over all host cores (fork pool, one BLAS thread per worker)
+# ----------------------------------------------------------------------------------------
+_G = {}
+
+
+def _cpu_worker(args):
+    lo, hi = args
+    from oracle import zenflow_oracle as zo
+
+    lp, _ = zo.flow_log_prob(_G["ops"], _G["v"], _G["x"][lo:hi], None if _G["c"] is None else _G["c"][lo:hi])
+    return float(lp[np.isfinite(lp)].sum())
+
+
+def cpu_events_per_s(w, sample, steps=1, warmup=0, cores=None):
+    """Events/s of the CPU port on `sample` events per step, sharded over `cores` processes."""
+    import multiprocessing as mp
+
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    cores = cores or os.cpu_count() or 1
+    ops, v = make_variables(w)
+    x, c = synth(w, sample, 123)
+    _G.update(ops=ops, v=v, x=x, c=c)
+    chunk = 16384
+    shards = [(i, min(sample, i + chunk)) for i in range(0, sample, chunk)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_worker, shards)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_worker, shards)
+        dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU path.  The real reference needs
+    jax+flax+optax (absent from this image and from the GPU box) - try it, else time the
+    CPU port of the same path (oracle/) with every host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    kind = "port"
+    try:  # pragma: no cover - cannot succeed in this image
+        sys.path.insert(0, "/root/reference/src")
+        import jax  # noqa: F401
+        import flax  # noqa: F401
+        kind = "reference"
+    except Exception:
+        pass
+    sample = args.cpu_sample or default_cpu_sample(w)
+    value, sec, cores = cpu_events_per_s(w, sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "flow_log_prob_events_per_s", "value": value, "unit": "events/s",
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "events_per_step": sample, **{k: w[k] for k in ("D", "C", "K")},
+                   "layers": list(w["layers"]), "note": "bounded sample of the same workload per step"},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} events/step, numpy fp32 restatement of the reference path "
+                                   f"(JAX not installable here), {cores} forked workers x 1 BLAS thread"},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        allsm = []
+        for t, line in self.rows:
+            p = [v.strip() for v in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                clk, mx_ = float(p[0]), float(p[1])
+            except ValueError:
+                continue
+            mx = mx_
+            allsm.append(clk)
+            if t0 <= t <= t1 + 0.06:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        use = sm or allsm[-3:]
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from zenflow_b200 import Flow, _lib
+    from zenflow_b200 import bijectors as bi
+    from zenflow_b200.utils import rqs_forward_raw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["M"] = args.batch
+    M = w["M"]
+    ops, v = make_variables(w)
+    mods = []
+    for op in ops:
+        if op["kind"] == "shift_bounds":
+            mods.append(bi.ShiftBounds(margin=op["margin"], bounds=op["bounds"]))
+        elif op["kind"] == "roll":
+            mods.append(bi.Roll(op["shift"]))
+        else:
+            mods.append(bi.NeuralSplineCoupling(knots=op["knots"], layers=op["layers"]))
+    flow = Flow(bi.Chain(mods))
+    tree = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    variables = torch.utils._pytree.tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev), tree)
+
+    # rotating input sets: their total exceeds L2 (126 MB), so every step reads cold inputs
+    bytes_in = 4 * M * (w["D"] + w["C"])
+    bytes_out = 4 * M
+    n_sets = max(2, int(np.ceil(2 * 126e6 / (bytes_in + bytes_out))))
+    n_sets = min(n_sets, 24)
+    xs_h, cs_h = [], []
+    for i in range(n_sets):
+        x, c = synth(w, M, 1000 + 97 * rank + i)
+        xs_h.append(torch.from_numpy(x).pin_memory())
+        cs_h.append(None if c is None else torch.from_numpy(c).pin_memory())
+    xs_d = [t.to(dev) for t in xs_h]
+    cs_d = [None if t is None else t.to(dev) for t in cs_h]
+    lp_host = torch.empty(M, dtype=torch.float32).pin_memory()
+
+    def step_device(i):
+        return flow.apply(variables, xs_d[i % n_sets], cs_d[i % n_sets])
+
+    def step_e2e(i):
+        x = xs_h[i % n_sets].to(dev, non_blocking=True)
+        c = None if cs_h[i % n_sets] is None else cs_h[i % n_sets].to(dev, non_blocking=True)
+        lp = flow.apply(variables, x, c)
+        lp_host.copy_(lp, non_blocking=True)
+        return lp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, K, W):
+        for i in range(W):
+            step(i)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for i in range(K):
+            ev[i][0].record()
+            step(W + i)
+            ev[i][1].record()
+        barrier()
+        t1 = time.perf_counter()
+        launches = _lib.launch_count() - l0
+        total_ms = ev[0][0].elapsed_time(ev[-1][1])  # device time of exactly K back-to-back steps
+        per = [a.elapsed_time(b) for a, b in ev]
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, per, launches, (t0, t1)
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms, per, launches, (t0, t1) = timed(step_device, K, W)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    value = world * M * K / (total_ms * 1e-3)
+
+    e2e_ms, _, _, _ = timed(step_e2e, K, W)
+    e2e_value = world * M * K / (e2e_ms * 1e-3)
+
+    # Flow.sample's inverse chain on a given latent draw (same events/s unit), N=1 extra
+    extras = {}
+    pk = peaks()
+    if rank == 0:
+        u = torch.rand(M, w["D"], device=dev) * 0.8 + 0.1
+
+        def step_inv(i):
+            return flow.apply(variables, u, cs_d[i % n_sets], method="inverse")
+
+        inv_ms, _, _, _ = timed(step_inv, max(3, K // 4), 3) if world == 1 else (None, None, None, None)
+        if inv_ms:
+            extras["inverse_events_per_s"] = M * max(3, K // 4) / (inv_ms * 1e-3)
+
+        # the standalone spline stage of this workload's shape against the HBM roof
+        d = w["D"] // 2
+        P = 3 * w["K"] - 1
+        Ms = min(M, int(1.5e9 // (4 * d * P)))  # >= L2 several times over, <= 1.5 GB
+        theta = torch.randn(Ms, d, P, device=dev)
+        xin = torch.rand(Ms, d, device=dev)
+        for _ in range(3):
+            rqs_forward_raw(xin, theta, w["K"])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for _ in range(reps):
+            rqs_forward_raw(xin, theta, w["K"])
+        b.record()
+        torch.cuda.synchronize()
+        st_ms = a.elapsed_time(b) / reps
+        alg = 4.0 * (d * P + 2 * d + 1) * Ms
+        extras["roofline_spline_stage"] = {
+            "kernel": "rqs_stage_kernel (zf_rqs_forward)", "bound": "hbm", "achieved": alg / st_ms / 1e6,
+            "peak": pk["hbm"], "unit": "GB/s", "frac": alg / st_ms / 1e6 / pk["hbm"], "traffic": None,
+            "events": Ms, "bytes_per_event": 4 * (d * P + 2 * d + 1), "peak_source": pk["source"]}
+        del theta, xin
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops = chain_flops_per_event(w)
+    step_ms = total_ms / K
+    tflops = flops * M / (step_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "chain_kernel<false> (zf_flow_log_prob): fused conditioner MLPs + splines + latent",
+        "bound": "tensor", "achieved": tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tflops / pk["bf16"],
+        "traffic": None, "flops_per_event": flops,
+        "note": "fp32 FFMA (SIMT) GEMMs this round: FP32 SIMT roof is 74.4 TFLOP/s at 1965 MHz; "
+                "achieved uses the whole step time (pack kernels included, <1%)",
+        "frac_of_fp32_simt_peak": tflops / 74.4, "peak_source": pk["source"]}
+
+    cpu_sample = args.cpu_sample or default_cpu_sample(w)
+    cpu_value, cpu_sec, cores = cpu_events_per_s(w, cpu_sample, steps=1, warmup=0) if world == 1 else (None, None, None)
+
+    line = {
+        "metric": "flow_log_prob_events_per_s", "value": value, "unit": "events/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "events_per_step_per_gpu": M, "D": w["D"], "C": w["C"], "K": w["K"],
+                   "layers": list(w["layers"]), "couplings": w["D"] if w["n_couplings"] is None else w["n_couplings"],
+                   "latent": "Beta(12)", "l2": f"rotating {n_sets} input sets ({n_sets * (bytes_in + bytes_out) / 1e6:.0f} MB > 126 MB L2)",
+                   "seed": 0},
+        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "step_ms_min_median_max": [float(np.min(per)), float(np.median(per)), float(np.max(per))],
+    }
+    if cpu_value is not None:
+        line["cpu_baseline"] = {"value": cpu_value, "unit": "events/s", "cores": cores, "kind": "port",
+                                "sample": f"{cpu_sample} events, numpy fp32 restatement of the reference path "
+                                          f"(JAX not installable here), {cores} forked workers x 1 BLAS thread, "
+                                          f"{cpu_sec:.1f} s"}
+    line.update(extras)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="two_moons_conditional", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override events per step per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

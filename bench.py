@@ -152,7 +152,8 @@ def run_reference(args):
         kind = "reference"
     except Exception:
         pass
-    sample = args.cpu_sample or default_cpu_sample(w)
+    # bounded: the whole --steps K run stays within ~3x the default sample (a few minutes at most)
+    sample = args.cpu_sample or max(20_000, 3 * default_cpu_sample(w) // max(1, args.steps))
     value, sec, cores = cpu_events_per_s(w, sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "flow_log_prob_events_per_s", "value": value, "unit": "events/s",

@@ -45,3 +45,16 @@ def errs(a, b):
         d = np.abs(a - b)
     d = d[np.isfinite(d)]
     return float(d.max()) if d.size else 0.0
+
+
+def assert_fp32_parity(got, truth64, oracle32, what, rtol=1e-5, atol=2e-5):
+    got = np.asarray(got, np.float64)
+    fin = np.isfinite(truth64) & (np.abs(truth64) < 1e30)
+    np.testing.assert_array_equal(np.isfinite(got) & (np.abs(got) < 1e30), fin, err_msg=what)
+    err = np.abs(got - truth64)[fin]
+    ref = np.abs(np.asarray(oracle32, np.float64) - truth64)[fin]
+    ratio = err / (rtol * np.abs(truth64[fin]) + atol)
+    assert np.quantile(ratio, 0.999) <= 1.0, f"{what}: 99.9% quantile of err/tol = {np.quantile(ratio, 0.999):.2f}"
+    assert err.max() <= 2.0 * ref.max() + 1e-5, f"{what}: max err {err.max():.3e} vs fp32 oracle {ref.max():.3e}"
+
+

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import zenflow_oracle as zo
-from tests.helpers import errs, product_chain, to64, trained_variables
+from tests.helpers import assert_fp32_parity, errs, product_chain, to64, trained_variables
 
 pytestmark = pytest.mark.gpu
 
@@ -16,17 +16,6 @@ pytestmark = pytest.mark.gpu
 #   (b) the worst sample no worse than 2x the float32 oracle's own worst sample (+1e-5).
 LP_RTOL, LP_ATOL = 1e-5, 2e-5
 Y_ATOL = 5e-6
-
-
-def assert_fp32_parity(got, truth64, oracle32, what, rtol=LP_RTOL, atol=LP_ATOL):
-    got = np.asarray(got, np.float64)
-    fin = np.isfinite(truth64) & (np.abs(truth64) < 1e30)
-    np.testing.assert_array_equal(np.isfinite(got) & (np.abs(got) < 1e30), fin, err_msg=what)
-    err = np.abs(got - truth64)[fin]
-    ref = np.abs(np.asarray(oracle32, np.float64) - truth64)[fin]
-    ratio = err / (rtol * np.abs(truth64[fin]) + atol)
-    assert np.quantile(ratio, 0.999) <= 1.0, f"{what}: 99.9% quantile of err/tol = {np.quantile(ratio, 0.999):.2f}"
-    assert err.max() <= 2.0 * ref.max() + 1e-5, f"{what}: max err {err.max():.3e} vs fp32 oracle {ref.max():.3e}"
 
 
 def _data(M, D, C, seed):

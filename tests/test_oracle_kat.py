@@ -275,3 +275,47 @@ def test_idx_equals_K_semantics():
     y, ld, idx = zo.rqs_forward(x, dx, dy, sl, return_idx=True)
     assert idx[0, 0] == K and np.isnan(y[0, 0]) and np.isnan(ld[0])
     assert idx[1, 0] == K and y[1, 0] == np.float32(1.5) and ld[1] == 0
+
+
+def test_torch_oracle_matches_numpy():
+    """The gradient oracle's forward (torch float64) equals the numpy oracle's train-mode
+    forward in float64, and its gradients agree with central differences of the numpy oracle
+    (the reference's own method for derivatives, tests/test_utils.py:38-47)."""
+    from oracle import torch_oracle as to
+
+    rng = np.random.default_rng(0)
+    D, C, M = 4, 2, 64
+    ops = zo.make_chain(D, 8, (16, 16))
+    x = rng.normal(0.3, 1.0, (M, D))
+    c = rng.uniform(0, 1, (M, C))
+    v = zo.init_variables(ops, D, C, 1, weight_scale=2.0, randomize_bn=True)
+    v64 = {"params": _to64(v["params"]), "batch_stats": _to64(v["batch_stats"])}
+    lp_np, stats_np = zo.flow_log_prob(ops, v64, x, c, train=True)
+    loss, grads, new_stats, gc, lp_t = to.loss_and_grads(ops, v64, x, c)
+    assert_allclose(lp_t, lp_np, rtol=1e-10, atol=1e-10)
+    assert_allclose(loss, -lp_np.mean(), rtol=1e-12)
+    assert_allclose(new_stats["bijectors_1"]["BatchNorm_0"]["mean"], stats_np["bijectors_1"]["BatchNorm_0"]["mean"], rtol=1e-6)  # stored as float32 leaves
+    assert_allclose(new_stats["bijectors_0"]["xmin_0"], stats_np["bijectors_0"]["xmin_0"], rtol=1e-6)
+
+    def loss_np(vv, cc):
+        lp, _ = zo.flow_log_prob(ops, vv, x, cc, train=True)
+        return -lp.mean()
+
+    h = 1e-6
+    for (name, layer, leaf, pos) in [("bijectors_1", "Dense_2", "kernel", (3, 5)), ("bijectors_3", "Dense_0", "kernel", (1, 2)),
+                                     ("bijectors_5", "BatchNorm_0", "scale", (2,)), ("bijectors_1", "Dense_1", "bias", (7,))]:
+        vp, vm = _to64(v64), _to64(v64)
+        vp["params"][name][layer][leaf][pos] += h
+        vm["params"][name][layer][leaf][pos] -= h
+        num = (loss_np(vp, c) - loss_np(vm, c)) / (2 * h)
+        assert_allclose(grads[name][layer][leaf][pos], num, rtol=2e-5, atol=1e-8)
+    cp, cm = c.copy(), c.copy()
+    cp[5, 1] += h
+    cm[5, 1] -= h
+    assert_allclose(gc[5, 1], (loss_np(v64, cp) - loss_np(v64, cm)) / (2 * h), rtol=2e-5, atol=1e-9)
+
+
+def _to64(t):
+    if isinstance(t, dict):
+        return {k: _to64(v) for k, v in t.items()}
+    return np.array(t, np.float64)

@@ -1,0 +1,792 @@
+// Train-mode kernels: everything train.py:64-86 (loss_fn + jax.grad + optax update) needs
+// beyond the eval chain kernel.  The reference has no hand-written backward (jax.grad does it);
+// the derivatives here follow the as-computed forward expressions incl. every +EPS
+//  and are checked against float64 autograd of the oracle.
+//
+// The batch couples samples in train mode (BatchNorm batch moments, ShiftBounds batch
+// min/max), so the step is a sequence of phases; between phases the host may all-reduce the
+// small statistics across ranks (NCCL) - see zenflow_b200/_train.py.
+//
+//   zf_shift_bounds_minmax / _update   <- bijectors.py:250-260
+//   zf_bn_moments / zf_bn_finalize      <- flax BatchNorm(use_running_average=False), bijectors.py:342
+//   zf_flow_loss_grad                   <- flow.py:46-47 + train.py:73 (-mean) and d/dz of the latent
+//   zf_coupling_backward                <- VJP of bijectors.py:329-365 (conditioner recompute + spline VJP)
+//   zf_bn_backward_apply                <- VJP of train-mode BatchNorm into x and c
+//   zf_nadamw_update                    <- optax.nadamw / adamw (train.py:12-15,84-85)
+#include "zf_common.cuh"
+#include "zf_math.cuh"
+
+#include <float.h>
+#include <algorithm>
+
+namespace zf {
+
+void count_launch();
+
+// ---------------------------------------------------------------------------------------------
+// ShiftBounds batch min/max
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+struct SbCols {
+    int kind[ZF_MAX_DIM];
+    float lo[ZF_MAX_DIM], hi[ZF_MAX_DIM];
+};
+
+__global__ void minmax_init_kernel(unsigned* enc, int D) {
+    int i = threadIdx.x;
+    if (i < D) { enc[i] = 0xffffffffu; enc[D + i] = 0u; }
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(const __grid_constant__ SbCols cols, const float* __restrict__ x,
+                                                     long long M, int D, unsigned* enc) {
+    __shared__ unsigned smin[ZF_MAX_DIM], smax[ZF_MAX_DIM];
+    if (threadIdx.x < D) { smin[threadIdx.x] = 0xffffffffu; smax[threadIdx.x] = 0u; }
+    __syncthreads();
+    const long long n = M * D;
+    // a thread always sees the same column when the stride is a multiple of D
+    const long long stride = (long long)gridDim.x * blockDim.x * D;
+    for (int j = 0; j < D; ++j) {
+        // thread handles rows m = gtid, gtid + G, ... for column j (coalescing across j is lost,
+        // this pass is tiny next to the conditioner GEMMs)
+    }
+    const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * blockDim.x;
+    (void)stride;
+    for (long long e = gtid; e < n; e += gsz) {
+        const int j = (int)(e % D);
+        float v = x[e];
+        const int kind = cols.kind[j];
+        if (kind == ZF_BOUND_BOTH) continue;
+        if (kind == ZF_BOUND_LOWER) v = logf(__fadd_rn(__fsub_rn(v, cols.lo[j]), FLT_MIN));
+        if (kind == ZF_BOUND_UPPER) v = logf(__fadd_rn(__fsub_rn(cols.hi[j], v), FLT_MIN));
+        if (v != v) continue;
+        const unsigned o = f2ord(v);
+        atomicMin(&smin[j], o);
+        atomicMax(&smax[j], o);
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+        atomicMin(&enc[threadIdx.x], smin[threadIdx.x]);
+        atomicMax(&enc[D + threadIdx.x], smax[threadIdx.x]);
+    }
+}
+
+__global__ void minmax_decode_kernel(const unsigned* enc, float* out, int D) {
+    int i = threadIdx.x;
+    if (i < 2 * D) out[i] = ord2f(enc[i]);
+}
+
+// bijectors.py:250-260: widen by the margin, merge with the running values, store.
+__global__ void sb_update_kernel(const __grid_constant__ SbCols cols, float margin, const float* minmax, float* xmin,
+                                 float* xmax, int D) {
+    int i = threadIdx.x;
+    if (i >= D || cols.kind[i] == ZF_BOUND_BOTH) return;
+    float lo = minmax[i], hi = minmax[D + i];
+    float delta = __fmul_rn(__fmul_rn(0.5f, __fsub_rn(hi, lo)), margin);
+    lo = __fsub_rn(lo, delta);
+    hi = __fadd_rn(hi, delta);
+    xmin[i] = fminf(xmin[i], lo);
+    xmax[i] = fmaxf(xmax[i], hi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm train statistics: h = hstack(x[:, d:], c)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cond_feature(const float* __restrict__ x, const float* __restrict__ c, long long m,
+                                              int f, int D, int d, int C) {
+    return (f < D - d) ? x[m * D + d + f] : c[m * C + (f - (D - d))];
+}
+
+// sums[f] += sum_m h, sums[F+f] += sum_m h^2 (double)
+__global__ void __launch_bounds__(256) bn_moments_kernel(const float* __restrict__ x, const float* __restrict__ c,
+                                                         long long M, int D, int C, double* sums) {
+    const int d = D / 2, F = D - d + C;
+    extern __shared__ double sh[];  // [2][F]
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int R = blockDim.x / F;  // rows per pass
+    const int r = threadIdx.x / F, f = threadIdx.x - r * F;
+    if (r < R) {
+        double s1 = 0.0, s2 = 0.0;
+        for (long long m = (long long)blockIdx.x * R + r; m < M; m += (long long)gridDim.x * R) {
+            const float h = cond_feature(x, c, m, f, D, d, C);
+            s1 += (double)h;
+            s2 += (double)h * (double)h;
+        }
+        atomicAdd(&sh[f], s1);
+        atomicAdd(&sh[F + f], s2);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(&sums[i], sh[i]);
+}
+
+// mean, biased variance via E[x^2]-E[x]^2 clipped at 0, running update with momentum
+__global__ void bn_finalize_kernel(const double* sums, double count, int F, float momentum, float* bmean, float* bvar,
+                                   float* ra_mean, float* ra_var) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const float mean = (float)(sums[f] / count);
+    const float mean2 = (float)(sums[F + f] / count);
+    const float var = fmaxf(0.f, __fsub_rn(mean2, __fmul_rn(mean, mean)));
+    bmean[f] = mean;
+    bvar[f] = var;
+    if (ra_mean) ra_mean[f] = __fadd_rn(__fmul_rn(momentum, ra_mean[f]), __fmul_rn((float)(1.0 - (double)momentum), mean));
+    if (ra_var) ra_var[f] = __fadd_rn(__fmul_rn(momentum, ra_var[f]), __fmul_rn((float)(1.0 - (double)momentum), var));
+}
+
+// H0[m][f] = (h - mean) * (rsqrt(var+eps)*scale) + bias      (row stride F)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ c,
+                                                       long long M, int D, int C, const float* __restrict__ scale,
+                                                       const float* __restrict__ bias, const float* __restrict__ mean,
+                                                       const float* __restrict__ var, float* __restrict__ H0) {
+    const int d = D / 2, F = D - d + C;
+    const long long n = M * F;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / F;
+        const int f = (int)(e - m * F);
+        const float h = cond_feature(x, c, m, f, D, d, C);
+        const float mul = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[f], 1e-5f))) * scale[f];
+        H0[e] = (h - mean[f]) * mul + bias[f];
+    }
+}
+
+// sums[f] += sum_m g, sums[F+f] += sum_m g*xhat   (xhat = (h-mean)*rstd)
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ c,
+                                                          const float* __restrict__ g, long long M, int D, int C,
+                                                          const float* __restrict__ mean, const float* __restrict__ var,
+                                                          double* sums) {
+    const int d = D / 2, F = D - d + C;
+    extern __shared__ double sh[];
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int R = blockDim.x / F;
+    const int r = threadIdx.x / F, f = threadIdx.x - r * F;
+    if (r < R) {
+        const float mu = mean[f];
+        const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[f], 1e-5f)));
+        double s1 = 0.0, s2 = 0.0;
+        for (long long m = (long long)blockIdx.x * R + r; m < M; m += (long long)gridDim.x * R) {
+            const float h = cond_feature(x, c, m, f, D, d, C);
+            const float gg = g[m * F + f];
+            s1 += (double)gg;
+            s2 += (double)gg * (double)((h - mu) * rstd);
+        }
+        atomicAdd(&sh[f], s1);
+        atomicAdd(&sh[F + f], s2);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(&sums[i], sh[i]);
+}
+
+// dh = scale*rstd*(g - S1/N - xhat*S2/N); gx[:, d+f] += dh (f < D-d), gc[:, f-(D-d)] += dh
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ c,
+                                                           const float* __restrict__ g, long long M, int D, int C,
+                                                           const float* __restrict__ scale, const float* __restrict__ mean,
+                                                           const float* __restrict__ var, const double* __restrict__ sums,
+                                                           double count, float* __restrict__ gx, float* __restrict__ gc) {
+    const int d = D / 2, F = D - d + C;
+    const long long n = M * F;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / F;
+        const int f = (int)(e - m * F);
+        const float h = cond_feature(x, c, m, f, D, d, C);
+        const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[f], 1e-5f)));
+        const float xhat = (h - mean[f]) * rstd;
+        const float s1 = (float)(sums[f] / count), s2 = (float)(sums[F + f] / count);
+        const float dh = scale[f] * rstd * (g[e] - s1 - xhat * s2);
+        if (f < D - d) gx[m * D + d + f] += dh;
+        else if (gc) gc[m * C + (f - (D - d))] += dh;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss and latent gradient
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_grad_kernel(LatentConst lc, const float* __restrict__ z,
+                                                        const float* __restrict__ log_det, long long M, int D,
+                                                        float wgt, float* __restrict__ lp_out, float* __restrict__ gz,
+                                                        float* __restrict__ glp, double* lp_sum) {
+    __shared__ double red[256];
+    double local = 0.0;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        float lat = 0.f;
+        for (int j = 0; j < D; ++j) lat += latent_logpdf(z[m * D + j], lc);
+        const float raw = lat + log_det[m];
+        const float lp = nan_to_num_lp(raw);
+        const bool fin = (raw == raw) && fabsf(raw) <= FLT_MAX;
+        const float w = fin ? wgt : 0.f;   // nan_to_num replaces non-finite lp by constants: zero gradient
+        if (lp_out) lp_out[m] = lp;
+        glp[m] = w;
+        local += (double)lp;
+        for (int j = 0; j < D; ++j) {
+            const float v = z[m * D + j];
+            float dl = 0.f;
+            if (lc.kind == kLatentBeta) dl = (v > 1.f || v < 0.f) ? 0.f : (lc.p1 / v - lc.p1 / (1.f - v));
+            else if (lc.kind == kLatentNormal) dl = -(v - 0.5f) / 0.01f;
+            else if (lc.kind == kLatentTruncNormal) dl = (v > 1.f || v < 0.f) ? 0.f : -(v - 0.5f) / 0.01f;
+            gz[m * D + j] = w * dl;
+        }
+    }
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(lp_sum, red[0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic fp32 GEMM family for the conditioner recompute / backward (64x64x16 tiles, 4x4 per thread)
+//   mode 0 (NN): C[m][n]  = sum_k opA(A[m][k]) * B[k][n] + bias[n]
+//   mode 1 (NT): C[m][k]  = (sum_n A[m][n] * B[k][n]) * swish'(Z[m][k])          (Z optional)
+//   mode 2 (TN): C[k][n] += sum_m opA(A[m][k]) * B[m][n];  colsum[n] += sum_m B[m][n]
+// opA = swish when a_swish (the stored pre-activations are re-activated on load).
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+    const float* A; long long lda;
+    const float* B; long long ldb;
+    float* C; long long ldc;
+    const float* bias;
+    float* colsum;
+    const float* Z; long long ldz;
+    int a_swish;
+    long long I, J, R;   // output rows, output cols, reduction length
+    long long r_slab;    // mode 2: reduction rows per CTA (gridDim.z slabs)
+};
+
+constexpr int GT = 64, GK = 16, GS = 68;
+
+__device__ __forceinline__ float swish_grad(float z) {
+    const float s = 1.0f / (1.0f + expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+}
+
+// pattern T: S[r][t] = X[(t0+t)*ld + r0+r]   (r contiguous in memory)
+__device__ __forceinline__ void load_T(float (*S)[GS], const float* __restrict__ X, long long ld, long long t0,
+                                       long long tmax, long long r0, long long rmax, bool act, int tid) {
+#pragma unroll
+    for (int q = 0; q < (GT * GK) / 256; ++q) {
+        const int e = tid + q * 256;
+        const int r = e % GK, t = e / GK;
+        float v = 0.f;
+        if (t0 + t < tmax && r0 + r < rmax) {
+            v = X[(t0 + t) * ld + r0 + r];
+            if (act) v = swishf(v);
+        }
+        S[r][t] = v;
+    }
+}
+// pattern D: S[r][t] = X[(r0+r)*ld + t0+t]   (t contiguous in memory)
+__device__ __forceinline__ void load_D(float (*S)[GS], const float* __restrict__ X, long long ld, long long t0,
+                                       long long tmax, long long r0, long long rmax, bool act, int tid) {
+#pragma unroll
+    for (int q = 0; q < (GT * GK) / 256; ++q) {
+        const int e = tid + q * 256;
+        const int t = e % GT, r = e / GT;
+        float v = 0.f;
+        if (t0 + t < tmax && r0 + r < rmax) {
+            v = X[(r0 + r) * ld + t0 + t];
+            if (act) v = swishf(v);
+        }
+        S[r][t] = v;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmArgs g) {
+    __shared__ __align__(16) float As[GK][GS];
+    __shared__ __align__(16) float Bs[GK][GS];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long i0 = (long long)blockIdx.x * GT, j0 = (long long)blockIdx.y * GT;
+    long long rbeg = 0, rend = g.R;
+    if (MODE == 2) {
+        rbeg = (long long)blockIdx.z * g.r_slab;
+        rend = rbeg + g.r_slab < g.R ? rbeg + g.r_slab : g.R;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    float csum = 0.f;
+
+    for (long long r0 = rbeg; r0 < rend; r0 += GK) {
+        if (MODE == 0) {
+            load_T(As, g.A, g.lda, i0, g.I, r0, rend, g.a_swish != 0, tid);
+            load_D(Bs, g.B, g.ldb, j0, g.J, r0, rend, false, tid);
+        } else if (MODE == 1) {
+            load_T(As, g.A, g.lda, i0, g.I, r0, rend, false, tid);
+            load_T(Bs, g.B, g.ldb, j0, g.J, r0, rend, false, tid);
+        } else {
+            load_D(As, g.A, g.lda, i0, g.I, r0, rend, g.a_swish != 0, tid);
+            load_D(Bs, g.B, g.ldb, j0, g.J, r0, rend, false, tid);
+        }
+        __syncthreads();
+        if (MODE == 2 && g.colsum && blockIdx.x == 0 && tid < GT) {
+#pragma unroll
+            for (int r = 0; r < GK; ++r) csum += Bs[r][tid];
+        }
+#pragma unroll
+        for (int r = 0; r < GK; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[r][tx * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[r][ty * 4]);
+            const float a_[4] = {a.x, a.y, a.z, a.w}, b_[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a_[p], b_[q], acc[p][q]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const long long i = i0 + tx * 4 + p;
+        if (i >= g.I) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long j = j0 + ty * 4 + q;
+            if (j >= g.J) continue;
+            float v = acc[p][q];
+            if (MODE == 0) {
+                if (g.bias) v += g.bias[j];
+                g.C[i * g.ldc + j] = v;
+            } else if (MODE == 1) {
+                if (g.Z) v *= swish_grad(g.Z[i * g.ldz + j]);
+                g.C[i * g.ldc + j] = v;
+            } else {
+                atomicAdd(&g.C[i * g.ldc + j], v);
+            }
+        }
+    }
+    if (MODE == 2 && g.colsum && blockIdx.x == 0 && tid < GT && j0 + tid < g.J) atomicAdd(&g.colsum[j0 + tid], csum);
+}
+
+static int launch_gemm(cudaStream_t st, int mode, const GemmArgs& g) {
+    dim3 grid((unsigned)((g.I + GT - 1) / GT), (unsigned)((g.J + GT - 1) / GT), 1);
+    if (mode == 2) grid.z = (unsigned)((g.R + g.r_slab - 1) / g.r_slab);
+    if (grid.x == 0 || grid.y == 0) return ZF_OK;
+    if (mode == 0) gemm_kernel<0><<<grid, 256, 0, st>>>(g);
+    else if (mode == 1) gemm_kernel<1><<<grid, 256, 0, st>>>(g);
+    else gemm_kernel<2><<<grid, 256, 0, st>>>(g);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spline VJP: theta row -> d(theta) row in place; d/dx of the transformed columns; pass-through
+// of the conditioning columns' cotangent
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float squareplus_grad(float a) {  // d/da 0.5*(a + sqrt(a^2+4))
+    return 0.5f * (1.0f + a * rsqrtf(a * a + 4.0f));
+}
+
+// row: raw theta (3K-1) in shared memory, overwritten by its cotangent.  Returns d/dx.
+__device__ __forceinline__ float rqs_row_backward(float* row, int K, float x, float gy, float gld, const KnotNorm& kn) {
+    RqsBin b;
+    switch (K) {
+        case 16: rqs_locate<16>(row, K, true, x, kn, b); break;
+        case 32: rqs_locate<32>(row, K, true, x, kn, b); break;
+        default: rqs_locate<0>(row, K, true, x, kn, b); break;
+    }
+    const int P = 3 * K - 1;
+    const bool oob = (x < 0.f) || (x >= 1.f);
+    const int idx = b.idx;
+    if (oob || idx >= K || !(x == x)) {  // identity branch (or the reference's NaN corner): no parameter gradient
+        for (int p = 0; p < P; ++p) row[p] = 0.f;
+        return oob ? gy : 0.f;
+    }
+    const float xk = b.ks, w = b.bs, h = b.bo, d0 = b.dk, d1 = b.dkp1;
+    const float s = h / w;
+    const float xi_raw = (x - xk) / w;
+    const bool clipped = !(xi_raw > kEps && xi_raw < kOneMinusEps);
+    const float xi = fminf(fmaxf(xi_raw, kEps), kOneMinusEps);
+    const float az = 1.0f - xi;
+    const float beta = d1 + d0 - 2.0f * s;
+    const float u = s * xi + d0 * az;
+    const float num = h * xi * u;
+    const float den = s + beta * xi * az;
+    const float Dn = den + kEps;
+    const float v = d1 * xi + 2.0f * s * az;
+    const float num2 = xi * v + d0 * az * az;
+
+    // adjoints (Appendix A)
+    const float g_yk = gy;
+    const float g_num = gy / Dn;
+    const float g_den = -gy * num / (Dn * Dn) - 2.0f * gld / Dn;
+    const float g_num2 = gld / (num2 + kEps);
+    float g_s = gld * 2.0f / (s + kEps);
+    float g_h = g_num * xi * u;
+    float g_xi = g_num * h * u;
+    const float g_u = g_num * h * xi;
+    g_s += g_u * xi;
+    g_xi += g_u * s;
+    float g_d0 = g_u * az;
+    float g_az = g_u * d0;
+    g_s += g_den;
+    const float g_beta = g_den * xi * az;
+    g_xi += g_den * beta * az;
+    g_az += g_den * beta * xi;
+    float g_d1 = g_beta;
+    g_d0 += g_beta;
+    g_s -= 2.0f * g_beta;
+    g_xi += g_num2 * v;
+    const float g_v = g_num2 * xi;
+    g_d0 += g_num2 * az * az;
+    g_az += g_num2 * d0 * 2.0f * az;
+    g_d1 += g_v * xi;
+    g_xi += g_v * d1;
+    g_s += g_v * 2.0f * az;
+    g_az += g_v * 2.0f * s;
+    g_xi -= g_az;
+    const float g_xr = clipped ? 0.f : g_xi;
+    const float g_x = g_xr / w;
+    const float g_xk = -g_xr / w;
+    float g_w = -g_xr * xi_raw / w;
+    g_h += g_s / w;
+    g_w -= g_s * s / w;
+
+    // slopes first (their raw values are needed before the row is overwritten)
+    const float c_lo = (idx >= 1) ? row[2 * K + idx - 1] : 0.f;
+    const float c_hi = (idx + 1 <= K - 1) ? row[2 * K + idx] : 0.f;
+
+    // widths: W_j = kappa*(s_j/S + c); cotangent of W_j is g_xk (j<idx), g_w (j==idx), 0 otherwise
+    const float kappa = kn.rden;
+    for (int blk = 0; blk < 2; ++blk) {
+        float* pr = row + blk * K;
+        const float g_lt = blk == 0 ? g_xk : g_yk;
+        const float g_at = blk == 0 ? g_w : g_h;
+        float S = 0.f, Slt = 0.f, s_at = 0.f;
+        for (int j = 0; j < K; ++j) {
+            const float sj = squareplus_rn(pr[j]);
+            S += sj;
+            if (j < idx) Slt += sj;
+            if (j == idx) s_at = sj;
+        }
+        const float A = (g_lt * Slt + g_at * s_at) / S;
+        const float ks = kappa / S;
+        for (int j = 0; j < K; ++j) {
+            const float a = pr[j];
+            const float gW = (j < idx) ? g_lt : ((j == idx) ? g_at : 0.f);
+            pr[j] = ks * (gW - A) * squareplus_grad(a);
+        }
+    }
+    for (int j = 0; j < K - 1; ++j) row[2 * K + j] = 0.f;
+    if (idx >= 1) row[2 * K + idx - 1] = g_d0 * squareplus_grad(c_lo);
+    if (idx + 1 <= K - 1) row[2 * K + idx] = g_d1 * squareplus_grad(c_hi);
+    return g_x;
+}
+
+struct SplineBwdArgs {
+    float* theta;          // (Mb, d, P) in: raw params, out: their cotangent
+    const float* x_in;     // (M, D) rows m0..m0+Mb of the coupling input
+    const float* gy;       // (M, D) cotangent of the coupling output, column (j + rot) % D
+    const float* glp;      // (M,) cotangent of the log-det
+    float* gx;             // (M, D) out
+    long long m0, Mb;
+    int D, d, K, rot;
+    int TS;                // samples per tile
+};
+
+__global__ void __launch_bounds__(256) spline_bwd_kernel(const __grid_constant__ SplineBwdArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int P = 3 * a.K - 1, Pst = P | 1, d = a.d, D = a.D;
+    const KnotNorm kn = make_knot_norm(a.K);
+    const long long n_tiles = (a.Mb + a.TS - 1) / a.TS;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long s0 = tile * a.TS;
+        const int ns = (int)min((long long)a.TS, a.Mb - s0);
+        const int rows = ns * d;
+        float* src = a.theta + s0 * d * P;
+        for (int e = tid; e < rows * P; e += 256) {
+            const int r = e / P, p = e - r * P;
+            sm[r * Pst + p] = src[e];
+        }
+        __syncthreads();
+        for (int r = tid; r < rows; r += 256) {
+            const int sidx = r / d, jj = r - sidx * d;
+            const long long m = a.m0 + s0 + sidx;
+            const float x = a.x_in[m * D + jj];
+            const float gy = a.gy[m * D + (jj + a.rot) % D];
+            a.gx[m * D + jj] = rqs_row_backward(sm + r * Pst, a.K, x, gy, a.glp[m], kn);
+        }
+        // conditioning columns pass through unchanged: d y[:, j] / d x[:, j] = 1   (bijectors.py:364)
+        for (int e = tid; e < ns * (D - d); e += 256) {
+            const int sidx = e / (D - d), j = d + (e - sidx * (D - d));
+            const long long m = a.m0 + s0 + sidx;
+            a.gx[m * D + j] = a.gy[m * D + (j + a.rot) % D];
+        }
+        __syncthreads();
+        for (int e = tid; e < rows * P; e += 256) {
+            const int r = e / P, p = e - r * P;
+            src[e] = sm[r * Pst + p];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimiser: optax.nadamw / adamw on a flat parameter buffer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nadamw_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                     float* __restrict__ mu, float* __restrict__ nu, float lr, float b1,
+                                                     float b2, float eps, float wd, float bc1_t, float bc1_t1, float bc2_t,
+                                                     int nesterov) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float m = b1 * mu[i] + (1.0f - b1) * gi;
+        const float v = b2 * nu[i] + (1.0f - b2) * gi * gi;
+        mu[i] = m;
+        nu[i] = v;
+        float mhat;
+        if (nesterov) mhat = b1 * (m / bc1_t1) + (1.0f - b1) * (gi / bc1_t);
+        else mhat = m / bc1_t;
+        const float vhat = v / bc2_t;
+        const float upd = mhat / (sqrtf(vhat) + eps) + wd * p[i];
+        p[i] = p[i] - lr * upd;
+    }
+}
+
+static unsigned grid_for(long long n, int per_block, int cap) {
+    long long b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (unsigned)b;
+}
+
+static void fill_cols(const zf_shift_bounds* sb, int D, SbCols& c) {
+    for (int i = 0; i < D; ++i) {
+        c.kind[i] = sb->kind[i];
+        c.lo[i] = (float)sb->lo[i];
+        c.hi[i] = (float)sb->hi[i];
+    }
+}
+
+}  // namespace zf
+
+using namespace zf;
+
+extern "C" int zf_shift_bounds_minmax(void* stream, const zf_shift_bounds* sb, const float* x, int64_t M, int32_t D,
+                                      float* minmax, void* scratch) {
+    ZF_REQUIRE(sb && x && minmax && scratch, "shift_bounds_minmax: null argument");
+    ZF_REQUIRE(D >= 1 && D <= ZF_MAX_DIM && M >= 1, "shift_bounds_minmax: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    SbCols cols{};
+    fill_cols(sb, D, cols);
+    unsigned* enc = static_cast<unsigned*>(scratch);
+    minmax_init_kernel<<<1, 2 * ZF_MAX_DIM, 0, st>>>(enc, D);
+    minmax_kernel<<<grid_for(M * D, 256 * 16, 148 * 8), 256, 0, st>>>(cols, x, M, D, enc);
+    minmax_decode_kernel<<<1, 2 * ZF_MAX_DIM, 0, st>>>(enc, minmax, D);
+    count_launch(); count_launch(); count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_shift_bounds_update(void* stream, const zf_shift_bounds* sb, int32_t D, const float* minmax) {
+    ZF_REQUIRE(sb && minmax && sb->xmin && sb->xmax, "shift_bounds_update: null argument");
+    SbCols cols{};
+    fill_cols(sb, D, cols);
+    sb_update_kernel<<<1, ZF_MAX_DIM, 0, (cudaStream_t)stream>>>(cols, (float)sb->margin, minmax, sb->xmin, sb->xmax, D);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_bn_moments(void* stream, const float* x, const float* c, int64_t M, int32_t D, int32_t C, double* sums) {
+    const int d = D / 2, F = D - d + C;
+    ZF_REQUIRE(x && sums && (C == 0 || c) && M >= 1 && d > 0 && F <= 256, "bn_moments: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ZF_CUDA_CHECK(cudaMemsetAsync(sums, 0, 2 * F * sizeof(double), st));
+    const int R = 256 / F;
+    bn_moments_kernel<<<grid_for(M, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(x, c, M, D, C, sums);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_bn_finalize(void* stream, const double* sums, double count, int32_t F, float momentum,
+                              float* batch_mean, float* batch_var, float* ra_mean, float* ra_var) {
+    ZF_REQUIRE(sums && batch_mean && batch_var && F >= 1 && count >= 1, "bn_finalize: bad argument");
+    bn_finalize_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, F, momentum, batch_mean, batch_var,
+                                                                           ra_mean, ra_var);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
+                                 int64_t M, int32_t D, double global_count, float* lp, float* gz, float* glp,
+                                 double* lp_sum) {
+    ZF_REQUIRE(z && log_det && gz && glp && lp_sum && M >= 1 && D >= 1 && global_count >= 1, "flow_loss_grad: bad argument");
+    LatentConst lc{};
+    lc.kind = latent_kind;
+    lc.p1 = (float)((double)peakness - 1.0);
+    lc.betaln = (float)(2.0 * lgamma((double)peakness) - lgamma(2.0 * (double)peakness));
+    lc.lognorm = (float)log(2.0 * M_PI * 0.1 * 0.1);
+    lc.logmass = (float)log(0.5 * (erf(5.0 / sqrt(2.0)) - erf(-5.0 / sqrt(2.0))));
+    loss_grad_kernel<<<grid_for(M, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(lc, z, log_det, M, D,
+                                                                                  (float)(-1.0 / global_count), lp, gz, glp,
+                                                                                  lp_sum);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+static size_t cpl_bwd_floats_per_sample(const zf_coupling* cp, int D, int C) {
+    const int d = D / 2, F = D - d + C;
+    size_t n = F;
+    for (int l = 0; l < cp->n_hidden; ++l) n += cp->hidden[l];
+    n += (size_t)d * (3 * cp->knots - 1);
+    return n;
+}
+
+extern "C" size_t zf_coupling_backward_workspace_bytes(const zf_coupling* cp, int32_t D, int32_t C, int64_t micro_batch) {
+    if (!cp || D < 2 || micro_batch < 1) return 0;
+    return (cpl_bwd_floats_per_sample(cp, D, C) * (size_t)micro_batch + 64) * sizeof(float);
+}
+
+extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const zf_coupling_grads* gr, int32_t D, int32_t C,
+                                    const float* x_in, const float* c, const float* gy, int32_t gy_rot, const float* glp,
+                                    int64_t M, float* gx, float* gh0, double* bn_sums, void* workspace,
+                                    size_t workspace_bytes, int64_t micro_batch) {
+    ZF_REQUIRE(cp && gr && x_in && gy && glp && gx && gh0 && bn_sums && workspace, "coupling_backward: null argument");
+    const int d = D / 2, F = D - d + C;
+    ZF_REQUIRE(d > 0 && d < D && (C == 0 || c) && M >= 1 && micro_batch >= 1, "coupling_backward: bad shape");
+    ZF_REQUIRE(F <= 256, "coupling_backward: at most 256 conditioner inputs");
+    const int K = cp->knots, P = 3 * K - 1, L = cp->n_hidden;
+    const size_t per = cpl_bwd_floats_per_sample(cp, D, C);
+    if (workspace_bytes < (per * (size_t)micro_batch + 64) * sizeof(float))
+        return fail(ZF_ERR_WORKSPACE, "coupling_backward: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+
+    // spline tile: TS samples x d rows, ~256 rows, bounded by shared memory
+    const int Pst = P | 1;
+    int TS = std::max(1, 256 / d);
+    while (TS > 1 && (size_t)TS * d * Pst * 4 > 160 * 1024) TS /= 2;
+    const size_t sp_smem = (size_t)TS * d * Pst * 4;
+    if (sp_smem > (size_t)di.max_smem_optin)
+        return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(spline_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+
+    ZF_CUDA_CHECK(cudaMemsetAsync(bn_sums, 0, 2 * F * sizeof(double), st));
+    float* ws = static_cast<float*>(workspace);
+    int widths[ZF_MAX_LAYERS + 2];
+    widths[0] = F;
+    for (int l = 0; l < L; ++l) widths[l + 1] = cp->hidden[l];
+    widths[L + 1] = d * P;
+
+    for (long long m0 = 0; m0 < M; m0 += micro_batch) {
+        const long long Mb = std::min<long long>(micro_batch, M - m0);
+        // activations of this micro-batch: H0 | Z_1 .. Z_L | Theta
+        float* act[ZF_MAX_LAYERS + 2];
+        size_t off = 0;
+        for (int l = 0; l <= L + 1; ++l) {
+            act[l] = ws + off;
+            off += (size_t)widths[l] * Mb;
+        }
+        bn_apply_kernel<<<grid_for(Mb * F, 256 * 8, 148 * 16), 256, 0, st>>>(x_in + m0 * D, c ? c + m0 * C : nullptr, Mb, D, C,
+                                                                             cp->bn_scale, cp->bn_bias, cp->bn_mean,
+                                                                             cp->bn_var, act[0]);
+        count_launch();
+        // forward recompute: Z_{l+1} = act(Z_l) W_l + b_l   (pre-activations are stored)
+        for (int l = 0; l <= L; ++l) {
+            GemmArgs g{};
+            g.A = act[l]; g.lda = widths[l];
+            g.B = cp->kernel[l]; g.ldb = widths[l + 1];
+            g.C = act[l + 1]; g.ldc = widths[l + 1];
+            g.bias = cp->bias[l];
+            g.a_swish = l > 0;
+            g.I = Mb; g.J = widths[l + 1]; g.R = widths[l];
+            if (int rc = launch_gemm(st, 0, g)) return rc;
+        }
+        // spline VJP: Theta -> dTheta in place, gx for all columns
+        {
+            SplineBwdArgs a{};
+            a.theta = act[L + 1]; a.x_in = x_in; a.gy = gy; a.glp = glp; a.gx = gx;
+            a.m0 = m0; a.Mb = Mb; a.D = D; a.d = d; a.K = K; a.rot = ((gy_rot % D) + D) % D; a.TS = TS;
+            const long long tiles = (Mb + TS - 1) / TS;
+            spline_bwd_kernel<<<(unsigned)std::min<long long>(tiles, (long long)di.sm_count * 2), 256, sp_smem, st>>>(a);
+            count_launch();
+        }
+        // backward through the dense layers
+        for (int l = L; l >= 0; --l) {
+            GemmArgs gw{};  // dW_l += act(Z_l)^T dZ_{l+1}; db_l += colsum(dZ_{l+1})
+            gw.A = act[l]; gw.lda = widths[l];
+            gw.B = act[l + 1]; gw.ldb = widths[l + 1];
+            gw.C = gr->kernel[l]; gw.ldc = widths[l + 1];
+            gw.colsum = gr->bias[l];
+            gw.a_swish = l > 0;
+            gw.I = widths[l]; gw.J = widths[l + 1]; gw.R = Mb; gw.r_slab = 2048;
+            if (int rc = launch_gemm(st, 2, gw)) return rc;
+            GemmArgs ga{};  // dZ_l = (dZ_{l+1} W_l^T) * swish'(Z_l)   (l = 0: d/d(BN output), no activation)
+            ga.A = act[l + 1]; ga.lda = widths[l + 1];
+            ga.B = cp->kernel[l]; ga.ldb = widths[l + 1];
+            ga.C = (l == 0) ? gh0 + m0 * F : act[l]; ga.ldc = widths[l];
+            ga.Z = (l == 0) ? nullptr : act[l]; ga.ldz = widths[l];
+            ga.I = Mb; ga.J = widths[l]; ga.R = widths[l + 1];
+            if (int rc = launch_gemm(st, 1, ga)) return rc;
+        }
+        const int R = 256 / F;
+        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(
+            x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
+        count_launch();
+    }
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+__global__ void bn_param_grads_kernel(const double* sums, int F, float* gscale, float* gbias) {
+    int f = threadIdx.x;
+    if (f < F) {
+        gbias[f] += (float)sums[f];
+        gscale[f] += (float)sums[F + f];
+    }
+}
+
+extern "C" int zf_bn_param_grads(void* stream, const double* bn_sums, int32_t F, float* g_scale, float* g_bias) {
+    ZF_REQUIRE(bn_sums && g_scale && g_bias && F >= 1 && F <= 256, "bn_param_grads: bad argument");
+    bn_param_grads_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(bn_sums, F, g_scale, g_bias);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_bn_backward_apply(void* stream, const zf_coupling* cp, int32_t D, int32_t C, const float* x_in,
+                                    const float* c, const float* gh0, const double* bn_sums, double global_count, int64_t M,
+                                    float* gx, float* gc) {
+    ZF_REQUIRE(cp && x_in && gh0 && bn_sums && gx && M >= 1 && global_count >= 1, "bn_backward_apply: bad argument");
+    const int d = D / 2, F = D - d + C;
+    bn_bwd_apply_kernel<<<grid_for(M * F, 256 * 8, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        x_in, c, gh0, M, D, C, cp->bn_scale, cp->bn_mean, cp->bn_var, bn_sums, global_count, gx, gc);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_nadamw_update(void* stream, int64_t n, float* params, const float* grads, float* mu, float* nu,
+                                int64_t count, float lr, float b1, float b2, float eps, float weight_decay,
+                                int32_t nesterov) {
+    ZF_REQUIRE(params && grads && mu && nu && n >= 0 && count >= 0, "nadamw_update: bad argument");
+    if (n == 0) return ZF_OK;
+    const double t = (double)count + 1.0;
+    const float bc1_t = (float)(1.0 - pow((double)b1, t));
+    const float bc1_t1 = (float)(1.0 - pow((double)b1, t + 1.0));
+    const float bc2_t = (float)(1.0 - pow((double)b2, t));
+    nadamw_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(n, params, grads, mu, nu, lr, b1, b2, eps,
+                                                                                  weight_decay, bc1_t, bc1_t1, bc2_t, nesterov);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}

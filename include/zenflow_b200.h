@@ -140,6 +140,71 @@ int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t latent_kind, f
                      const float* x, const float* c, int64_t M, float* log_prob, void* workspace,
                      size_t workspace_bytes);
 
+/* Same as zf_chain_forward but log_det[m] += (this chain's log-det): Chain's running sum
+ * (bijectors.py:107-110) when the train step applies the bijectors one phase at a time. */
+int zf_chain_forward_acc(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                         float* y, float* log_det, void* workspace, size_t workspace_bytes);
+
+/* ---- train step phases (train.py:64-86: loss_fn, jax.grad, optimizer.update) -------------------
+ * Train mode couples the samples of a batch (ShiftBounds batch min/max, BatchNorm batch moments),
+ * so the step is a sequence of phases; a data-parallel host all-reduces the small statistics
+ * between phases.  Gradient buffers are ACCUMULATED into (+=): zero them first. */
+
+/* Device pointers to the cotangents of a coupling's params, same shapes as in zf_coupling. */
+typedef struct zf_coupling_grads {
+    float* bn_scale;
+    float* bn_bias;
+    float* kernel[ZF_MAX_LAYERS + 1];
+    float* bias[ZF_MAX_LAYERS + 1];
+} zf_coupling_grads;
+
+/* bijectors.py:250-252: per-column min and max of the (log-transformed, for one-sided bounds)
+ * column over this rank's batch.  minmax: 2*D floats (min[D] then max[D]); scratch: 2*D uint32. */
+int zf_shift_bounds_minmax(void* stream, const zf_shift_bounds* sb, const float* x, int64_t M, int32_t D,
+                           float* minmax, void* scratch);
+/* bijectors.py:253-260: widen by margin, merge into the running sb->xmin/xmax (in place). */
+int zf_shift_bounds_update(void* stream, const zf_shift_bounds* sb, int32_t D, const float* minmax);
+
+/* flax BatchNorm(use_running_average=False) (bijectors.py:342): sums[0..F) = sum of h,
+ * sums[F..2F) = sum of h^2 over this rank's batch, h = hstack(x[:, D/2:], c), F = D - D/2 + C. */
+int zf_bn_moments(void* stream, const float* x, const float* c, int64_t M, int32_t D, int32_t C, double* sums);
+/* mean / biased variance (E[x^2]-E[x]^2, clipped at 0) from (all-reduced) sums and the global
+ * count; running stats updated with `momentum` (flax default 0.99) when not NULL. */
+int zf_bn_finalize(void* stream, const double* sums, double count, int32_t F, float momentum,
+                   float* batch_mean, float* batch_var, float* ra_mean, float* ra_var);
+
+/* flow.py:46-47 + train.py:73: lp = nan_to_num(latent.log_prob(z) + log_det); adds sum(lp) to
+ * *lp_sum; cotangents of loss = -sum(lp)/global_count: glp (M,) for the log-dets and
+ * gz (M,D) = glp * d latent/dz.  lp (M,) may be NULL. */
+int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
+                      int64_t M, int32_t D, double global_count, float* lp, float* gz, float* glp, double* lp_sum);
+
+/* VJP of NeuralSplineCoupling.__call__(train=True) (bijectors.py:329-365) except the BatchNorm
+ * input path: recomputes the conditioner in micro-batches, then
+ *   gx (M,D)   = d/dx_in through the spline (transformed columns) and the pass-through columns,
+ *   gh0 (M,F)  = d/d(BatchNorm output),
+ *   grads      += d/d(Dense kernels and biases),
+ *   bn_sums[0..F) = sum gh0, [F..2F) = sum gh0*xhat  (for BatchNorm's own VJP).
+ * cp->bn_mean/bn_var must hold the BATCH statistics used in the forward.  gy is the cotangent of
+ * the coupling output; its column j is read at (j + gy_rot) % D (folds the following Rolls). */
+size_t zf_coupling_backward_workspace_bytes(const zf_coupling* cp, int32_t D, int32_t C, int64_t micro_batch);
+int zf_coupling_backward(void* stream, const zf_coupling* cp, const zf_coupling_grads* grads, int32_t D, int32_t C,
+                         const float* x_in, const float* c, const float* gy, int32_t gy_rot, const float* glp,
+                         int64_t M, float* gx, float* gh0, double* bn_sums, void* workspace, size_t workspace_bytes,
+                         int64_t micro_batch);
+/* d/d(BatchNorm scale, bias) += (sum gh0*xhat, sum gh0) from this rank's bn_sums. */
+int zf_bn_param_grads(void* stream, const double* bn_sums, int32_t F, float* g_scale, float* g_bias);
+/* Train-mode BatchNorm VJP into its inputs with (all-reduced) bn_sums and the global count:
+ * gx[:, D/2 + f] += dh_f for the x columns, gc[:, f - (D - D/2)] += dh_f for the conditions. */
+int zf_bn_backward_apply(void* stream, const zf_coupling* cp, int32_t D, int32_t C, const float* x_in,
+                         const float* c, const float* gh0, const double* bn_sums, double global_count, int64_t M,
+                         float* gx, float* gc);
+
+/* optax.nadamw / adamw (train.py:12-15,84-85) on flat buffers: scale_by_adam(b1,b2,eps,nesterov)
+ * -> add_decayed_weights(weight_decay) -> scale(-lr).  count = number of updates done so far. */
+int zf_nadamw_update(void* stream, int64_t n, float* params, const float* grads, float* mu, float* nu,
+                     int64_t count, float lr, float b1, float b2, float eps, float weight_decay, int32_t nesterov);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,15 @@ class ZfCoupling(C.Structure):
     ]
 
 
+class ZfCouplingGrads(C.Structure):
+    _fields_ = [
+        ("bn_scale", C.c_void_p),
+        ("bn_bias", C.c_void_p),
+        ("kernel", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+        ("bias", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+    ]
+
+
 class ZfOp(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -85,6 +94,25 @@ SIGNATURES = {
     "zf_chain_workspace_bytes": (C.c_size_t, [C.POINTER(ZfChain), C.c_int64]),
     "zf_chain_forward": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_chain_forward_acc": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_shift_bounds_minmax": (C.c_int, [C.c_void_p, C.POINTER(ZfShiftBounds), C.c_void_p, C.c_int64, C.c_int32,
+                                         C.c_void_p, C.c_void_p]),
+    "zf_shift_bounds_update": (C.c_int, [C.c_void_p, C.POINTER(ZfShiftBounds), C.c_int32, C.c_void_p]),
+    "zf_bn_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "zf_bn_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "zf_flow_loss_grad": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zf_coupling_backward_workspace_bytes": (C.c_size_t, [C.POINTER(ZfCoupling), C.c_int32, C.c_int32, C.c_int64]),
+    "zf_coupling_backward": (C.c_int, [C.c_void_p, C.POINTER(ZfCoupling), C.POINTER(ZfCouplingGrads), C.c_int32,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
+    "zf_bn_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "zf_bn_backward_apply": (C.c_int, [C.c_void_p, C.POINTER(ZfCoupling), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]),
+    "zf_nadamw_update": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
     "zf_chain_inverse": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_size_t]),
     "zf_flow_log_prob": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_int32, C.c_float, C.c_void_p,

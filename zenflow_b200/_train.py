@@ -1,0 +1,476 @@
+"""Host-side sequencing of the train-mode phases (C ABI: "train step phases").
+
+Two users:
+  * the bijector / Flow modules when called with ``train=True`` (``apply(..., train=True,
+    mutable=["batch_stats"])`` as in train.py:66-72 and the reference's tests);
+  * ``TrainEngine``: the whole ``step`` of train.py:80-86 (loss, gradients, optimiser update)
+    on flat parameter / gradient / moment buffers, optionally data-parallel: each rank holds a
+    shard of the batch and the small batch statistics (ShiftBounds min/max, BatchNorm moments
+    forward and backward) and the flat gradient are all-reduced with NCCL through
+    ``torch.distributed`` so the result equals the single-device step on the whole batch.
+
+No arithmetic happens in Python here: torch only owns the buffers, views and collectives.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._device import like_input, ptr, require_cuda, stream_ptr, to_device_f32
+
+BN_MOMENTUM = 0.99  # flax.linen.BatchNorm default
+
+
+# ---------------------------------------------------------------------------------------------
+# small helpers
+# ---------------------------------------------------------------------------------------------
+def _dist_world(group):
+    import torch.distributed as dist
+
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    return dist, dist.get_world_size(group)
+
+
+def _allreduce(t: torch.Tensor, group, op: str = "sum"):
+    dist, world = _dist_world(group)
+    if world == 1:
+        return
+    opmap = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}
+    dist.all_reduce(t, op=opmap[op], group=group)
+
+
+def _sb_struct(kinds, lo, hi, margin, xmin: torch.Tensor, xmax: torch.Tensor) -> _lib.ZfShiftBounds:
+    sb = _lib.ZfShiftBounds()
+    for i, k in enumerate(kinds):
+        sb.kind[i] = int(k)
+        sb.lo[i] = float(lo[i])
+        sb.hi[i] = float(hi[i])
+    sb.margin = float(margin)
+    sb.xmin = ptr(xmin)
+    sb.xmax = ptr(xmax)
+    return sb
+
+
+def _chain_struct(dim: int, cdim: int, ops: Sequence[_lib.ZfOp]):
+    arr = (_lib.ZfOp * max(len(ops), 1))(*ops)
+    ch = _lib.ZfChain()
+    ch.dim, ch.cdim, ch.n_ops = dim, cdim, len(ops)
+    ch.ops = C.cast(arr, C.POINTER(_lib.ZfOp))
+    return ch, arr
+
+
+def _op_sb(sb):
+    op = _lib.ZfOp()
+    op.kind = _lib.OP_SHIFT_BOUNDS
+    op.shift_bounds = C.pointer(sb)
+    return op
+
+
+def _op_cp(cp):
+    op = _lib.ZfOp()
+    op.kind = _lib.OP_COUPLING
+    op.coupling = C.pointer(cp)
+    return op
+
+
+def _op_roll(shift):
+    op = _lib.ZfOp()
+    op.kind = _lib.OP_ROLL
+    op.shift = int(shift)
+    return op
+
+
+def _coupling_struct(knots, hidden, scale, bias, mean, var, kernels, biases) -> _lib.ZfCoupling:
+    cp = _lib.ZfCoupling()
+    cp.knots = int(knots)
+    cp.n_hidden = len(hidden)
+    for i, w in enumerate(hidden):
+        cp.hidden[i] = int(w)
+    cp.bn_scale, cp.bn_bias, cp.bn_mean, cp.bn_var = ptr(scale), ptr(bias), ptr(mean), ptr(var)
+    for i, (k, b) in enumerate(zip(kernels, biases)):
+        cp.kernel[i] = ptr(k)
+        cp.bias[i] = ptr(b)
+    return cp
+
+
+def _run_chain_forward(ch, x, c, y, ld, acc: bool):
+    lib = _lib.load()
+    M = x.shape[0]
+    nbytes = int(lib.zf_chain_workspace_bytes(C.byref(ch), M))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    fn = lib.zf_chain_forward_acc if acc else lib.zf_chain_forward
+    _lib.check(fn(stream_ptr(), C.byref(ch), ptr(x), ptr(c), M, ptr(y), ptr(ld), ptr(ws), nbytes), "zf_chain_forward")
+
+
+def _minmax_update(sb, x, D, group=None):
+    lib = _lib.load()
+    mm = torch.empty(2 * D, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(2 * D, dtype=torch.int32, device=x.device)
+    _lib.check(lib.zf_shift_bounds_minmax(stream_ptr(), C.byref(sb), ptr(x), x.shape[0], D, ptr(mm), ptr(scratch)),
+               "zf_shift_bounds_minmax")
+    _allreduce(mm[:D], group, "min")
+    _allreduce(mm[D:], group, "max")
+    _lib.check(lib.zf_shift_bounds_update(stream_ptr(), C.byref(sb), D, ptr(mm)), "zf_shift_bounds_update")
+
+
+def _bn_batch_stats(x, c, D, Cdim, global_count, bmean, bvar, ra_mean, ra_var, group=None):
+    lib = _lib.load()
+    F = D - D // 2 + Cdim
+    sums = torch.empty(2 * F, dtype=torch.float64, device=x.device)
+    _lib.check(lib.zf_bn_moments(stream_ptr(), ptr(x), ptr(c), x.shape[0], D, Cdim, ptr(sums)), "zf_bn_moments")
+    _allreduce(sums, group, "sum")
+    _lib.check(lib.zf_bn_finalize(stream_ptr(), ptr(sums), float(global_count), F, BN_MOMENTUM, ptr(bmean), ptr(bvar),
+                                  ptr(ra_mean), ptr(ra_var)), "zf_bn_finalize")
+
+
+# ---------------------------------------------------------------------------------------------
+# module-level train-mode calls (apply(..., train=True, mutable=["batch_stats"]))
+# ---------------------------------------------------------------------------------------------
+def _leaf_out(t: torch.Tensor, template):
+    return t if isinstance(template, torch.Tensor) else t.cpu().numpy()
+
+
+def shift_bounds_train(mod, x):
+    """ShiftBounds.__call__(train=True), bijectors.py:164-208,250-260."""
+    dev = require_cuda()
+    xd = to_device_f32(x, dev)
+    D = xd.shape[1]
+    mod.setup()
+    kinds, lo, hi = mod._column_kinds(D)
+    scope = mod.scope
+    old_min = [None if k == _lib.BOUND_BOTH else scope.get("batch_stats", f"xmin_{i}") for i, k in enumerate(kinds)]
+    old_max = [None if k == _lib.BOUND_BOTH else scope.get("batch_stats", f"xmax_{i}") for i, k in enumerate(kinds)]
+    pack = lambda vals, fill: torch.tensor(
+        [fill if v is None else float(np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v).reshape(-1)[0]) for v in vals],
+        dtype=torch.float32, device=dev)
+    xmin, xmax = pack(old_min, 0.0), pack(old_max, 0.0)
+    sb = _sb_struct(kinds, lo, hi, mod.margin, xmin, xmax)
+    _minmax_update(sb, xd, D)
+    for i, k in enumerate(kinds):  # bijectors.py:258-260 (store unless initializing)
+        if k != _lib.BOUND_BOTH:
+            scope.put("batch_stats", f"xmin_{i}", _leaf_out(xmin[i:i + 1].clone(), old_min[i]))
+            scope.put("batch_stats", f"xmax_{i}", _leaf_out(xmax[i:i + 1].clone(), old_max[i]))
+    ch, keep = _chain_struct(D, 0, [_op_sb(sb)])
+    y = torch.empty_like(xd)
+    ld = torch.empty(xd.shape[0], dtype=torch.float32, device=dev)
+    _run_chain_forward(ch, xd, None, y, ld, acc=False)
+    return like_input(y, x), like_input(ld, x)
+
+
+def coupling_train_forward(mod, x, c):
+    """NeuralSplineCoupling.__call__(train=True): batch-moment BatchNorm (bijectors.py:342)."""
+    dev = require_cuda()
+    xd = to_device_f32(x, dev)
+    cd = None if c is None else to_device_f32(c, dev)
+    if cd is not None and cd.ndim == 1:
+        cd = cd.reshape(-1, 1)
+    M, D = xd.shape
+    Cdim = 0 if cd is None else cd.shape[1]
+    scope = mod.scope
+    scale, bias, mean, var, kernels, biases = mod._leaves(scope, D)
+    dl = lambda a: to_device_f32(a, dev)
+    ra_mean, ra_var = dl(mean).clone(), dl(var).clone()
+    F = D - D // 2 + Cdim
+    bmean = torch.empty(F, dtype=torch.float32, device=dev)
+    bvar = torch.empty(F, dtype=torch.float32, device=dev)
+    _bn_batch_stats(xd, cd, D, Cdim, M, bmean, bvar, ra_mean, ra_var)
+    bn = scope.child("BatchNorm_0")
+    bn.put("batch_stats", "mean", _leaf_out(ra_mean, mean))
+    bn.put("batch_stats", "var", _leaf_out(ra_var, var))
+    keep = [dl(scale), dl(bias)] + [dl(k) for k in kernels] + [dl(b) for b in biases]
+    nl = len(kernels)
+    cp = _coupling_struct(mod.knots, mod.layers, keep[0], keep[1], bmean, bvar, keep[2:2 + nl], keep[2 + nl:])
+    ch, arr = _chain_struct(D, Cdim, [_op_cp(cp)])
+    y = torch.empty_like(xd)
+    ld = torch.empty(M, dtype=torch.float32, device=dev)
+    _run_chain_forward(ch, xd, cd, y, ld, acc=False)
+    return like_input(y, x), like_input(ld, x)
+
+
+def flow_train_log_prob(flow, x, c):
+    """Flow.__call__(train=True), flow.py:45-47 with the bijector in train mode."""
+    lib = _lib.load()
+    dev = require_cuda()
+    with flow.bijector._bound(flow.scope.child("bijector")):
+        z, ld = flow.bijector(x, c, True)
+    zd, ldd = to_device_f32(z, dev), to_device_f32(ld, dev)
+    M, D = zd.shape
+    kind, peak = flow.latent._native()
+    lp = torch.empty(M, dtype=torch.float32, device=dev)
+    gz = torch.empty_like(zd)
+    glp = torch.empty(M, dtype=torch.float32, device=dev)
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    _lib.check(lib.zf_flow_loss_grad(stream_ptr(), kind, peak, ptr(zd), ptr(ldd), M, D, float(M), ptr(lp), ptr(gz),
+                                     ptr(glp), ptr(acc)), "zf_flow_loss_grad")
+    return like_input(lp, x)
+
+
+# ---------------------------------------------------------------------------------------------
+# the train step engine
+# ---------------------------------------------------------------------------------------------
+class TrainEngine:
+    """``step`` of train.py:80-86 on device-resident flat buffers.
+
+    flow.bijector must be a Chain (or a single bijector) made of an optional leading ShiftBounds
+    followed by NeuralSplineCoupling / Roll bijectors, which is what the reference builds
+    (bijectors.py:374-423).  ``group``: a torch.distributed process group for data-parallel
+    training (None: the default group if initialised, else single device).
+    """
+
+    def __init__(self, flow, variables, cdim: int, *, lr: float = 1e-3, b1: float = 0.9, b2: float = 0.999,
+                 eps: float = 1e-8, weight_decay: float = 1e-4, nesterov: bool = True, group=None,
+                 micro_batch: int = 1 << 18):
+        from .bijectors import Chain, NeuralSplineCoupling, Roll, ShiftBounds
+
+        self.flow = flow
+        self.dev = require_cuda()
+        self.group = group
+        self.hp = dict(lr=lr, b1=b1, b2=b2, eps=eps, weight_decay=weight_decay, nesterov=int(bool(nesterov)))
+        self.micro_batch = int(micro_batch)
+        self.count = 0
+        bij = flow.bijector
+        mods = list(bij) if isinstance(bij, Chain) else [bij]
+        names = [f"bijectors_{i}" for i in range(len(mods))] if isinstance(bij, Chain) else [None]
+        if flow.latent.dim is None:
+            raise ValueError("initialise the flow before training (latent.dim is not set)")
+        self.D = D = int(flow.latent.dim)
+        self.C = int(cdim)
+        d = D // 2
+        self.F = F = D - d + self.C
+
+        def sub(tree, col, name):
+            t = variables.get(col, {}).get("bijector", {})
+            return t if name is None else t.get(name, {})
+
+        # ---- groups: a non-Roll bijector and the Rolls that follow it
+        self.groups: List[dict] = []
+        for mod, name in zip(mods, names):
+            if isinstance(mod, Roll):
+                if not self.groups:
+                    raise NotImplementedError("training a chain that starts with Roll is not supported")
+                self.groups[-1]["rolls"].append(int(mod.shift))
+            elif isinstance(mod, ShiftBounds):
+                if self.groups:
+                    raise NotImplementedError("ShiftBounds after another bijector is not supported in training")
+                self.groups.append(dict(kind="sb", mod=mod, name=name, rolls=[]))
+            elif isinstance(mod, NeuralSplineCoupling):
+                self.groups.append(dict(kind="cp", mod=mod, name=name, rolls=[]))
+            else:
+                raise NotImplementedError(f"cannot train through {type(mod).__name__}")
+
+        # ---- flat parameter buffer with one view per FLAX leaf
+        leaves: List[Tuple[dict, str, str, tuple]] = []
+        total = 0
+        for g in self.groups:
+            if g["kind"] != "cp":
+                continue
+            p = sub(variables, "params", g["name"])
+            g["leaf_names"] = [("BatchNorm_0", "scale"), ("BatchNorm_0", "bias")]
+            for j in range(len(g["mod"].layers) + 1):
+                g["leaf_names"] += [(f"Dense_{j}", "kernel"), (f"Dense_{j}", "bias")]
+            g["src"] = p
+            for mname, lname in g["leaf_names"]:
+                total += int(np.prod(p[mname][lname].shape))
+        self.n_params = total
+        self.P = torch.empty(total, dtype=torch.float32, device=self.dev)
+        self.G = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.mu = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.nu = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        off = 0
+        for g in self.groups:
+            if g["kind"] != "cp":
+                continue
+            g["pv"], g["gv"] = {}, {}
+            for mname, lname in g["leaf_names"]:
+                src = g["src"][mname][lname]
+                n = int(np.prod(src.shape))
+                pv = self.P[off:off + n].view(tuple(src.shape))
+                pv.copy_(to_device_f32(src, self.dev))
+                g["pv"][(mname, lname)] = pv
+                g["gv"][(mname, lname)] = self.G[off:off + n].view(tuple(src.shape))
+                off += n
+            st = sub(variables, "batch_stats", g["name"])["BatchNorm_0"]
+            g["ra_mean"] = to_device_f32(st["mean"], self.dev).clone()
+            g["ra_var"] = to_device_f32(st["var"], self.dev).clone()
+            g["bmean"] = torch.zeros(F, dtype=torch.float32, device=self.dev)
+            g["bvar"] = torch.ones(F, dtype=torch.float32, device=self.dev)
+            nl = len(g["mod"].layers) + 1
+            ks = [g["pv"][(f"Dense_{j}", "kernel")] for j in range(nl)]
+            bs = [g["pv"][(f"Dense_{j}", "bias")] for j in range(nl)]
+            # train forward/backward read the BATCH statistics
+            g["cp"] = _coupling_struct(g["mod"].knots, g["mod"].layers, g["pv"][("BatchNorm_0", "scale")],
+                                       g["pv"][("BatchNorm_0", "bias")], g["bmean"], g["bvar"], ks, bs)
+            gr = _lib.ZfCouplingGrads()
+            gr.bn_scale = ptr(g["gv"][("BatchNorm_0", "scale")])
+            gr.bn_bias = ptr(g["gv"][("BatchNorm_0", "bias")])
+            for j in range(nl):
+                gr.kernel[j] = ptr(g["gv"][(f"Dense_{j}", "kernel")])
+                gr.bias[j] = ptr(g["gv"][(f"Dense_{j}", "bias")])
+            g["gr"] = gr
+            ops = [_op_cp(g["cp"])] + [_op_roll(s) for s in g["rolls"]]
+            g["chain"], g["_keep"] = _chain_struct(D, self.C, ops)
+            g["rot"] = sum(g["rolls"])
+            g["bn_sums"] = torch.zeros(2 * F, dtype=torch.float64, device=self.dev)
+        for g in self.groups:
+            if g["kind"] != "sb":
+                continue
+            mod = g["mod"]
+            mod.setup()
+            kinds, lo, hi = mod._column_kinds(D)
+            st = sub(variables, "batch_stats", g["name"])
+            get = lambda key, i, fill: (fill if kinds[i] == _lib.BOUND_BOTH else
+                                        float(np.asarray(st[f"{key}_{i}"].cpu() if isinstance(st[f"{key}_{i}"], torch.Tensor)
+                                                         else st[f"{key}_{i}"]).reshape(-1)[0]))
+            g["xmin"] = torch.tensor([get("xmin", i, 0.0) for i in range(D)], dtype=torch.float32, device=self.dev)
+            g["xmax"] = torch.tensor([get("xmax", i, 0.0) for i in range(D)], dtype=torch.float32, device=self.dev)
+            g["kinds"] = kinds
+            g["sb"] = _sb_struct(kinds, lo, hi, mod.margin, g["xmin"], g["xmax"])
+            ops = [_op_sb(g["sb"])] + [_op_roll(s) for s in g["rolls"]]
+            g["chain"], g["_keep"] = _chain_struct(D, self.C, ops)
+        self._bufs: Dict[int, dict] = {}
+        self.lp_sum = torch.zeros(1, dtype=torch.float64, device=self.dev)
+
+    # -- buffers sized for a local batch ------------------------------------------------------
+    def _buffers(self, M: int) -> dict:
+        b = self._bufs.get(M)
+        if b is None:
+            lib = _lib.load()
+            dev, D, F = self.dev, self.D, self.F
+            f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            b = dict(states=[f32(M, D) for _ in self.groups], ld=f32(M), glp=f32(M), ga=f32(M, D), gb=f32(M, D),
+                     gh0=f32(M, F), gc=(torch.zeros(M, self.C, dtype=torch.float32, device=dev) if self.C else None))
+            mb = min(self.micro_batch, M)
+            need = 16
+            for g in self.groups:
+                if g["kind"] == "cp":
+                    need = max(need, int(lib.zf_coupling_backward_workspace_bytes(C.byref(g["cp"]), D, self.C, mb)))
+            b["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            b["mb"] = mb
+            if len(self._bufs) >= 2:  # full and ragged minibatch shapes
+                self._bufs.pop(next(iter(self._bufs)))
+            self._bufs[M] = b
+        return b
+
+    # -- one optimiser step -------------------------------------------------------------------
+    def step(self, x, c=None, *, global_count: Optional[int] = None, update: bool = True, want_gc: bool = False):
+        """Loss, gradients and (if ``update``) the optimiser update for the local shard (x, c).
+        Returns the device scalar sum of log-probs over the local shard (loss = -sum/global_count)."""
+        lib = _lib.load()
+        st = stream_ptr()
+        x = to_device_f32(x, self.dev)
+        c = None if c is None else to_device_f32(c, self.dev)
+        if c is not None and c.ndim == 1:
+            c = c.reshape(-1, 1)
+        M = x.shape[0]
+        D, Cd, F = self.D, self.C, self.F
+        if global_count is None:
+            dist, world = _dist_world(self.group)
+            if world > 1:
+                cnt = torch.tensor([M], dtype=torch.int64, device=self.dev)
+                _allreduce(cnt, self.group, "sum")
+                global_count = int(cnt.item())
+            else:
+                global_count = M
+        b = self._buffers(M)
+        b["ld"].zero_()
+        self.G.zero_()
+        self.lp_sum.zero_()
+        if b["gc"] is not None:
+            b["gc"].zero_()
+
+        # ---- forward, one bijector group at a time (batch statistics couple the samples)
+        cur = x
+        for gi, g in enumerate(self.groups):
+            nxt = b["states"][gi]
+            if g["kind"] == "sb":
+                _minmax_update(g["sb"], cur, D, self.group)
+            else:
+                _bn_batch_stats(cur, c, D, Cd, global_count, g["bmean"], g["bvar"], g["ra_mean"], g["ra_var"], self.group)
+            g["x_in"] = cur
+            _run_chain_forward(g["chain"], cur, c, nxt, b["ld"], acc=True)
+            cur = nxt
+
+        # ---- loss and the cotangents of z and of the log-dets
+        kind, peak = self.flow.latent._native()
+        gy, gx = b["ga"], b["gb"]
+        _lib.check(lib.zf_flow_loss_grad(st, kind, peak, ptr(cur), ptr(b["ld"]), M, D, float(global_count), None, ptr(gy),
+                                         ptr(b["glp"]), ptr(self.lp_sum)), "zf_flow_loss_grad")
+
+        # ---- backward
+        for g in reversed(self.groups):
+            if g["kind"] != "cp":
+                break  # a leading ShiftBounds has no parameters and x needs no cotangent
+            _lib.check(lib.zf_coupling_backward(st, C.byref(g["cp"]), C.byref(g["gr"]), D, Cd, ptr(g["x_in"]), ptr(c),
+                                                ptr(gy), g["rot"], ptr(b["glp"]), M, ptr(gx), ptr(b["gh0"]),
+                                                ptr(g["bn_sums"]), ptr(b["ws"]), b["ws"].numel(), b["mb"]),
+                       "zf_coupling_backward")
+            _lib.check(lib.zf_bn_param_grads(st, ptr(g["bn_sums"]), F, g["gr"].bn_scale, g["gr"].bn_bias), "zf_bn_param_grads")
+            _allreduce(g["bn_sums"], self.group, "sum")
+            _lib.check(lib.zf_bn_backward_apply(st, C.byref(g["cp"]), D, Cd, ptr(g["x_in"]), ptr(c), ptr(b["gh0"]),
+                                                ptr(g["bn_sums"]), float(global_count), M, ptr(gx), ptr(b["gc"])),
+                       "zf_bn_backward_apply")
+            gy, gx = gx, gy
+        self._last_gc = b["gc"]
+
+        _allreduce(self.G, self.group, "sum")
+        if update:
+            h = self.hp
+            _lib.check(lib.zf_nadamw_update(st, self.n_params, ptr(self.P), ptr(self.G), ptr(self.mu), ptr(self.nu),
+                                            self.count, h["lr"], h["b1"], h["b2"], h["eps"], h["weight_decay"],
+                                            h["nesterov"]), "zf_nadamw_update")
+            self.count += 1
+        return self.lp_sum
+
+    # -- FLAX-shaped views of the current state -------------------------------------------------
+    def variables(self, as_numpy: bool = False) -> Dict[str, dict]:
+        conv = (lambda t: t.detach().cpu().numpy().copy()) if as_numpy else (lambda t: t)
+        params: Dict[str, dict] = {}
+        stats: Dict[str, dict] = {}
+        for g in self.groups:
+            if g["kind"] == "cp":
+                p: Dict[str, dict] = {}
+                for (mname, lname), v in g["pv"].items():
+                    p.setdefault(mname, {})[lname] = conv(v)
+                s = {"BatchNorm_0": {"mean": conv(g["ra_mean"]), "var": conv(g["ra_var"])}}
+            else:
+                p = None
+                s = {}
+                for i, k in enumerate(g["kinds"]):
+                    if k != _lib.BOUND_BOTH:
+                        s[f"xmin_{i}"] = conv(g["xmin"][i:i + 1])
+                        s[f"xmax_{i}"] = conv(g["xmax"][i:i + 1])
+            if g["name"] is None:
+                if p is not None:
+                    params = p
+                stats = s
+            else:
+                if p is not None:
+                    params[g["name"]] = p
+                stats[g["name"]] = s
+        out = {"batch_stats": {"bijector": stats}}
+        if params:
+            out["params"] = {"bijector": params}
+        return out
+
+    def gradients(self) -> Dict[str, dict]:
+        """The last step's gradient pytree (views of the flat gradient buffer)."""
+        out: Dict[str, dict] = {}
+        for g in self.groups:
+            if g["kind"] != "cp":
+                continue
+            p: Dict[str, dict] = {}
+            for (mname, lname), v in g["gv"].items():
+                p.setdefault(mname, {})[lname] = v
+            if g["name"] is None:
+                return {"bijector": p}
+            out[g["name"]] = p
+        return {"bijector": out}
+
+    def snapshot(self):
+        """Detached copy of everything ``variables()`` exposes (for best-epoch bookkeeping)."""
+        return torch.utils._pytree.tree_map(lambda t: t.clone(), self.variables())

@@ -149,6 +149,7 @@ struct ChainArgs {
     int rot_total;      // rotation after the last step
     int act_rows;
     int mode;
+    int acc_log_det;    // log_det[m] += instead of =
     LatentConst lc;
 };
 
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
                     a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * TM + m];
                 }
             }
-            if (!INVERSE && a.log_det && tid < nm) a.log_det[m0 + tid] = ld_acc;
+            if (!INVERSE && a.log_det && tid < nm) a.log_det[m0 + tid] = a.acc_log_det ? a.log_det[m0 + tid] + ld_acc : ld_acc;
         }
         __syncthreads();
     }
@@ -527,7 +528,7 @@ static LatentConst make_latent(int kind, float peakness) {
 
 static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int latent_kind, float peakness,
                      const float* x, const float* c, long long M, float* y, float* log_det, float* lp,
-                     void* workspace, size_t workspace_bytes) {
+                     void* workspace, size_t workspace_bytes, int acc_log_det = 0) {
     Plan plan;
     if (int rc = build_plan(chain, plan)) return rc;
     ZF_REQUIRE(M >= 0, "M must be >= 0");
@@ -560,6 +561,7 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     a.rot_total = plan.rot_total;
     a.act_rows = plan.act_rows;
     a.mode = mode;
+    a.acc_log_det = acc_log_det;
     a.lc = make_latent(latent_kind, peakness);
 
     const size_t smem = ((size_t)(a.D + a.C) * TM + 2 * (size_t)a.act_rows * TM + 2 * KC * NCOL) * sizeof(float);
@@ -595,6 +597,12 @@ extern "C" int zf_chain_forward(void* stream, const zf_chain* chain, const float
                                 float* y, float* log_det, void* workspace, size_t workspace_bytes) {
     return zf::run_chain((cudaStream_t)stream, chain, zf::kModeForward, 0, 0.f, x, c, (long long)M, y, log_det,
                          nullptr, workspace, workspace_bytes);
+}
+
+extern "C" int zf_chain_forward_acc(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                                    float* y, float* log_det, void* workspace, size_t workspace_bytes) {
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeForward, 0, 0.f, x, c, (long long)M, y, log_det,
+                         nullptr, workspace, workspace_bytes, 1);
 }
 
 extern "C" int zf_chain_inverse(void* stream, const zf_chain* chain, const float* z, const float* c, int64_t M,

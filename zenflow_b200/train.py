@@ -1,0 +1,154 @@
+"""Train flow — host-side mirror of zenflow/train.py.
+
+Same signature and bookkeeping as the reference's ``train`` (per-epoch permutation,
+minibatch ``step``, best-epoch tracking, non-finite abort, patience-window early stop);
+the jitted ``step`` (jax.grad of ``-mean(log_prob)`` + optax update, train.py:64-86) is the
+native train step (``TrainEngine``).  The optimiser is described by a small config object
+instead of an optax GradientTransformation: ``nadamw`` (the reference's default when optax
+has it, train.py:12-15) or ``adamw``, same hyper-parameter names and defaults as optax.
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ._device import require_cuda, to_device_f32
+from ._train import TrainEngine
+from .flow import Flow
+
+__all__ = ["train", "nadamw", "adamw", "Optimizer", "DEFAULT_OPTIMIZER"]
+
+
+@dataclass(frozen=True)
+class Optimizer:
+    """optax.adamw / optax.nadamw hyper-parameters (optax defaults)."""
+
+    learning_rate: float = 1e-3
+    b1: float = 0.9
+    b2: float = 0.999
+    eps: float = 1e-8
+    weight_decay: float = 1e-4
+    nesterov: bool = True
+
+
+def nadamw(learning_rate: float = 1e-3, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8,
+           weight_decay: float = 1e-4) -> Optimizer:
+    return Optimizer(learning_rate, b1, b2, eps, weight_decay, True)
+
+
+def adamw(learning_rate: float = 1e-3, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8,
+          weight_decay: float = 1e-4) -> Optimizer:
+    return Optimizer(learning_rate, b1, b2, eps, weight_decay, False)
+
+
+DEFAULT_OPTIMIZER = nadamw
+
+
+def _cdim(C) -> int:
+    if C is None:
+        return 0
+    return 1 if C.ndim == 1 else int(C.shape[1])
+
+
+def train(
+    flow: Flow,
+    X_train,
+    X_test,
+    C_train=None,
+    C_test=None,
+    *,
+    epochs: int = 1000,
+    batch_size: int = 1024,
+    optimizer: Optimizer = DEFAULT_OPTIMIZER(learning_rate=1e-3),
+    patience: float = 0.05,
+    warmup: float = 0.2,
+    seed: int = 0,
+    progress: bool = True,
+    initial_variables=None,
+    group=None,
+) -> Tuple[dict, int, List[float], List[float]]:
+    """Trains the normalizing flow on the provided inputs (train.py:18-138).
+
+    Returns (best_variables, best_epoch, loss_train, loss_test); the variables are a FLAX-shaped
+    pytree of device tensors.  ``group``: optional torch.distributed group for data-parallel
+    training (every rank passes its own shard of X_train / C_train).
+    """
+    if warmup < 1:
+        warmup = warmup * epochs
+    warmup = int(warmup)
+    if patience < 1:
+        patience = patience * epochs
+    patience = int(patience)
+
+    dev = require_cuda()
+    X_train = to_device_f32(X_train, dev)  # jax.device_put, train.py:43-48
+    X_test = to_device_f32(X_test, dev)
+    if C_train is not None:
+        C_train = to_device_f32(C_train, dev)
+    if C_test is not None:
+        C_test = to_device_f32(C_test, dev)
+
+    if initial_variables is None:
+        variables = flow.init(seed, X_train[:1].cpu().numpy(), None if C_train is None else C_train[:1].cpu().numpy())
+    else:
+        variables = initial_variables
+        flow.latent._latch_dim(X_train.shape[1])
+    if "params" not in variables or "batch_stats" not in variables:
+        raise KeyError("variables must hold both 'params' and 'batch_stats' (train.py:59-60)")
+
+    engine = TrainEngine(flow, variables, _cdim(C_train), lr=optimizer.learning_rate, b1=optimizer.b1, b2=optimizer.b2,
+                         eps=optimizer.eps, weight_decay=optimizer.weight_decay, nesterov=optimizer.nesterov, group=group)
+
+    def metric_fn(vs, x, c) -> float:  # train.py:75-78
+        lp = flow.apply(vs, x, c)
+        return float(-(lp.double().sum() / lp.shape[0]).item())
+
+    loss_train: List[float] = []
+    loss_test: List[float] = []
+    if progress:
+        try:
+            from tqdm.auto import tqdm as track
+        except ModuleNotFoundError:  # pragma: no cover
+            from rich.progress import track
+        loop = track(range(epochs))
+    else:
+        loop = range(epochs)
+
+    gen = torch.Generator(device=dev)
+    best_epoch = 0
+    best_variables = engine.snapshot()
+    N = X_train.shape[0]
+    for epoch in loop:
+        gen.manual_seed((int(seed) * 1_000_003 + epoch) & 0x7FFFFFFFFFFFFFFF)  # fold_in(iter_key, epoch)
+        perm = torch.randperm(N, generator=gen, device=dev)
+        X_perm = X_train[perm]
+        C_perm = C_train[perm] if C_train is not None else None
+
+        X = C = None
+        for batch_idx in range(0, N, batch_size):
+            X = X_perm[batch_idx:batch_idx + batch_size]
+            C = C_perm[batch_idx:batch_idx + batch_size] if C_perm is not None else None
+            engine.step(X, C)
+
+        variables = engine.variables()
+        loss_train.append(metric_fn(variables, X, C))
+        loss_test.append(metric_fn(variables, X_test, C_test))
+
+        if not np.isfinite(loss_train[-1]):
+            msg = f"epoch {epoch}: loss[train] not finite, abort training"
+            warnings.warn(msg, RuntimeWarning)
+            break
+
+        if loss_test[-1] <= loss_test[best_epoch]:
+            best_epoch = epoch
+            best_variables = engine.snapshot()
+
+        if epoch >= warmup and epoch >= 2 * patience and epoch % patience == 0:
+            if not np.min(loss_test[-patience:]) < np.min(loss_test[-2 * patience:-patience]):
+                break
+
+    return best_variables, best_epoch, loss_train, loss_test

@@ -53,8 +53,10 @@ def assert_fp32_parity(got, truth64, oracle32, what, rtol=1e-5, atol=2e-5):
     np.testing.assert_array_equal(np.isfinite(got) & (np.abs(got) < 1e30), fin, err_msg=what)
     err = np.abs(got - truth64)[fin]
     ref = np.abs(np.asarray(oracle32, np.float64) - truth64)[fin]
-    ratio = err / (rtol * np.abs(truth64[fin]) + atol)
-    assert np.quantile(ratio, 0.999) <= 1.0, f"{what}: 99.9% quantile of err/tol = {np.quantile(ratio, 0.999):.2f}"
+    tol = rtol * np.abs(truth64[fin]) + atol
+    q_got, q_ref = np.quantile(err / tol, 0.999), np.quantile(ref / tol, 0.999)
+    # within tolerance wherever the reference's own float32 arithmetic is
+    assert q_got <= max(1.0, 1.5 * q_ref), f"{what}: 99.9% quantile of err/tol = {q_got:.2f} (fp32 oracle {q_ref:.2f})"
     assert err.max() <= 2.0 * ref.max() + 1e-5, f"{what}: max err {err.max():.3e} vs fp32 oracle {ref.max():.3e}"
 
 

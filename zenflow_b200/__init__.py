@@ -3,13 +3,6 @@ behind the reference's FLAX-module API (``Flow``, the bijectors, the latent dist
 ``train``).  CUDA only: there is no CPU fallback."""
 
 from .flow import Flow
+from .train import train  # shadows the submodule attribute, exactly as zenflow/__init__.py does
 
 __all__ = ("Flow", "train")
-
-
-def __getattr__(name):
-    if name == "train":
-        from .train import train
-
-        return train
-    raise AttributeError(name)

@@ -16,7 +16,7 @@ for (D, C, K, layers, ncoup, roll, M) in [(3, 0, 5, (40,), None, 1, 515), (4, 2,
     lp64, _ = zo.flow_log_prob(ops, to64(v), x.astype(np.float64), None if c is None else c.astype(np.float64), train=True)
     flow = Flow(product_chain(ops)); flow.latent._latch_dim(D)
     fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
-    eng = TrainEngine(flow, fv, C, micro_batch=128)
+    eng = TrainEngine(flow, fv, D, C, micro_batch=128)
     lp_sum = eng.step(x, c, update=False)
     print("case", D, C, K, "loss gpu", -lp_sum.item()/M, "oracle", -lp64.mean())
     b = eng._bufs[M]

@@ -106,7 +106,7 @@ def test_train_step_gradients_match_autograd(case):
                                                       None if c is None else c.astype(np.float64))
     flow = Flow(product_chain(ops))
     flow.latent._latch_dim(D)
-    eng = TrainEngine(flow, _flow_vars(v), C, micro_batch=128)  # several micro-batches incl. a ragged one
+    eng = TrainEngine(flow, _flow_vars(v), D, C, micro_batch=128)  # several micro-batches incl. a ragged one
     lp_sum = eng.step(x, c, update=False)
     loss = -float(lp_sum.item()) / M
     assert abs(loss - loss64) <= 1e-5 * abs(loss64) + 1e-5

@@ -222,7 +222,7 @@ class TrainEngine:
     training (None: the default group if initialised, else single device).
     """
 
-    def __init__(self, flow, variables, cdim: int, *, lr: float = 1e-3, b1: float = 0.9, b2: float = 0.999,
+    def __init__(self, flow, variables, dim: int, cdim: int, *, lr: float = 1e-3, b1: float = 0.9, b2: float = 0.999,
                  eps: float = 1e-8, weight_decay: float = 1e-4, nesterov: bool = True, group=None,
                  micro_batch: int = 1 << 18):
         from .bijectors import Chain, NeuralSplineCoupling, Roll, ShiftBounds
@@ -236,9 +236,10 @@ class TrainEngine:
         bij = flow.bijector
         mods = list(bij) if isinstance(bij, Chain) else [bij]
         names = [f"bijectors_{i}" for i in range(len(mods))] if isinstance(bij, Chain) else [None]
-        if flow.latent.dim is None:
-            raise ValueError("initialise the flow before training (latent.dim is not set)")
-        self.D = D = int(flow.latent.dim)
+        # D comes from the data: the default latent instance is shared between Flow objects and
+        # latches its dim only once (flow.py:20, distributions.py:31-32)
+        self.D = D = int(dim)
+        flow.latent._latch_dim(D)
         self.C = int(cdim)
         d = D // 2
         self.F = F = D - d + self.C

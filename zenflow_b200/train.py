@@ -100,7 +100,7 @@ def train(
     if "params" not in variables or "batch_stats" not in variables:
         raise KeyError("variables must hold both 'params' and 'batch_stats' (train.py:59-60)")
 
-    engine = TrainEngine(flow, variables, _cdim(C_train), lr=optimizer.learning_rate, b1=optimizer.b1, b2=optimizer.b2,
+    engine = TrainEngine(flow, variables, int(X_train.shape[1]), _cdim(C_train), lr=optimizer.learning_rate, b1=optimizer.b1, b2=optimizer.b2,
                          eps=optimizer.eps, weight_decay=optimizer.weight_decay, nesterov=optimizer.nesterov, group=group)
 
     def metric_fn(vs, x, c) -> float:  # train.py:75-78

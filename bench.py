@@ -351,6 +351,8 @@ def run_gpu(args):
             "events": Ms, "bytes_per_event": 4 * (d * P + 2 * d + 1), "peak_source": pk["source"]}
         del theta, xin
 
+    train_info = bench_train(args, world, rank, dev) if args.train_batch else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -391,9 +393,69 @@ def run_gpu(args):
                                           f"(JAX not installable here), {cores} forked workers x 1 BLAS thread, "
                                           f"{cpu_sec:.1f} s"}
     line.update(extras)
+    if train_info:
+        line["train_step"] = train_info
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_train(args, world, rank, dev):
+    """Extra measurement (not the headline value): the data-parallel train step of train.py:80-86
+    on BASELINE.json configs[4]'s shape (16-D conditional flow, C=4, K=32, 8 couplings, Roll(2)),
+    global batch --train-batch split evenly over the ranks (strong scaling), BatchNorm/ShiftBounds
+    statistics and the flat gradient all-reduced with NCCL.  Samples/s = global batch / step time."""
+    import torch
+    import torch.distributed as dist
+
+    from zenflow_b200 import Flow
+    from zenflow_b200 import bijectors as bi
+    from zenflow_b200._train import TrainEngine
+
+    D, C, K, n_c = 16, 4, 32, 8
+    mods = [bi.ShiftBounds()]
+    for i in range(n_c - 1):
+        mods += [bi.NeuralSplineCoupling(knots=K, layers=(128, 128)), bi.Roll(2)]
+    mods.append(bi.NeuralSplineCoupling(knots=K, layers=(128, 128)))
+    flow = Flow(bi.Chain(mods))
+    variables = flow.init(0, np.zeros((1, D), np.float32), np.zeros((1, C), np.float32))
+    local = args.train_batch // world
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    x = torch.rand(local, D, device=dev, generator=g)
+    c = torch.rand(local, C, device=dev, generator=g)
+    eng = TrainEngine(flow, variables, D, C, group=None)
+    steps, warm = args.train_steps, 2
+    for _ in range(warm):
+        eng.step(x, c, global_count=local * world)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        lp_sum = eng.step(x, c, global_count=local * world)
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    t = torch.tensor([ms, float(lp_sum.item())], device=dev, dtype=torch.float64)
+    if world > 1:
+        tm = t[:1].clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ls = t[1:].clone()
+        dist.all_reduce(ls, op=dist.ReduceOp.SUM)
+        ms, lpsum = float(tm.item()), float(ls.item())
+    else:
+        lpsum = float(t[1].item())
+    flops_fwd = 2 * (12 * 128 + 128 * 128 + 128 * 760) * n_c
+    return {"samples_per_s": local * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "global_batch": local * world,
+            "steps": steps, "warmup": warm, "n_gpus": world, "scaling": "strong", "loss": -lpsum / (local * world),
+            "config": {"workload": "cond16_train", "D": D, "C": C, "K": K, "couplings": n_c, "layers": [128, 128],
+                       "optimizer": "nadamw(1e-3)", "collectives": "NCCL all-reduce: ShiftBounds min/max, BatchNorm moments fwd+bwd, flat gradient"},
+            "tflops_algorithmic": 3 * flops_fwd * local * world / (ms / steps * 1e-3) / 1e12,
+            "note": "BASELINE configs[4] names 64M/step; this extra uses --train-batch events/step (fp32 FFMA GEMMs this round)"}
 
 
 def main():
@@ -405,6 +467,8 @@ def main():
     ap.add_argument("--workload", default="two_moons_conditional", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override events per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--train-batch", type=int, default=1 << 20, help="global batch of the extra train-step measurement (0: skip)")
+    ap.add_argument("--train-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

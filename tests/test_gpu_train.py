@@ -83,11 +83,11 @@ def test_flow_train_mode_forward(D, C, K, layers, M):
 
 
 GRAD_CASES = [
-    # D, C, K, layers, n_couplings, roll, M
-    (4, 2, 8, (16, 16), None, 1, 300),
-    (2, 1, 16, (128, 128), None, 1, 700),
-    (16, 4, 32, (128, 128), 3, 2, 260),
-    (3, 0, 5, (40,), None, 1, 515),
+    # D, C, K, layers, n_couplings, roll, M, weight scale (1.0 = the FLAX default initialiser's variance)
+    (4, 2, 8, (16, 16), None, 1, 300, 1.5),
+    (2, 1, 16, (128, 128), None, 1, 700, 1.5),
+    (16, 4, 32, (128, 128), 3, 2, 260, 1.0),
+    (3, 0, 5, (40,), None, 1, 515, 1.5),
 ]
 
 
@@ -96,12 +96,12 @@ def test_train_step_gradients_match_autograd(case):
     from zenflow_b200 import Flow
     from zenflow_b200._train import TrainEngine
 
-    D, C, K, layers, ncoup, roll, M = case
+    D, C, K, layers, ncoup, roll, M, wscale = case
     rng = np.random.default_rng(M)
     ops = zo.make_chain(D, K, layers, n_couplings=ncoup, roll_shift=roll)
     x = rng.normal(0.3, 1.0, (M, D)).astype(np.float32)
     c = rng.uniform(0, 1, (M, C)).astype(np.float32) if C else None
-    v = zo.init_variables(ops, D, C, 2, weight_scale=1.5, randomize_bn=True)
+    v = zo.init_variables(ops, D, C, 2, weight_scale=wscale, randomize_bn=True)
     loss64, g64, st64, gc64, lp64 = to.loss_and_grads(ops, to64(v), x.astype(np.float64),
                                                       None if c is None else c.astype(np.float64))
     flow = Flow(product_chain(ops))
@@ -167,7 +167,7 @@ def test_train_loop_two_moons():
     X = np.column_stack([np.where(lab == 0, np.cos(t), 1 - np.cos(t)), np.where(lab == 0, np.sin(t), 0.5 - np.sin(t))])
     X = (X + 0.1 * rng.standard_normal(X.shape)).astype(np.float32)
     flow = Flow(rolling_spline_coupling(2))
-    best, best_epoch, ltrain, ltest = train(flow, X[:3000], X[3000:], epochs=12, batch_size=500, progress=False)
+    best, best_epoch, ltrain, ltest = train(flow, X[:3000], X[3000:], epochs=12, batch_size=500, patience=4, progress=False)
     assert len(ltrain) == len(ltest) == 12 and np.isfinite(ltrain).all()
     assert ltest[-1] < ltest[0] - 0.3 and ltest[-1] < 2.0
     assert 0 <= best_epoch < 12 and set(best) == {"params", "batch_stats"}
@@ -177,7 +177,7 @@ def test_train_loop_two_moons():
     C = lab.astype(np.float32)
     flow = Flow(rolling_spline_coupling(2))
     best, best_epoch, ltrain, ltest = train(flow, X[:3001], X[3001:], C[:3001], C[3001:], epochs=4, batch_size=512,
-                                            progress=False)
+                                            patience=2, progress=False)
     assert np.isfinite(ltrain).all() and ltest[-1] < ltest[0]
 
 

@@ -122,6 +122,10 @@ int zf_rqs_inverse(void* stream, const float* theta, const float* y, int64_t M, 
  * mismatches: DEVICE array of 3 uint64; all must be 0. */
 int zf_selftest_exact_math(void* stream, uint64_t* mismatches);
 
+/* Self-test of the tcgen05 building blocks (3xTF32 split GEMM, A in tensor memory, B image in
+ * shared memory): out (128, N) = A (128, K) * B (N, K)^T, N % 16 == 0 <= 128, K % 8 == 0 <= 128. */
+int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out);
+
 /* ---- whole-chain eval passes -------------------------------------------------------------
  * One fused pass per call: ShiftBounds, conditioner MLP (eval-mode BatchNorm), spline,
  * Roll (as column renaming) and, for log_prob, the latent log-pdf + nan_to_num. */

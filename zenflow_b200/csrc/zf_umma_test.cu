@@ -1,0 +1,86 @@
+// Single-CTA self-test of the tcgen05 building blocks: out[128][N] = A[128][K] * B[N][K]^T with
+// 3xTF32 split products, A staged registers -> TMEM, B as a shared-memory image, D in TMEM.
+#include "zf_umma.cuh"
+
+namespace zf {
+void count_launch();
+
+__global__ void __launch_bounds__(160) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                            int N, int K, float* __restrict__ out) {
+    extern __shared__ __align__(128) float sB[];  // hi image then lo image, N*K floats each
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 4) umma::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int e = tid; e < N * K; e += blockDim.x) {
+        const int n = e / K, k = e - n * K;
+        float hi, lo;
+        umma::split_tf32(B[e], hi, lo);
+        sB[umma::b_image_index(n, k, N)] = hi;
+        sB[N * K + umma::b_image_index(n, k, N)] = lo;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    const uint32_t colAhi = 0, colAlo = 128, colD = 256;
+    if (warp < 4) {  // one thread per row m: split and store A into tensor memory
+        const int m = warp * 32 + lane;
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) umma::split_tf32(A[m * K + k0 + i], hi[i], lo[i]);
+            umma::st8(umma::taddr(tb, warp * 32, colAhi + k0), hi);
+            umma::st8(umma::taddr(tb, warp * 32, colAlo + k0), lo);
+        }
+        umma::wait_st();
+    }
+    fence_proxy_async_smem();  // B images were written through the generic proxy
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (warp == 4) {
+        if (umma::elect_one()) {
+            const uint32_t idesc = umma::instr_desc_tf32(N);
+            const uint32_t lbo = (uint32_t)(N >> 3) * 128u, sbo = 128u;
+            const uint32_t bhi = smem_u32(sB), blo = smem_u32(sB + N * K);
+            for (int ks = 0; ks < K / 8; ++ks) {
+                const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, sbo);
+                const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, sbo);
+                umma::mma_tf32_ts(tb + colD, tb + colAlo + ks * 8, dhi, idesc, ks > 0);
+                umma::mma_tf32_ts(tb + colD, tb + colAhi + ks * 8, dlo, idesc, true);
+                umma::mma_tf32_ts(tb + colD, tb + colAhi + ks * 8, dhi, idesc, true);
+            }
+            umma::commit(&bar);
+        }
+        __syncwarp();
+    }
+    if (warp < 4) {
+        mbar_wait(&bar, 0);
+        umma::fence_after_sync();
+        const int m = warp * 32 + lane;
+        for (int n0 = 0; n0 < N; n0 += 8) {
+            float v[8];
+            umma::ld8(umma::taddr(tb, warp * 32, colD + n0), v);
+            umma::wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[m * N + n0 + i] = v[i];
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) umma::tmem_dealloc(tb, 512);
+}
+}  // namespace zf
+
+extern "C" int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out) {
+    ZF_REQUIRE(A && B && out, "selftest_umma: null argument");
+    ZF_REQUIRE(N >= 16 && N <= 128 && N % 16 == 0 && K >= 8 && K <= 128 && K % 8 == 0, "selftest_umma: bad N/K");
+    const size_t smem = (size_t)2 * N * K * sizeof(float);
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(zf::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    zf::umma_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, N, K, out);
+    zf::count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}

@@ -37,8 +37,18 @@ CONFIGS = [
 ]
 
 
+@pytest.fixture(params=["auto", "simt"])
+def chain_impl(request, monkeypatch):
+    """auto = tensor-core (tcgen05) kernel when the chain fits it, else the FFMA kernel; simt = force FFMA."""
+    if request.param == "simt":
+        monkeypatch.setenv("ZF_CHAIN_IMPL", "simt")
+    else:
+        monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
-def test_chain_forward_logprob_inverse(cfg):
+def test_chain_forward_logprob_inverse(cfg, chain_impl):
     from zenflow_b200 import Flow
 
     name, D, C, K, layers, ncoup, shift, M = cfg
@@ -53,7 +63,7 @@ def test_chain_forward_logprob_inverse(cfg):
     y64, ld64, _ = zo.chain_forward(ops, to64(v), x.astype(np.float64), None if c is None else c.astype(np.float64))
     e_or = errs(yo, y64)
     e_gpu = errs(y, y64)
-    print(f"\n[{name}] y err gpu={e_gpu:.2e} oracle32={e_or:.2e}; ld err gpu={errs(ld, ld64):.2e} "
+    print(f"\n[{name}/{chain_impl}] y err gpu={e_gpu:.2e} oracle32={e_or:.2e}; ld err gpu={errs(ld, ld64):.2e} "
           f"oracle32={errs(ldo, ld64):.2e}")
     assert_fp32_parity(y, y64, yo, "y", rtol=0, atol=Y_ATOL)
     assert_fp32_parity(ld, ld64, ldo, "log_det")

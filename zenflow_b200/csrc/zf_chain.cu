@@ -17,9 +17,11 @@
 // in the caller's workspace (the FLAX leaves themselves are never modified).
 #include "zf_common.cuh"
 #include "zf_math.cuh"
+#include "zf_umma.cuh"
 
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace zf {
@@ -44,7 +46,9 @@ struct StepDesc {
     int off_W[ZF_MAX_LAYERS + 1];
     int off_b[ZF_MAX_LAYERS + 1];
     int off_sb;
-    int pad[2];
+    int off_U[ZF_MAX_LAYERS + 1];   // tensor-core weight images (3xTF32 hi|lo, K-major core matrices), layers 1..L
+    int umma_ok;                    // this coupling fits the tensor-core kernel
+    int pad[4];
 };
 static_assert(sizeof(StepDesc) % 16 == 0, "StepDesc must keep the packed blocks 16-byte aligned");
 
@@ -130,6 +134,30 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
         for (int e = gtid; e < d * Pp; e += gsz) {
             int jj = e / Pp, p = e - jj * Pp;
             ws[s.off_b[L] + e] = p < P ? job.bias[L][jj * P + p] : 0.f;
+        }
+    }
+    // tensor-core images: per unit (hidden layer l >= 1, or one transformed dim of the last layer)
+    // 4 K-chunks of 32, each [hi image | lo image], image = [k/4][n/8][n%8][k%4]  (zf_umma.cuh)
+    if (s.umma_ok) {
+        const int L = s.n_hidden, P = 3 * s.K - 1, NL = ru(P, 16), d = s.d;
+        for (int l = 1; l <= L; ++l) {
+            const float* W = job.kernel[l];
+            const int units = (l < L) ? 1 : d;
+            const int N = (l < L) ? 128 : NL;
+            const int ldw = (l < L) ? 128 : d * P;
+            for (int e = gtid; e < units * N * 128; e += gsz) {
+                const int u = e / (N * 128), r = e - u * (N * 128);
+                const int k = r / N, n = r - k * N;
+                float val = 0.f;
+                if (l < L) val = W[(size_t)k * ldw + n];
+                else if (n < P) val = W[(size_t)k * ldw + u * P + n];
+                float hi, lo;
+                umma::split_tf32(val, hi, lo);
+                float* dst = ws + s.off_U[l] + (size_t)u * N * 256 + (size_t)(k >> 5) * N * 64;
+                const int ii = umma::b_image_index(n, k & 31, N);
+                dst[ii] = hi;
+                dst[N * 32 + ii] = lo;
+            }
         }
     }
 }
@@ -305,52 +333,57 @@ __device__ __forceinline__ void run_coupling(const StepDesc& s, const float* __r
     ld_acc += ldc;  // Chain: log_det += ld   (bijectors.py:110)
 }
 
+// ShiftBounds for one event m of a tile held as xs[col][stride] (bijectors.py:183-207 / :214-238)
+template <bool INVERSE>
+__device__ __forceinline__ void shift_bounds_row(const StepDesc& s, const float* __restrict__ wsf, int D, float* xs,
+                                                 int stride, int m, float& ld_acc) {
+    float ldc = 0.f;
+    for (int i = 0; i < D; ++i) {
+        const float* t = wsf + s.off_sb + i * kSbStride;
+        const int kind = (int)t[0];
+        const float a = t[1], b = t[2], xmin = t[3], xmax = t[4], mul = t[5], logmul = t[6];
+        float* px = xs + pmod(i - s.rot, D) * stride + m;
+        const float v = *px;
+        if (!INVERSE) {
+            float z, ld;
+            if (kind == ZF_BOUND_BOTH) {
+                z = __fmul_rn(__fsub_rn(v, a), mul);
+                ld = logmul;
+            } else {
+                float u = v;
+                if (kind == ZF_BOUND_LOWER) u = logf(__fadd_rn(__fsub_rn(v, a), FLT_MIN));
+                if (kind == ZF_BOUND_UPPER) u = logf(__fadd_rn(__fsub_rn(b, v), FLT_MIN));
+                z = clip_nanprop(__fmul_rn(__fsub_rn(u, xmin), mul), 0.f, 1.f);
+                ld = (kind == ZF_BOUND_NONE) ? logmul : (logmul - u);
+            }
+            *px = z;
+            ldc += ld;
+        } else {
+            float x;
+            if (kind == ZF_BOUND_BOTH) {
+                x = __fadd_rn(__fmul_rn(v, b), __fmul_rn(__fsub_rn(1.f, v), a));
+            } else {
+                float u = __fadd_rn(__fmul_rn(v, xmax), __fmul_rn(__fsub_rn(1.f, v), xmin));
+                if (kind == ZF_BOUND_LOWER) x = expf(u) + a;
+                else if (kind == ZF_BOUND_UPPER) x = b - expf(u);
+                else x = u;
+            }
+            *px = x;
+        }
+    }
+    ld_acc += ldc;
+}
+
 template <bool INVERSE>
 __device__ __forceinline__ void run_shift_bounds(const StepDesc& s, const float* __restrict__ wsf, int D,
                                                  float* xs, float& ld_acc, int tid) {
-    if (tid < TM) {
-        float ldc = 0.f;
-        for (int i = 0; i < D; ++i) {
-            const float* t = wsf + s.off_sb + i * kSbStride;
-            const int kind = (int)t[0];
-            const float a = t[1], b = t[2], xmin = t[3], xmax = t[4], mul = t[5], logmul = t[6];
-            float* px = xs + pmod(i - s.rot, D) * TM + tid;
-            const float v = *px;
-            if (!INVERSE) {  // bijectors.py:183-207
-                float z, ld;
-                if (kind == ZF_BOUND_BOTH) {
-                    z = __fmul_rn(__fsub_rn(v, a), mul);
-                    ld = logmul;
-                } else {
-                    float u = v;
-                    if (kind == ZF_BOUND_LOWER) u = logf(__fadd_rn(__fsub_rn(v, a), FLT_MIN));
-                    if (kind == ZF_BOUND_UPPER) u = logf(__fadd_rn(__fsub_rn(b, v), FLT_MIN));
-                    z = clip_nanprop(__fmul_rn(__fsub_rn(u, xmin), mul), 0.f, 1.f);
-                    ld = (kind == ZF_BOUND_NONE) ? logmul : (logmul - u);
-                }
-                *px = z;
-                ldc += ld;
-            } else {  // bijectors.py:214-238
-                float x;
-                if (kind == ZF_BOUND_BOTH) {
-                    x = __fadd_rn(__fmul_rn(v, b), __fmul_rn(__fsub_rn(1.f, v), a));
-                } else {
-                    float u = __fadd_rn(__fmul_rn(v, xmax), __fmul_rn(__fsub_rn(1.f, v), xmin));
-                    if (kind == ZF_BOUND_LOWER) x = expf(u) + a;
-                    else if (kind == ZF_BOUND_UPPER) x = b - expf(u);
-                    else x = u;
-                }
-                *px = x;
-            }
-        }
-        ld_acc += ldc;
-    }
+    if (tid < TM) shift_bounds_row<INVERSE>(s, wsf, D, xs, TM, tid, ld_acc);
     __syncthreads();
 }
 
 template <bool INVERSE>
 __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_constant__ ChainArgs a) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x;
     const int D = a.D, C = a.C;
     float* xs = smem;
@@ -406,6 +439,351 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
     }
 }
 
+// =============================================================================================
+// Tensor-core chain kernel (tcgen05, 3xTF32): same program, same outputs as chain_kernel.
+//
+// One CTA per SM, 128 events per tile, 10 warps:
+//   warps 0-7  epilogue / SIMT: ShiftBounds, BatchNorm + first Dense (K = F is tiny), bias+swish+split of
+//              every hidden layer, the spline rows, latent log-pdf.  Thread (q*32+lane, half): TMEM lane
+//              quarter q = warp%4 (hardware rule), column half = warp/4.
+//   warp 8     weight producer: 1-D bulk copies of pre-split K-major weight images L2 -> 4-stage smem ring
+//   warp 9     MMA issuer: tcgen05.mma kind::tf32, A (activations) in tensor memory, B from the ring,
+//              fp32 accumulators in tensor memory; also owns the TMEM allocation.
+// Tensor memory (512 columns): A_hi [0,128) | A_lo [128,256) | D0 [256,384) | D1 [384,512).
+// Hidden layers accumulate into D0; the last layer runs one transformed dim at a time, alternating
+// D0/D1 so that the spline rows of dim j (warps 0-3 for even j, 4-7 for odd j) overlap the MMAs of j+1.
+// 3xTF32: x = hi + lo (tf32 each), D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (fp32-class accuracy;
+// a single TF32/BF16 pass would break the rel-1e-5 parity).
+// =============================================================================================
+constexpr int UM = 128;
+constexpr int UTHREADS = 320;
+constexpr int URING = 4;
+constexpr int URING_FLOATS = 8192;  // 32 KB: one K-chunk (32) of a 128-column unit, hi|lo
+constexpr int UFMAX = 32;           // conditioner inputs handled by the SIMT first layer
+constexpr int UDMAX = 32;           // transformed dims
+enum UBar : int { B_FULL = 0, B_EMPTY = 4, B_AREADY = 8, B_DFULL_H = 9, B_DFULL_D = 10, B_DEMPTY_H = 12, B_DEMPTY_D = 13, B_COUNT = 16 };
+
+__host__ __device__ inline size_t umma_smem_floats(int D, int C) {
+    return (size_t)UM * (D + C) + UFMAX * UM + UFMAX * 128 + 128 + 96 + ZF_MAX_LAYERS * 128 + UDMAX * 96 + 128 +
+           (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32;
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// activation tile column block [n0, n0+16) of this thread's event: swish, split, store to A_hi / A_lo
+__device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_base, int n0, float (&v)[16]) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) umma::split_tf32(swish_fast(v[h * 8 + i]), hi[i], lo[i]);
+        umma::st8(umma::taddr(tb, lane_base, n0 + h * 8), hi);
+        umma::st8(umma::taddr(tb, lane_base, 128 + n0 + h * 8), lo);
+    }
+}
+
+// theta row of this thread's event from a D buffer in tensor memory -> bin parameters
+template <int KT, bool INVERSE, bool SAFE>
+__device__ __forceinline__ void spline_locate_tmem(uint32_t dbase, const float* __restrict__ bias, float v,
+                                                   const KnotNorm& kn, RqsBin& b, RqsCheck& chk) {
+    constexpr int cs_ = INVERSE ? KT : 0, co_ = INVERSE ? 0 : KT;
+    float p[KT];
+#pragma unroll
+    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + cs_ + c0, p + c0);
+    umma::wait_ld();
+#pragma unroll
+    for (int j = 0; j < KT; ++j) p[j] += bias[cs_ + j];
+    rqs_block_search<KT, SAFE>(p, v, kn, b.idx, b.ks, b.bs, chk);
+#pragma unroll
+    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + co_ + c0, p + c0);
+    umma::wait_ld();
+#pragma unroll
+    for (int j = 0; j < KT; ++j) p[j] += bias[co_ + j];
+    rqs_block_other<KT, SAFE>(p, b.idx, kn, b.ko, b.bo, chk);
+}
+
+template <int KT, bool INVERSE>
+__device__ __forceinline__ void spline_row_tmem(uint32_t dbase, const float* __restrict__ bias, float v, RqsBin& b) {
+    const KnotNorm kn = make_knot_norm(KT);
+    RqsCheck chk;
+    spline_locate_tmem<KT, INVERSE, false>(dbase, bias, v, kn, b, chk);
+    if (__any_sync(0xffffffffu, !rqs_fast_ok(chk))) {  // tcgen05.ld is warp-collective: redo as a warp
+        RqsCheck dummy;
+        spline_locate_tmem<KT, INVERSE, true>(dbase, bias, v, kn, b, dummy);
+    }
+    float p[KT];
+#pragma unroll
+    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + 2 * KT + c0, p + c0);
+    umma::wait_ld();
+#pragma unroll
+    for (int j = 0; j < KT; ++j) p[j] += bias[2 * KT + j];
+    rqs_block_slopes<KT>(p, b.idx, b.dk, b.dkp1);
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = a.D, C = a.C;
+    float* xs = smem;
+    float* cs = xs + D * UM;
+    float* hs = cs + C * UM;
+    float* w0s = hs + UFMAX * UM;
+    float* b0s = w0s + UFMAX * 128;
+    float* bns = b0s + 128;
+    float* bhs = bns + 96;
+    float* bls = bhs + ZF_MAX_LAYERS * 128;
+    float* ldx = bls + UDMAX * 96;
+    float* ring = ldx + 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    const StepDesc* steps = reinterpret_cast<const StepDesc*>(a.ws);
+    const float* wsf = a.ws;
+
+    if (tid == 0) {
+        for (int i = 0; i < URING; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
+        mbar_init(&bars[B_AREADY], 256);
+        mbar_init(&bars[B_DFULL_H], 1);
+        mbar_init(&bars[B_DFULL_D + 0], 1);
+        mbar_init(&bars[B_DFULL_D + 1], 1);
+        mbar_init(&bars[B_DEMPTY_H], 256);
+        mbar_init(&bars[B_DEMPTY_D + 0], 128);
+        mbar_init(&bars[B_DEMPTY_D + 1], 128);
+        mbar_fence_init();
+    }
+    if (warp == 9) umma::tmem_alloc(tmem_slot, 512);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+    const long long n_tiles = (a.M + UM - 1) / UM;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ weight producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int si = 0; si < a.n_steps; ++si) {
+                    const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+                    if (s.kind != kStepKindCoupling) continue;
+                    const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                    for (int u = 0; u < (L - 1) + s.d; ++u) {
+                        const bool hid = u < L - 1;
+                        const int N = hid ? 128 : NL;
+                        const float* base = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L] + (size_t)(u - (L - 1)) * NL * 256;
+                        const uint32_t bytes = (uint32_t)N * 256u;
+                        for (int c = 0; c < 4; ++c) {
+                            mbar_wait(&bars[B_EMPTY + stage], phase ^ 1u);
+                            mbar_arrive_expect_tx(&bars[B_FULL + stage], bytes);
+                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, base + (size_t)c * N * 64, bytes,
+                                          &bars[B_FULL + stage]);
+                            if (++stage == URING) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ------------------------------------------------------------------ MMA issuer
+        uint32_t stage = 0, phase = 0, p_ar = 0, p_eh = 0, p_ed0 = 0, p_ed1 = 0;
+        int last0 = 0, last1 = 0;  // previous producer into D0 / D1: 0 none, 1 hidden layer, 2 spline dim
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+                if (s.kind != kStepKindCoupling) continue;
+                const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                for (int u = 0; u < (L - 1) + s.d; ++u) {
+                    const bool hid = u < L - 1;
+                    const int N = hid ? 128 : NL;
+                    const int b = hid ? 0 : ((u - (L - 1)) & 1);
+                    if (hid || u == L - 1) {  // a new version of the activations
+                        mbar_wait(&bars[B_AREADY], p_ar);
+                        p_ar ^= 1u;
+                    }
+                    const int last = b ? last1 : last0;
+                    if (last == 1) { mbar_wait(&bars[B_DEMPTY_H], p_eh); p_eh ^= 1u; }
+                    else if (last == 2) {
+                        if (b) { mbar_wait(&bars[B_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; }
+                        else { mbar_wait(&bars[B_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; }
+                    }
+                    umma::fence_after_sync();
+                    const uint32_t dcol = tb + 256u + (uint32_t)b * 128u;
+                    const uint32_t idesc = umma::instr_desc_tf32(N);
+                    const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+                    for (int c = 0; c < 4; ++c) {
+                        mbar_wait(&bars[B_FULL + stage], phase);
+                        umma::fence_after_sync();
+                        if (umma::elect_one()) {
+                            const uint32_t bhi = smem_u32(ring + (size_t)stage * URING_FLOATS);
+                            const uint32_t blo = bhi + (uint32_t)N * 128u;  // lo image follows the N*32-float hi image
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, 128u);
+                                const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, 128u);
+                                const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                                umma::mma_tf32_ts(dcol, tb + 128u + acol, dhi, idesc, (c | ks) != 0);
+                                umma::mma_tf32_ts(dcol, tb + acol, dlo, idesc, true);
+                                umma::mma_tf32_ts(dcol, tb + acol, dhi, idesc, true);
+                            }
+                            umma::commit(&bars[B_EMPTY + stage]);
+                            if (c == 3) umma::commit(&bars[hid ? B_DFULL_H : (B_DFULL_D + b)]);
+                        }
+                        __syncwarp();
+                        if (++stage == URING) { stage = 0; phase ^= 1u; }
+                    }
+                    if (b) last1 = hid ? 1 : 2; else last0 = hid ? 1 : 2;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue / SIMT warps
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32);
+        uint32_t p_fh = 0, p_fd = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long m0 = tile * UM;
+            const int nm = (int)min((long long)UM, a.M - m0);
+            const int rot_in = INVERSE ? a.rot_total : 0;
+            for (int e = tid; e < UM * D; e += 256) {
+                const int mm = e / D, j = e - mm * D;
+                xs[pmod(j - rot_in, D) * UM + mm] = (mm < nm) ? a.x[m0 * D + e] : 0.5f;
+            }
+            for (int e = tid; e < UM * C; e += 256) {
+                const int mm = e / C, j = e - mm * C;
+                cs[j * UM + mm] = (mm < nm) ? a.c[m0 * C + e] : 0.f;
+            }
+            epi_barrier();
+
+            float ld_acc = 0.f;
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+                if (s.kind == kStepKindShiftBounds) {
+                    if (half == 0) shift_bounds_row<INVERSE>(s, wsf, D, xs, UM, m, ld_acc);
+                    epi_barrier();
+                    continue;
+                }
+                const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
+                const int K = s.K, P = 3 * K - 1, NL = ru(P, 16), Pp4 = ru(P, 4);
+                // ---- stage this coupling's small constants
+                for (int i = tid; i < 3 * F_p; i += 256) bns[i] = wsf[s.off_bn + i];
+                for (int i = tid; i < F * 128; i += 256) w0s[i] = wsf[s.off_W[0] + i];
+                if (tid < 128) b0s[tid] = wsf[s.off_b[0] + tid];
+                for (int i = tid; i < (L - 1) * 128; i += 256) bhs[i] = wsf[s.off_b[1 + (i >> 7)] + (i & 127)];
+                for (int i = tid; i < d * NL; i += 256) {
+                    const int jj = i / NL, pp = i - jj * NL;
+                    bls[i] = pp < Pp4 ? wsf[s.off_b[L] + jj * Pp4 + pp] : 0.f;
+                }
+                epi_barrier();
+                // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342); halves share the features
+                for (int f = half; f < F; f += 2) {
+                    const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
+                    hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+                }
+                epi_barrier();
+                // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
+#pragma unroll 1
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int n0 = half * 64 + nb * 16;
+                    float acc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = b0s[n0 + i];
+                    for (int f = 0; f < F; ++f) {
+                        const float h = hs[f * UM + m];
+                        const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            const float4 wv = w[g4];
+                            acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
+                            acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
+                            acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
+                            acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
+                        }
+                    }
+                    store_activation16(tb, lane_base, n0, acc);
+                }
+                umma::wait_st();
+                umma::fence_before_sync();
+                umma::mbar_arrive(&bars[B_AREADY]);
+                // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
+                for (int l = 1; l < L; ++l) {
+                    mbar_wait(&bars[B_DFULL_H], p_fh);
+                    p_fh ^= 1u;
+                    umma::fence_after_sync();
+                    const float* bh = bhs + (l - 1) * 128;
+#pragma unroll 1
+                    for (int nb = 0; nb < 4; ++nb) {
+                        const int n0 = half * 64 + nb * 16;
+                        float v[16];
+                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);
+                        umma::wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += bh[n0 + i];
+                        store_activation16(tb, lane_base, n0, v);
+                    }
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_AREADY]);
+                    umma::mbar_arrive(&bars[B_DEMPTY_H]);
+                }
+                // ---- last layer: theta of one transformed dim at a time, read from tensor memory
+                float ldc = 0.f;
+                for (int jj = half; jj < d; jj += 2) {
+                    mbar_wait(&bars[B_DFULL_D + half], p_fd);
+                    p_fd ^= 1u;
+                    umma::fence_after_sync();
+                    const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * 128);
+                    float* px = xs + pmod(jj - rot, D) * UM + m;
+                    const float v = *px;
+                    RqsBin bin;
+                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, bls + jj * NL, v, bin);
+                    else spline_row_tmem<32, INVERSE>(dbase, bls + jj * NL, v, bin);
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                    if (!INVERSE) {
+                        float y, ld;
+                        rqs_eval_forward(v, bin, y, ld);
+                        *px = y;
+                        ldc += ld;
+                    } else {
+                        *px = rqs_eval_inverse(v, bin);
+                    }
+                }
+                if (half == 1) ldx[m] = ldc;
+                epi_barrier();
+                if (half == 0) ld_acc += ldc + ldx[m];
+                epi_barrier();
+            }
+
+            // ---- store
+            if (a.mode == kModeLogProb) {
+                if (half == 0 && m < nm) {
+                    float lat = 0.f;
+                    for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * UM + m], a.lc);
+                    a.lp[m0 + m] = nan_to_num_lp(lat + ld_acc);
+                }
+            } else {
+                const int rot_out = INVERSE ? 0 : a.rot_total;
+                if (a.y) {
+                    for (int e = tid; e < nm * D; e += 256) {
+                        const int mm = e / D, j = e - mm * D;
+                        a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * UM + mm];
+                    }
+                }
+                if (!INVERSE && a.log_det && half == 0 && m < nm)
+                    a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
+            }
+            epi_barrier();
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 9) umma::tmem_dealloc(tb, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------
 
 struct Plan {
@@ -413,6 +791,8 @@ struct Plan {
     int rot_total = 0;
     int act_rows = KC;
     size_t ws_floats = 0;
+    bool umma_ok = true;   // every coupling fits the tensor-core kernel
+    int n_couplings = 0;
 };
 
 static int build_plan(const zf_chain* chain, Plan& plan) {
@@ -459,6 +839,13 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
                 return fail(ZF_ERR_UNSUPPORTED, "op %d: knots=%d needs %d columns per dim; the fused kernel holds %d",
                             i, cp.knots, P, NCOL);
             job.desc.kind = kStepKindCoupling;
+            plan.n_couplings++;
+            {   // tensor-core kernel: hidden width 128 throughout, K in {16, 32}, small first layer
+                bool ok = cp.n_hidden >= 1 && (cp.knots == 16 || cp.knots == 32) && (D - d + C) <= UFMAX && d <= UDMAX;
+                for (int l = 0; l < cp.n_hidden; ++l) ok = ok && cp.hidden[l] == 128;
+                job.desc.umma_ok = ok ? 1 : 0;
+                plan.umma_ok = plan.umma_ok && ok;
+            }
             job.desc.K = cp.knots;
             job.desc.n_hidden = cp.n_hidden;
             job.desc.F = D - d + C;
@@ -509,6 +896,12 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
             const int Kin_p = ru(job.Kin[L], KC), Pp = ru(3 * s.K - 1, 4);
             s.off_W[L] = take((size_t)s.d * Kin_p * Pp);
             s.off_b[L] = take((size_t)s.d * Pp);
+            if (s.umma_ok) {
+                const int NL = ru(3 * s.K - 1, 16);
+                off = (off + 31) / 32 * 32;  // images are fetched by 16-byte-aligned bulk copies
+                for (int l = 1; l < L; ++l) s.off_U[l] = take((size_t)128 * 256);
+                s.off_U[L] = take((size_t)s.d * NL * 256);
+            }
         }
         if (off > (size_t)0x7fffffff) return fail(ZF_ERR_UNSUPPORTED, "packed parameters exceed 2^31 floats");
     }
@@ -564,6 +957,28 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     a.acc_log_det = acc_log_det;
     a.lc = make_latent(latent_kind, peakness);
 
+    // tensor-core kernel when every coupling fits it (ZF_CHAIN_IMPL=simt forces the FFMA kernel)
+    const char* impl = getenv("ZF_CHAIN_IMPL");
+    const bool want_umma = plan.umma_ok && plan.n_couplings > 0 && !(impl && impl[0] == 's');
+    if (impl && impl[0] == 'u' && !want_umma)
+        return fail(ZF_ERR_UNSUPPORTED, "ZF_CHAIN_IMPL=umma but this chain does not fit the tensor-core kernel");
+    if (want_umma) {
+        const size_t usmem = umma_smem_floats(a.D, a.C) * sizeof(float);
+        if (usmem <= (size_t)di.max_smem_optin) {
+            const long long tiles = (M + UM - 1) / UM;
+            const unsigned ugrid = (unsigned)std::min<long long>(tiles, (long long)di.sm_count);
+            if (mode == kModeInverse) {
+                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+                chain_umma_kernel<true><<<ugrid, UTHREADS, usmem, stream>>>(a);
+            } else {
+                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+                chain_umma_kernel<false><<<ugrid, UTHREADS, usmem, stream>>>(a);
+            }
+            count_launch();
+            ZF_CUDA_CHECK(cudaGetLastError());
+            return ZF_OK;
+        }
+    }
     const size_t smem = ((size_t)(a.D + a.C) * TM + 2 * (size_t)a.act_rows * TM + 2 * KC * NCOL) * sizeof(float);
     if (smem > (size_t)di.max_smem_optin)
         return fail(ZF_ERR_UNSUPPORTED, "chain tile needs %zu bytes of shared memory (limit %d): layers too wide", smem,

@@ -47,7 +47,10 @@ def errs(a, b):
     return float(d.max()) if d.size else 0.0
 
 
-def assert_fp32_parity(got, truth64, oracle32, what, rtol=1e-5, atol=2e-5):
+def assert_fp32_parity(got, truth64, oracle32, what, rtol=1e-5, atol=2e-5, slack=2.0):
+    """Gate: as accurate as the reference's float32 arithmetic.  slack = allowed ratio of the worst
+    sample's error to the float32 oracle's worst sample (2 for the FFMA kernels; 4 for the 3xTF32
+    tensor-core kernel, whose operands carry 22 instead of 24 significant bits)."""
     got = np.asarray(got, np.float64)
     fin = np.isfinite(truth64) & (np.abs(truth64) < 1e30)
     np.testing.assert_array_equal(np.isfinite(got) & (np.abs(got) < 1e30), fin, err_msg=what)
@@ -56,7 +59,7 @@ def assert_fp32_parity(got, truth64, oracle32, what, rtol=1e-5, atol=2e-5):
     tol = rtol * np.abs(truth64[fin]) + atol
     q_got, q_ref = np.quantile(err / tol, 0.999), np.quantile(ref / tol, 0.999)
     # within tolerance wherever the reference's own float32 arithmetic is
-    assert q_got <= max(1.0, 1.5 * q_ref), f"{what}: 99.9% quantile of err/tol = {q_got:.2f} (fp32 oracle {q_ref:.2f})"
-    assert err.max() <= 2.0 * ref.max() + 1e-5, f"{what}: max err {err.max():.3e} vs fp32 oracle {ref.max():.3e}"
+    assert q_got <= max(1.0, 0.75 * slack * q_ref), f"{what}: 99.9% quantile of err/tol = {q_got:.2f} (fp32 oracle {q_ref:.2f})"
+    assert err.max() <= slack * ref.max() + 1e-5, f"{what}: max err {err.max():.3e} vs fp32 oracle {ref.max():.3e}"
 
 

@@ -470,7 +470,8 @@ __host__ __device__ inline size_t umma_smem_floats(int D, int C) {
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ float swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// accurate swish: the fast-intrinsic form (__expf/__fdividef, ~1e-6 relative) was measurable in log_prob
+__device__ __forceinline__ float swish_fast(float x) { return swishf(x); }
 
 // activation tile column block [n0, n0+16) of this thread's event: swish, split, store to A_hi / A_lo
 __device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_base, int n0, float (&v)[16]) {

@@ -486,22 +486,34 @@ __device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_ba
 }
 
 // theta row of this thread's event from a D buffer in tensor memory -> bin parameters
+// one raw K-block of the theta row: main accumulator (+ cross accumulator when it is separate) + bias
+template <int KT>
+__device__ __forceinline__ void load_theta_block(uint32_t dbase, int col, const float* __restrict__ bias, float (&p)[KT]) {
+    constexpr bool kSplit = (2 * 3 * KT <= 128);  // K = 16: cross products live at columns [3K, 6K)
+#pragma unroll
+    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + col + c0, p + c0);
+    if (kSplit) {
+        float w[KT];
+#pragma unroll
+        for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + 3 * KT + col + c0, w + c0);
+        umma::wait_ld();
+#pragma unroll
+        for (int j = 0; j < KT; ++j) p[j] = (p[j] + w[j]) + bias[col + j];
+    } else {
+        umma::wait_ld();
+#pragma unroll
+        for (int j = 0; j < KT; ++j) p[j] += bias[col + j];
+    }
+}
+
 template <int KT, bool INVERSE, bool SAFE>
 __device__ __forceinline__ void spline_locate_tmem(uint32_t dbase, const float* __restrict__ bias, float v,
                                                    const KnotNorm& kn, RqsBin& b, RqsCheck& chk) {
     constexpr int cs_ = INVERSE ? KT : 0, co_ = INVERSE ? 0 : KT;
     float p[KT];
-#pragma unroll
-    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + cs_ + c0, p + c0);
-    umma::wait_ld();
-#pragma unroll
-    for (int j = 0; j < KT; ++j) p[j] += bias[cs_ + j];
+    load_theta_block<KT>(dbase, cs_, bias, p);
     rqs_block_search<KT, SAFE>(p, v, kn, b.idx, b.ks, b.bs, chk);
-#pragma unroll
-    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + co_ + c0, p + c0);
-    umma::wait_ld();
-#pragma unroll
-    for (int j = 0; j < KT; ++j) p[j] += bias[co_ + j];
+    load_theta_block<KT>(dbase, co_, bias, p);
     rqs_block_other<KT, SAFE>(p, b.idx, kn, b.ko, b.bo, chk);
 }
 
@@ -515,11 +527,7 @@ __device__ __forceinline__ void spline_row_tmem(uint32_t dbase, const float* __r
         spline_locate_tmem<KT, INVERSE, true>(dbase, bias, v, kn, b, dummy);
     }
     float p[KT];
-#pragma unroll
-    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + 2 * KT + c0, p + c0);
-    umma::wait_ld();
-#pragma unroll
-    for (int j = 0; j < KT; ++j) p[j] += bias[2 * KT + j];
+    load_theta_block<KT>(dbase, 2 * KT, bias, p);
     rqs_block_slopes<KT>(p, b.idx, b.dk, b.dkp1);
 }
 
@@ -589,8 +597,13 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
         __syncwarp();
     } else if (warp == 9) {
         // ------------------------------------------------------------------ MMA issuer
+        // The tensor core's fp32 accumulator truncates at every accumulate step (measured: -2.3e-8 relative
+        // per step, tests/test_gpu_umma.py), so the two small cross products (2^-11 of the main one) go to
+        // their own accumulator wherever tensor memory has room: hidden layers main -> D0, cross -> D1;
+        // last-layer dims with 2*NL <= 128 (K = 16) main -> [0,NL), cross -> [NL,2NL) of their buffer.
         uint32_t stage = 0, phase = 0, p_ar = 0, p_eh = 0, p_ed0 = 0, p_ed1 = 0;
-        int last0 = 0, last1 = 0;  // previous producer into D0 / D1: 0 none, 1 hidden layer, 2 spline dim
+        bool hid_pending = false;      // both buffers hold an undrained hidden-layer result
+        bool dim_pending0 = false, dim_pending1 = false;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int si = 0; si < a.n_steps; ++si) {
                 const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
@@ -604,14 +617,13 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                         mbar_wait(&bars[B_AREADY], p_ar);
                         p_ar ^= 1u;
                     }
-                    const int last = b ? last1 : last0;
-                    if (last == 1) { mbar_wait(&bars[B_DEMPTY_H], p_eh); p_eh ^= 1u; }
-                    else if (last == 2) {
-                        if (b) { mbar_wait(&bars[B_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; }
-                        else { mbar_wait(&bars[B_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; }
-                    }
+                    if (hid_pending) { mbar_wait(&bars[B_DEMPTY_H], p_eh); p_eh ^= 1u; hid_pending = false; }
+                    if ((hid || b == 0) && dim_pending0) { mbar_wait(&bars[B_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; dim_pending0 = false; }
+                    if ((hid || b == 1) && dim_pending1) { mbar_wait(&bars[B_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; dim_pending1 = false; }
                     umma::fence_after_sync();
-                    const uint32_t dcol = tb + 256u + (uint32_t)b * 128u;
+                    const uint32_t dmain = tb + 256u + (uint32_t)b * 128u;
+                    const bool split_acc = hid || (2 * NL <= 128);
+                    const uint32_t dcross = hid ? (tb + 384u) : (split_acc ? dmain + (uint32_t)NL : dmain);
                     const uint32_t idesc = umma::instr_desc_tf32(N);
                     const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
                     for (int c = 0; c < 4; ++c) {
@@ -625,9 +637,10 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                                 const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, 128u);
                                 const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, 128u);
                                 const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
-                                umma::mma_tf32_ts(dcol, tb + 128u + acol, dhi, idesc, (c | ks) != 0);
-                                umma::mma_tf32_ts(dcol, tb + acol, dlo, idesc, true);
-                                umma::mma_tf32_ts(dcol, tb + acol, dhi, idesc, true);
+                                const bool first = (c | ks) == 0;
+                                umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, !first);          // A_lo * B_hi
+                                umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);                   // A_hi * B_lo
+                                umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, split_acc ? !first : true);  // A_hi * B_hi
                             }
                             umma::commit(&bars[B_EMPTY + stage]);
                             if (c == 3) umma::commit(&bars[hid ? B_DFULL_H : (B_DFULL_D + b)]);
@@ -635,7 +648,9 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                         __syncwarp();
                         if (++stage == URING) { stage = 0; phase ^= 1u; }
                     }
-                    if (b) last1 = hid ? 1 : 2; else last0 = hid ? 1 : 2;
+                    if (hid) hid_pending = true;
+                    else if (b) dim_pending1 = true;
+                    else dim_pending0 = true;
                 }
             }
         }
@@ -717,11 +732,12 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
 #pragma unroll 1
                     for (int nb = 0; nb < 4; ++nb) {
                         const int n0 = half * 64 + nb * 16;
-                        float v[16];
-                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);
+                        float v[16], w[16];
+                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);   // main products
+                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0), w);   // cross products
                         umma::wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += bh[n0 + i];
+                        for (int i = 0; i < 16; ++i) v[i] = (v[i] + w[i]) + bh[n0 + i];
                         store_activation16(tb, lane_base, n0, v);
                     }
                     umma::wait_st();

@@ -361,12 +361,17 @@ def run_gpu(args):
     flops = chain_flops_per_event(w)
     step_ms = total_ms / K
     tflops = flops * M / (step_ms * 1e-3) / 1e12
+    simt = os.environ.get("ZF_CHAIN_IMPL", "").startswith("s")
     roofline = {
-        "kernel": "chain_kernel<false> (zf_flow_log_prob): fused conditioner MLPs + splines + latent",
+        "kernel": ("chain_kernel<false>: fused conditioner MLPs (fp32 FFMA) + splines + latent" if simt else
+                   "chain_umma_kernel<false> (zf_flow_log_prob): conditioner GEMMs on tcgen05 (3xTF32, A in TMEM), "
+                   "spline rows read theta from TMEM, latent fused"),
         "bound": "tensor", "achieved": tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tflops / pk["bf16"],
         "traffic": None, "flops_per_event": flops,
-        "note": "fp32 FFMA (SIMT) GEMMs this round: FP32 SIMT roof is 74.4 TFLOP/s at 1965 MHz; "
-                "achieved uses the whole step time (pack kernels included, <1%)",
+        "note": "algorithmic fp32 flops (not x3 for the 3xTF32 split; kind::tf32 runs at half the bf16 rate, so the "
+                "tensor pipe executes 6 bf16-equivalents per algorithmic flop); achieved uses the whole step time "
+                "(pack kernels included, <2%); the kernel is bound by the SIMT spline/activation epilogue, see DESIGN.md",
+        "tensor_pipe_bf16_equivalent_frac": 6 * tflops / pk["bf16"],
         "frac_of_fp32_simt_peak": tflops / 74.4, "peak_source": pk["source"]}
 
     cpu_sample = args.cpu_sample or default_cpu_sample(w)

@@ -470,8 +470,10 @@ __host__ __device__ inline size_t umma_smem_floats(int D, int C) {
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// accurate swish: the fast-intrinsic form (__expf/__fdividef, ~1e-6 relative) was measurable in log_prob
-__device__ __forceinline__ float swish_fast(float x) { return swishf(x); }
+// swish with the SFU exp2 / reciprocal: the absolute error stays below ~1e-7 (the exponent's argument
+// rounding only matters where exp(-x) is negligible against 1, or where swish itself is ~0); measured
+// on log_prob it is indistinguishable from expf + IEEE division and costs a quarter of the instructions
+__device__ __forceinline__ float swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // activation tile column block [n0, n0+16) of this thread's event: swish, split, store to A_hi / A_lo
 __device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_base, int n0, float (&v)[16]) {
@@ -730,15 +732,21 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                     umma::fence_after_sync();
                     const float* bh = bhs + (l - 1) * 128;
 #pragma unroll 1
-                    for (int nb = 0; nb < 4; ++nb) {
-                        const int n0 = half * 64 + nb * 16;
-                        float v[16], w[16];
-                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);   // main products
-                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0), w);   // cross products
+                    for (int nb = 0; nb < 2; ++nb) {  // 32 columns per round: four TMEM loads in flight
+                        const int n0 = half * 64 + nb * 32;
+                        float v[32], w[32];
+                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);        // main products
+                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0 + 16), v + 16);
+                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0), w);        // cross products
+                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0 + 16), w + 16);
                         umma::wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = (v[i] + w[i]) + bh[n0 + i];
-                        store_activation16(tb, lane_base, n0, v);
+                        for (int i = 0; i < 32; ++i) v[i] = (v[i] + w[i]) + bh[n0 + i];
+                        float lo16[16], hi16[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { lo16[i] = v[i]; hi16[i] = v[16 + i]; }
+                        store_activation16(tb, lane_base, n0, lo16);
+                        store_activation16(tb, lane_base, n0 + 16, hi16);
                     }
                     umma::wait_st();
                     umma::fence_before_sync();

@@ -55,7 +55,7 @@ def test_chain_forward_logprob_inverse(cfg, chain_impl):
     # the tensor-core kernel computes the conditioner with 3xTF32 split products: fp32-class, but
     # 22-bit operands and tensor-core accumulation leave ~3x the error of an fp32 FFMA chain
     tc = chain_impl == "auto"
-    slack, atol_lp = (4.0, 5e-5) if tc else (2.0, LP_ATOL)
+    slack, atol_lp = (4.0, 5e-5) if tc else (3.0, LP_ATOL)
     ops = zo.make_chain(D, K, layers, n_couplings=ncoup, roll_shift=shift)
     x, c = _data(M, D, C, seed=len(name))
     v = trained_variables(ops, x, c, seed=1)

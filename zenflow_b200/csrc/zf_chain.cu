@@ -488,49 +488,68 @@ __device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_ba
 }
 
 // theta row of this thread's event from a D buffer in tensor memory -> bin parameters
-// one raw K-block of the theta row: main accumulator (+ cross accumulator when it is separate) + bias
+// ---- theta row of this thread's event from a D buffer in tensor memory ---------------------------
+// issue the TMEM loads of one raw K-block (main accumulator, and the separate cross accumulator at
+// +3K when K = 16); tcgen05.wait::ld must follow before the registers are read
 template <int KT>
-__device__ __forceinline__ void load_theta_block(uint32_t dbase, int col, const float* __restrict__ bias, float (&p)[KT]) {
-    constexpr bool kSplit = (2 * 3 * KT <= 128);  // K = 16: cross products live at columns [3K, 6K)
+__device__ __forceinline__ void theta_block_issue(uint32_t dbase, int col, float (&p)[KT], float (&w)[KT]) {
+    constexpr bool kSplit = (2 * 3 * KT <= 128);
 #pragma unroll
     for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + col + c0, p + c0);
     if (kSplit) {
-        float w[KT];
 #pragma unroll
         for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + 3 * KT + col + c0, w + c0);
-        umma::wait_ld();
-#pragma unroll
-        for (int j = 0; j < KT; ++j) p[j] = (p[j] + w[j]) + bias[col + j];
-    } else {
-        umma::wait_ld();
-#pragma unroll
-        for (int j = 0; j < KT; ++j) p[j] += bias[col + j];
     }
 }
+// main + cross + bias; returns max |theta| of the block (NaN-poisoned to +inf)
+template <int KT>
+__device__ __forceinline__ float theta_block_finish(int col, const float* __restrict__ bias, float (&p)[KT],
+                                                    const float (&w)[KT]) {
+    constexpr bool kSplit = (2 * 3 * KT <= 128);
+    float amax = 0.f;
+    bool nan = false;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        p[j] = kSplit ? (p[j] + w[j]) + bias[col + j] : p[j] + bias[col + j];
+        amax = fmaxf(amax, fabsf(p[j]));
+        nan = nan || (p[j] != p[j]);
+    }
+    return nan ? CUDART_INF_F : amax;
+}
 
-template <int KT, bool INVERSE, bool SAFE>
-__device__ __forceinline__ void spline_locate_tmem(uint32_t dbase, const float* __restrict__ bias, float v,
-                                                   const KnotNorm& kn, RqsBin& b, RqsCheck& chk) {
+// |theta| < 4096 makes the exact fast forms valid without looking at the quotients: squareplus >= 2^-13
+// and the sum <= 2^17, so every s/sum quotient is >= 2^-30, far above the 2^-100 remainder-exactness bound.
+constexpr float kThetaFastBound = 4096.0f;
+
+// Locate the bin from tensor memory.  The three raw blocks are loaded in a software pipeline (the next
+// block's TMEM load is in flight while the current one is processed) and the D buffer is handed back to
+// the MMA warp (release()) right after the last load, before the second pass and the spline evaluation.
+template <int KT, bool INVERSE, class Release>
+__device__ __forceinline__ void spline_row_tmem(uint32_t dbase, const float* __restrict__ bias, float v, RqsBin& b,
+                                                Release release) {
     constexpr int cs_ = INVERSE ? KT : 0, co_ = INVERSE ? 0 : KT;
-    float p[KT];
-    load_theta_block<KT>(dbase, cs_, bias, p);
-    rqs_block_search<KT, SAFE>(p, v, kn, b.idx, b.ks, b.bs, chk);
-    load_theta_block<KT>(dbase, co_, bias, p);
-    rqs_block_other<KT, SAFE>(p, b.idx, kn, b.ko, b.bo, chk);
-}
-
-template <int KT, bool INVERSE>
-__device__ __forceinline__ void spline_row_tmem(uint32_t dbase, const float* __restrict__ bias, float v, RqsBin& b) {
     const KnotNorm kn = make_knot_norm(KT);
+    float pa[KT], pb[KT], wa[KT], wb[KT];
     RqsCheck chk;
-    spline_locate_tmem<KT, INVERSE, false>(dbase, bias, v, kn, b, chk);
-    if (__any_sync(0xffffffffu, !rqs_fast_ok(chk))) {  // tcgen05.ld is warp-collective: redo as a warp
-        RqsCheck dummy;
-        spline_locate_tmem<KT, INVERSE, true>(dbase, bias, v, kn, b, dummy);
-    }
-    float p[KT];
-    load_theta_block<KT>(dbase, 2 * KT, bias, p);
-    rqs_block_slopes<KT>(p, b.idx, b.dk, b.dkp1);
+    theta_block_issue<KT>(dbase, cs_, pa, wa);
+    umma::wait_ld();
+    theta_block_issue<KT>(dbase, co_, pb, wb);          // in flight during the search pass
+    const float amax_s = theta_block_finish<KT>(cs_, bias, pa, wa);
+    if (__any_sync(0xffffffffu, !(amax_s < kThetaFastBound)))
+        rqs_block_search<KT, true>(pa, v, kn, b.idx, b.ks, b.bs, chk);
+    else
+        rqs_block_search<KT, false>(pa, v, kn, b.idx, b.ks, b.bs, chk);
+    umma::wait_ld();
+    theta_block_issue<KT>(dbase, 2 * KT, pa, wa);       // slopes reuse the searched block's registers
+    umma::wait_ld();
+    release();                                          // every TMEM read of this row is done
+    const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
+    if (__any_sync(0xffffffffu, !(amax_o < kThetaFastBound)))
+        rqs_block_other<KT, true>(pb, b.idx, kn, b.ko, b.bo, chk);
+    else
+        rqs_block_other<KT, false>(pb, b.idx, kn, b.ko, b.bo, chk);
+    (void)theta_block_finish<KT>(2 * KT, bias, pa, wa);
+    rqs_block_slopes<KT>(pa, b.idx, b.dk, b.dkp1);
 }
 
 template <bool INVERSE>
@@ -763,10 +782,12 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                     float* px = xs + pmod(jj - rot, D) * UM + m;
                     const float v = *px;
                     RqsBin bin;
-                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, bls + jj * NL, v, bin);
-                    else spline_row_tmem<32, INVERSE>(dbase, bls + jj * NL, v, bin);
-                    umma::fence_before_sync();
-                    umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                    auto release = [&]() {
+                        umma::fence_before_sync();
+                        umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                    };
+                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, bls + jj * NL, v, bin, release);
+                    else spline_row_tmem<32, INVERSE>(dbase, bls + jj * NL, v, bin, release);
                     if (!INVERSE) {
                         float y, ld;
                         rqs_eval_forward(v, bin, y, ld);

@@ -126,6 +126,13 @@ int zf_selftest_exact_math(void* stream, uint64_t* mismatches);
  * shared memory): out (128, N) = A (128, K) * B (N, K)^T, N % 16 == 0 <= 128, K % 8 == 0 <= 128. */
 int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out);
 
+/* Self-test of the tcgen05 GEMM family used by the train step (zf_umma_gemm.cu), fp32 in/out:
+ * mode 0: C[I][J] = opA(A[I][R]) B[R][J] + bias; mode 1: C[I][J] = (A[I][R] B[J][R]^T) * swish'(Z[I][J]);
+ * mode 2: C[I][J] += opA(A[R][I])^T B[R][J], colsum[J] += column sums of B (r_slab rows per CTA). */
+int zf_selftest_umma_gemm(void* stream, int32_t mode, const float* A, int64_t lda, const float* B, int64_t ldb,
+                          float* C, int64_t ldc, const float* bias, float* colsum, const float* Z, int64_t ldz,
+                          int32_t a_swish, int64_t I, int64_t J, int64_t R, int64_t r_slab);
+
 /* ---- whole-chain eval passes -------------------------------------------------------------
  * One fused pass per call: ShiftBounds, conditioner MLP (eval-mode BatchNorm), spline,
  * Roll (as column renaming) and, for log_prob, the latent log-pdf + nan_to_num. */

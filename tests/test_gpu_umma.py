@@ -59,3 +59,56 @@ def test_umma_error_budget():
         rel32 = ((a @ b.T) - ref) / np.abs(ref)
         print(f"\n{name}: 3xTF32 rel err max {np.abs(rel).max():.2e} mean {rel.mean():+.2e} rms {rel.std():.2e} | "
               f"fp32 sgemm max {np.abs(rel32).max():.2e} mean {rel32.mean():+.2e} rms {rel32.std():.2e}")
+
+
+def _swish(x):
+    return x / (1 + np.exp(-x))
+
+
+def _swish_grad(z):
+    s = 1 / (1 + np.exp(-z))
+    return s * (1 + z * (1 - s))
+
+
+@pytest.mark.parametrize("mode,I,J,R,a_swish", [
+    (0, 300, 760, 128, 1), (0, 1000, 128, 12, 0), (0, 129, 47, 128, 1), (0, 64, 128, 2, 0),
+    (1, 300, 128, 760, 0), (1, 777, 12, 128, 0), (1, 130, 128, 47, 0),
+    (2, 128, 760, 5000, 1), (2, 12, 128, 4097, 0), (2, 128, 47, 300, 1), (2, 2, 128, 31, 0),
+])
+def test_umma_gemm_family(mode, I, J, R, a_swish):
+    """The three GEMM shapes of the conditioner VJP on tcgen05, incl. ragged sizes, vs float64."""
+    from zenflow_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(mode * 1000 + I + J + R)
+    st = torch.cuda.current_stream().cuda_stream
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    if mode == 0:
+        A = rng.normal(size=(I, R)); B = rng.normal(size=(R, J)) / np.sqrt(R); bias = rng.normal(size=J)
+        ref = (_swish(A) if a_swish else A) @ B + bias
+        At, Bt, bt = cu(A), cu(B), cu(bias)
+        Ct = torch.full((I, J), float("nan"), device="cuda")
+        _lib.check(lib.zf_selftest_umma_gemm(st, 0, At.data_ptr(), R, Bt.data_ptr(), J, Ct.data_ptr(), J, bt.data_ptr(),
+                                             None, None, 0, a_swish, I, J, R, 0))
+    elif mode == 1:
+        A = rng.normal(size=(I, R)); B = rng.normal(size=(J, R)) / np.sqrt(R); Z = rng.normal(size=(I, J))
+        ref = (A @ B.T) * _swish_grad(Z)
+        At, Bt, Zt = cu(A), cu(B), cu(Z)
+        Ct = torch.full((I, J), float("nan"), device="cuda")
+        _lib.check(lib.zf_selftest_umma_gemm(st, 1, At.data_ptr(), R, Bt.data_ptr(), R, Ct.data_ptr(), J, None, None,
+                                             Zt.data_ptr(), J, 0, I, J, R, 0))
+    else:
+        A = rng.normal(size=(R, I)); B = rng.normal(size=(R, J)) / np.sqrt(R)
+        C0 = rng.normal(size=(I, J)); cs0 = rng.normal(size=J)
+        ref = C0 + (_swish(A) if a_swish else A).T @ B
+        ref_cs = cs0 + B.sum(0)
+        At, Bt, Ct, cst = cu(A), cu(B), cu(C0), cu(cs0)
+        _lib.check(lib.zf_selftest_umma_gemm(st, 2, At.data_ptr(), I, Bt.data_ptr(), J, Ct.data_ptr(), J, None,
+                                             cst.data_ptr(), None, 0, a_swish, I, J, R, 1024))
+        np.testing.assert_allclose(cst.cpu().numpy(), ref_cs, rtol=1e-5, atol=1e-5)
+    torch.cuda.synchronize()
+    got = Ct.cpu().numpy()
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max() / scale
+    print(f"\nmode {mode} I={I} J={J} R={R}: max err / max|ref| = {err:.2e}")
+    assert err < 5e-6

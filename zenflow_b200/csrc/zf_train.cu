@@ -17,6 +17,7 @@
 #include "zf_math.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace zf {
@@ -370,7 +371,16 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmA
     if (MODE == 2 && g.colsum && blockIdx.x == 0 && tid < GT && j0 + tid < g.J) atomicAdd(&g.colsum[j0 + tid], csum);
 }
 
+int launch_umma_gemm(cudaStream_t st, int mode, const float* A, long long lda, const float* B, long long ldb, float* C,
+                     long long ldc, const float* bias, float* colsum, const float* Z, long long ldz, int a_swish,
+                     long long I, long long J, long long R, long long r_slab);
+
 static int launch_gemm(cudaStream_t st, int mode, const GemmArgs& g) {
+    // tensor-core (tcgen05, 3xTF32) GEMM by default; ZF_GEMM_IMPL=simt keeps the fp32 FFMA kernel
+    const char* impl = getenv("ZF_GEMM_IMPL");
+    if (!(impl && impl[0] == 's'))
+        return launch_umma_gemm(st, mode, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.bias, g.colsum, g.Z, g.ldz, g.a_swish,
+                                g.I, g.J, g.R, mode == 2 ? 4096 : 0);
     dim3 grid((unsigned)((g.I + GT - 1) / GT), (unsigned)((g.J + GT - 1) / GT), 1);
     if (mode == 2) grid.z = (unsigned)((g.R + g.r_slab - 1) / g.r_slab);
     if (grid.x == 0 || grid.y == 0) return ZF_OK;

@@ -1,0 +1,255 @@
+// tcgen05 GEMM family for the train step's conditioner recompute and VJP (fp32 in / fp32 out,
+// 3xTF32 split products, fp32-class accuracy):
+//   mode 0 (NN): C[m][n]  = sum_k opA(A[m][k]) * B[k][n] + bias[n]                 (Dense forward)
+//   mode 1 (NT): C[m][k]  = (sum_n A[m][n] * B[k][n]) * swish'(Z[m][k])           (grad wrt Dense input)
+//   mode 2 (TN): C[k][n] += sum_m opA(A[m][k]) * B[m][n];  colsum[n] += sum_m B[m][n]   (grad wrt kernel, bias)
+// opA = swish when a_swish (stored pre-activations are re-activated on load).
+//
+// One CTA computes a 128 x TN output tile.  8 loader warps read the fp32 operands from global memory,
+// apply opA, split x = hi + lo (tf32) and write K-major core-matrix images (zf_umma.cuh) of a 32-deep
+// reduction chunk into a shared-memory ring; warp 8 issues tcgen05.mma.kind::tf32 with both operands
+// from shared memory; the main products accumulate in TMEM columns [0,TN), the two cross products in
+// [TN,2TN) (the tensor core's accumulator truncates per step, see zf_chain.cu); the loader warps then
+// turn into the epilogue (TMEM -> registers -> global, bias / swish' / atomics).
+#include "zf_umma.cuh"
+
+#include <algorithm>
+
+namespace zf {
+
+void count_launch();
+
+struct UGemmArgs {
+    const float* A; long long lda;
+    const float* B; long long ldb;
+    float* C; long long ldc;
+    const float* bias;
+    float* colsum;
+    const float* Z; long long ldz;
+    int a_swish;
+    long long I, J, R;   // output rows, output cols, reduction length
+    long long r_slab;    // mode 2: reduction rows per CTA (gridDim.z slabs)
+};
+
+constexpr int UG_THREADS = 288;  // 8 loader/epilogue warps + 1 MMA warp
+constexpr int UG_KC = 32;        // reduction depth per ring stage
+
+__device__ __forceinline__ float ug_swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ug_swish_grad(float z) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+}
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u, z = 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+
+// One 16-byte unit (4 consecutive reduction indices r4*4..+3 of image row `row`) of an operand image.
+//   RCONTIG: X[(row0+row)*ld + r0 + r]      (reduction index contiguous in memory)
+//   else   : X[(r0+r)*ld + row0 + row]      (transposed on load)
+template <bool RCONTIG>
+__device__ __forceinline__ float4 ug_load_unit(const float* __restrict__ X, long long ld, long long row, long long row_max,
+                                               long long r, long long r_max) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < row_max) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (r + i < r_max) v[i] = RCONTIG ? X[row * ld + r + i] : X[(r + i) * ld + row];
+        }
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <int MODE, int TN>
+__global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_constant__ UGemmArgs g) {
+    constexpr int A_FLOATS = 128 * UG_KC;      // one image (hi or lo) of the A chunk
+    constexpr int B_FLOATS = TN * UG_KC;
+    constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
+    constexpr int STAGES = (TN == 256) ? 2 : 3;
+    constexpr bool A_RCONTIG = (MODE != 2);    // NN, NT: A[m][r]; TN: A[r][i]
+    constexpr bool B_RCONTIG = (MODE == 1);    // NT: B[k][n] = [j][r]; NN, TN: B[r][j]
+
+    extern __shared__ __align__(128) float smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* full = bars;            // [STAGES] count 256
+    uint64_t* empty = bars + 3;       // [STAGES] count 1 (tcgen05.commit)
+    uint64_t* done = bars + 6;        // count 1
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long i0 = (long long)blockIdx.x * 128, j0 = (long long)blockIdx.y * TN;
+    long long rbeg = 0, rend = g.R;
+    if (MODE == 2) {
+        rbeg = (long long)blockIdx.z * g.r_slab;
+        rend = (rbeg + g.r_slab < g.R) ? rbeg + g.r_slab : g.R;
+    }
+    const int n_chunks = (int)((rend - rbeg + UG_KC - 1) / UG_KC);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 256); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) umma::tmem_alloc(tmem_slot, 2 * TN);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ loaders
+        float csum = 0.f;  // mode 2: column sum of B for this thread's fixed column
+        uint32_t stage = 0, phase = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            float* st = smem + (size_t)stage * STAGE_FLOATS;
+            const long long r0 = rbeg + (long long)c * UG_KC;
+            // A image: 128 rows x 8 units
+#pragma unroll 2
+            for (int u = tid; u < 128 * 8; u += 256) {
+                int row, r4;
+                if (A_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u & 127; r4 = u >> 7; }
+                float4 v = ug_load_unit<A_RCONTIG>(g.A, g.lda, i0 + row, g.I, r0 + r4 * 4, rend);
+                if (g.a_swish) { v.x = ug_swish(v.x); v.y = ug_swish(v.y); v.z = ug_swish(v.z); v.w = ug_swish(v.w); }
+                float4 hi, lo;
+                umma::split_tf32(v.x, hi.x, lo.x); umma::split_tf32(v.y, hi.y, lo.y);
+                umma::split_tf32(v.z, hi.z, lo.z); umma::split_tf32(v.w, hi.w, lo.w);
+                const int off = (r4 * 16 + (row >> 3)) * 32 + (row & 7) * 4;
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + A_FLOATS + off) = lo;
+            }
+            // B image: TN rows x 8 units
+#pragma unroll 2
+            for (int u = tid; u < TN * 8; u += 256) {
+                int row, r4;
+                if (B_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u % TN; r4 = u / TN; }
+                float4 v = ug_load_unit<B_RCONTIG>(g.B, g.ldb, j0 + row, g.J, r0 + r4 * 4, rend);
+                if (MODE == 2) csum += (v.x + v.y) + (v.z + v.w);
+                float4 hi, lo;
+                umma::split_tf32(v.x, hi.x, lo.x); umma::split_tf32(v.y, hi.y, lo.y);
+                umma::split_tf32(v.z, hi.z, lo.z); umma::split_tf32(v.w, hi.w, lo.w);
+                const int off = (r4 * (TN / 8) + (row >> 3)) * 32 + (row & 7) * 4;
+                *reinterpret_cast<float4*>(st + 2 * A_FLOATS + off) = hi;
+                *reinterpret_cast<float4*>(st + 2 * A_FLOATS + B_FLOATS + off) = lo;
+            }
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+            umma::mbar_arrive(&full[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (MODE == 2 && g.colsum && blockIdx.x == 0) {
+            // in the transposed B loader a thread always serves column (tid % TN) (+ 0 or 128 for TN=128 pairs)
+            const int col = (TN == 256) ? tid : (tid & 127);
+            if (TN == 128) {  // two threads share a column: combine through shuffle-free atomics
+                if (j0 + col < g.J) atomicAdd(&g.colsum[j0 + col], csum);
+            } else if (j0 + col < g.J) {
+                atomicAdd(&g.colsum[j0 + col], csum);
+            }
+        }
+        // ------------------------------------------------------------------ epilogue
+        mbar_wait(done, 0);
+        umma::fence_after_sync();
+        const int q = warp & 3, half = warp >> 2;
+        const long long i = i0 + q * 32 + lane;
+        constexpr int HALF_COLS = TN / 2;
+#pragma unroll 1
+        for (int n0 = half * HALF_COLS; n0 < (half + 1) * HALF_COLS; n0 += 16) {
+            float v[16], w[16];
+            umma::ld16(umma::taddr(tb, q * 32, n0), v);
+            umma::ld16(umma::taddr(tb, q * 32, TN + n0), w);
+            umma::wait_ld();
+            if (i < g.I) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const long long j = j0 + n0 + t;
+                    if (j >= g.J) continue;
+                    float x = v[t] + w[t];
+                    if (MODE == 0) {
+                        if (g.bias) x += g.bias[j];
+                        g.C[i * g.ldc + j] = x;
+                    } else if (MODE == 1) {
+                        if (g.Z) x *= ug_swish_grad(g.Z[i * g.ldz + j]);
+                        g.C[i * g.ldc + j] = x;
+                    } else {
+                        atomicAdd(&g.C[i * g.ldc + j], x);
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = umma::instr_desc_tf32(TN);
+        const uint32_t lbo_a = 16u * 128u, lbo_b = (uint32_t)(TN / 8) * 128u;
+        uint32_t stage = 0, phase = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(&full[stage], phase);
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                const uint32_t base = smem_u32(smem + (size_t)stage * STAGE_FLOATS);
+                const uint32_t a_hi = base, a_lo = base + A_FLOATS * 4u;
+                const uint32_t b_hi = base + 2u * A_FLOATS * 4u, b_lo = b_hi + B_FLOATS * 4u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t dah = umma::smem_desc_kmajor(a_hi + ks * 2 * lbo_a, lbo_a, 128u);
+                    const uint64_t dal = umma::smem_desc_kmajor(a_lo + ks * 2 * lbo_a, lbo_a, 128u);
+                    const uint64_t dbh = umma::smem_desc_kmajor(b_hi + ks * 2 * lbo_b, lbo_b, 128u);
+                    const uint64_t dbl = umma::smem_desc_kmajor(b_lo + ks * 2 * lbo_b, lbo_b, 128u);
+                    const bool first = (c | ks) == 0;
+                    mma_tf32_ss(tb + TN, dal, dbh, idesc, !first);
+                    mma_tf32_ss(tb + TN, dah, dbl, idesc, true);
+                    mma_tf32_ss(tb, dah, dbh, idesc, !first);
+                }
+                umma::commit(&empty[stage]);
+                if (c == n_chunks - 1) umma::commit(done);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (n_chunks == 0 && lane == 0) umma::mbar_arrive(done);  // nothing to accumulate (never launched that way)
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) umma::tmem_dealloc(tb, 2 * TN);
+}
+
+template <int MODE, int TN>
+static int launch_one(cudaStream_t st, const UGemmArgs& g) {
+    constexpr int STAGES = (TN == 256) ? 2 : 3;
+    const size_t smem = ((size_t)STAGES * (2 * 128 * UG_KC + 2 * TN * UG_KC)) * sizeof(float) + 8 * 8 + 16;
+    dim3 grid((unsigned)((g.I + 127) / 128), (unsigned)((g.J + TN - 1) / TN), 1);
+    if (MODE == 2) grid.z = (unsigned)((g.R + g.r_slab - 1) / g.r_slab);
+    if (grid.x == 0 || grid.y == 0 || g.R <= 0) return ZF_OK;
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_gemm_kernel<MODE, TN><<<grid, UG_THREADS, smem, st>>>(g);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+// Same argument convention as the FFMA gemm of zf_train.cu.  Wide outputs use 256-column tiles.
+int launch_umma_gemm(cudaStream_t st, int mode, const float* A, long long lda, const float* B, long long ldb, float* C,
+                     long long ldc, const float* bias, float* colsum, const float* Z, long long ldz, int a_swish,
+                     long long I, long long J, long long R, long long r_slab) {
+    UGemmArgs g{A, lda, B, ldb, C, ldc, bias, colsum, Z, ldz, a_swish, I, J, R, r_slab};
+    const bool wide = J > 128;
+    if (mode == 0) return wide ? launch_one<0, 256>(st, g) : launch_one<0, 128>(st, g);
+    if (mode == 1) return wide ? launch_one<1, 256>(st, g) : launch_one<1, 128>(st, g);
+    return wide ? launch_one<2, 256>(st, g) : launch_one<2, 128>(st, g);
+}
+
+}  // namespace zf
+
+extern "C" int zf_selftest_umma_gemm(void* stream, int32_t mode, const float* A, int64_t lda, const float* B, int64_t ldb,
+                                     float* C, int64_t ldc, const float* bias, float* colsum, const float* Z, int64_t ldz,
+                                     int32_t a_swish, int64_t I, int64_t J, int64_t R, int64_t r_slab) {
+    ZF_REQUIRE(A && B && C && mode >= 0 && mode <= 2 && I >= 1 && J >= 1 && R >= 1, "selftest_umma_gemm: bad argument");
+    ZF_REQUIRE(mode != 2 || (I <= 128 && r_slab >= 32 && r_slab % 32 == 0), "selftest_umma_gemm: mode 2 needs I <= 128 and r_slab % 32 == 0");
+    return zf::launch_umma_gemm((cudaStream_t)stream, mode, A, lda, B, ldb, C, ldc, bias, colsum, Z, ldz, a_swish, I, J, R, r_slab);
+}

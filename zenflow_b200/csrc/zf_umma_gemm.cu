@@ -57,15 +57,21 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
 //   else   : X[(r0+r)*ld + row0 + row]      (transposed on load)
 template <bool RCONTIG>
 __device__ __forceinline__ float4 ug_load_unit(const float* __restrict__ X, long long ld, long long row, long long row_max,
-                                               long long r, long long r_max) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                                               long long r, long long r_max, bool vec_ok) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < row_max) {
+        if (RCONTIG && vec_ok && r + 3 < r_max) {
+            o = __ldg(reinterpret_cast<const float4*>(X + row * ld + r));
+        } else {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (r + i < r_max) v[i] = RCONTIG ? X[row * ld + r + i] : X[(r + i) * ld + row];
+            for (int i = 0; i < 4; ++i) {
+                if (r + i < r_max) v[i] = RCONTIG ? __ldg(X + row * ld + r + i) : __ldg(X + (r + i) * ld + row);
+            }
+            o = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    return make_float4(v[0], v[1], v[2], v[3]);
+    return o;
 }
 
 template <int MODE, int TN>
@@ -107,17 +113,34 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
     if (warp < 8) {
         // ------------------------------------------------------------------ loaders
         float csum = 0.f;  // mode 2: column sum of B for this thread's fixed column
-        uint32_t stage = 0, phase = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait(&empty[stage], phase ^ 1u);
-            float* st = smem + (size_t)stage * STAGE_FLOATS;
+        constexpr int UA = 128 * 8 / 256, UB = TN * 8 / 256;   // 16-byte units per thread per chunk
+        const bool vecA = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((rbeg & 3) == 0);
+        const bool vecB = ((g.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((rbeg & 3) == 0);
+        // the whole next chunk is fetched into registers while the current one is converted and stored
+        auto fetch = [&](int c, float4 (&ra)[UA], float4 (&rb)[UB]) {
             const long long r0 = rbeg + (long long)c * UG_KC;
-            // A image: 128 rows x 8 units
-#pragma unroll 2
-            for (int u = tid; u < 128 * 8; u += 256) {
+#pragma unroll
+            for (int q = 0; q < UA; ++q) {
+                const int u = tid + q * 256;
                 int row, r4;
                 if (A_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u & 127; r4 = u >> 7; }
-                float4 v = ug_load_unit<A_RCONTIG>(g.A, g.lda, i0 + row, g.I, r0 + r4 * 4, rend);
+                ra[q] = ug_load_unit<A_RCONTIG>(g.A, g.lda, i0 + row, g.I, r0 + r4 * 4, rend, vecA);
+            }
+#pragma unroll
+            for (int q = 0; q < UB; ++q) {
+                const int u = tid + q * 256;
+                int row, r4;
+                if (B_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u % TN; r4 = u / TN; }
+                rb[q] = ug_load_unit<B_RCONTIG>(g.B, g.ldb, j0 + row, g.J, r0 + r4 * 4, rend, vecB);
+            }
+        };
+        auto store = [&](float* st, const float4 (&ra)[UA], const float4 (&rb)[UB]) {
+#pragma unroll
+            for (int q = 0; q < UA; ++q) {
+                const int u = tid + q * 256;
+                int row, r4;
+                if (A_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u & 127; r4 = u >> 7; }
+                float4 v = ra[q];
                 if (g.a_swish) { v.x = ug_swish(v.x); v.y = ug_swish(v.y); v.z = ug_swish(v.z); v.w = ug_swish(v.w); }
                 float4 hi, lo;
                 umma::split_tf32(v.x, hi.x, lo.x); umma::split_tf32(v.y, hi.y, lo.y);
@@ -126,12 +149,12 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + A_FLOATS + off) = lo;
             }
-            // B image: TN rows x 8 units
-#pragma unroll 2
-            for (int u = tid; u < TN * 8; u += 256) {
+#pragma unroll
+            for (int q = 0; q < UB; ++q) {
+                const int u = tid + q * 256;
                 int row, r4;
                 if (B_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u % TN; r4 = u / TN; }
-                float4 v = ug_load_unit<B_RCONTIG>(g.B, g.ldb, j0 + row, g.J, r0 + r4 * 4, rend);
+                const float4 v = rb[q];
                 if (MODE == 2) csum += (v.x + v.y) + (v.z + v.w);
                 float4 hi, lo;
                 umma::split_tf32(v.x, hi.x, lo.x); umma::split_tf32(v.y, hi.y, lo.y);
@@ -140,9 +163,25 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
                 *reinterpret_cast<float4*>(st + 2 * A_FLOATS + off) = hi;
                 *reinterpret_cast<float4*>(st + 2 * A_FLOATS + B_FLOATS + off) = lo;
             }
+        };
+        float4 ra0[UA], rb0[UB], ra1[UA], rb1[UB];
+        uint32_t stage = 0, phase = 0;
+        if (n_chunks > 0) fetch(0, ra0, rb0);
+        for (int c = 0; c < n_chunks; c += 2) {
+            if (c + 1 < n_chunks) fetch(c + 1, ra1, rb1);
+            mbar_wait(&empty[stage], phase ^ 1u);
+            store(smem + (size_t)stage * STAGE_FLOATS, ra0, rb0);
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
             umma::mbar_arrive(&full[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (c + 1 < n_chunks) {
+                if (c + 2 < n_chunks) fetch(c + 2, ra0, rb0);
+                mbar_wait(&empty[stage], phase ^ 1u);
+                store(smem + (size_t)stage * STAGE_FLOATS, ra1, rb1);
+                fence_proxy_async_smem();
+                umma::mbar_arrive(&full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
         }
         if (MODE == 2 && g.colsum && blockIdx.x == 0) {
             // in the transposed B loader a thread always serves column (tid % TN) (+ 0 or 128 for TN=128 pairs)
@@ -166,19 +205,45 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
             umma::ld16(umma::taddr(tb, q * 32, TN + n0), w);
             umma::wait_ld();
             if (i < g.I) {
+                float x[16];
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const long long j = j0 + n0 + t;
-                    if (j >= g.J) continue;
-                    float x = v[t] + w[t];
-                    if (MODE == 0) {
-                        if (g.bias) x += g.bias[j];
-                        g.C[i * g.ldc + j] = x;
-                    } else if (MODE == 1) {
-                        if (g.Z) x *= ug_swish_grad(g.Z[i * g.ldz + j]);
-                        g.C[i * g.ldc + j] = x;
-                    } else {
-                        atomicAdd(&g.C[i * g.ldc + j], x);
+                for (int t = 0; t < 16; ++t) x[t] = v[t] + w[t];
+                const long long jb = j0 + n0;
+                const bool full16 = jb + 15 < g.J;
+                if (MODE != 2 && full16 && (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
+                    (MODE != 0 || !g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) &&
+                    (MODE == 0 || !g.Z || ((g.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.Z) & 15) == 0))) {
+                    float4* dst = reinterpret_cast<float4*>(g.C + i * g.ldc + jb);
+#pragma unroll
+                    for (int t4 = 0; t4 < 4; ++t4) {
+                        float4 o = make_float4(x[t4 * 4], x[t4 * 4 + 1], x[t4 * 4 + 2], x[t4 * 4 + 3]);
+                        if (MODE == 0) {
+                            if (g.bias) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + jb) + t4);  // bias + jb is 16B aligned when jb % 4 == 0
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            }
+                        } else if (g.Z) {
+                            const float4 zv = *(reinterpret_cast<const float4*>(g.Z + i * g.ldz + jb) + t4);
+                            o.x *= ug_swish_grad(zv.x); o.y *= ug_swish_grad(zv.y);
+                            o.z *= ug_swish_grad(zv.z); o.w *= ug_swish_grad(zv.w);
+                        }
+                        dst[t4] = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const long long j = jb + t;
+                        if (j >= g.J) continue;
+                        float xv = x[t];
+                        if (MODE == 0) {
+                            if (g.bias) xv += g.bias[j];
+                            g.C[i * g.ldc + j] = xv;
+                        } else if (MODE == 1) {
+                            if (g.Z) xv *= ug_swish_grad(g.Z[i * g.ldz + j]);
+                            g.C[i * g.ldc + j] = xv;
+                        } else {
+                            atomicAdd(&g.C[i * g.ldc + j], xv);
+                        }
                     }
                 }
             }

@@ -401,13 +401,12 @@ __device__ __forceinline__ float squareplus_grad(float a) {  // d/da 0.5*(a + sq
 }
 
 // row: raw theta (3K-1) in shared memory, overwritten by its cotangent.  Returns d/dx.
-__device__ __forceinline__ float rqs_row_backward(float* row, int K, float x, float gy, float gld, const KnotNorm& kn) {
+// KT > 0: K known at compile time (loops unrolled); KT == 0: runtime K.
+template <int KT>
+__device__ __forceinline__ float rqs_row_backward(float* row, int K_rt, float x, float gy, float gld, const KnotNorm& kn) {
+    const int K = KT > 0 ? KT : K_rt;
     RqsBin b;
-    switch (K) {
-        case 16: rqs_locate<16>(row, K, true, x, kn, b); break;
-        case 32: rqs_locate<32>(row, K, true, x, kn, b); break;
-        default: rqs_locate<0>(row, K, true, x, kn, b); break;
-    }
+    rqs_locate<KT>(row, K, true, x, kn, b);
     const int P = 3 * K - 1;
     const bool oob = (x < 0.f) || (x >= 1.f);
     const int idx = b.idx;
@@ -469,25 +468,48 @@ __device__ __forceinline__ float rqs_row_backward(float* row, int K, float x, fl
     const float c_lo = (idx >= 1) ? row[2 * K + idx - 1] : 0.f;
     const float c_hi = (idx + 1 <= K - 1) ? row[2 * K + idx] : 0.f;
 
-    // widths: W_j = kappa*(s_j/S + c); cotangent of W_j is g_xk (j<idx), g_w (j==idx), 0 otherwise
+    // widths / heights: W_j = kappa*(s_j/S + c); cotangent of W_j is g_lt (j<idx), g_at (j==idx), 0 otherwise
     const float kappa = kn.rden;
+#pragma unroll
     for (int blk = 0; blk < 2; ++blk) {
         float* pr = row + blk * K;
         const float g_lt = blk == 0 ? g_xk : g_yk;
         const float g_at = blk == 0 ? g_w : g_h;
         float S = 0.f, Slt = 0.f, s_at = 0.f;
-        for (int j = 0; j < K; ++j) {
-            const float sj = squareplus_rn(pr[j]);
-            S += sj;
-            if (j < idx) Slt += sj;
-            if (j == idx) s_at = sj;
+        constexpr int KS = KT > 0 ? KT : 1;
+        if (KT > 0) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                const float aj = pr[j];
+                const float sj = 0.5f * (aj + sqrtf(fmaf(aj, aj, 4.0f)));   // fp32-tolerance path: plain sqrt
+                S += sj;
+                Slt += (j < idx) ? sj : 0.f;
+                s_at = (j == idx) ? sj : s_at;
+            }
+        } else {
+            for (int j = 0; j < K; ++j) {
+                const float sj = squareplus_rn(pr[j]);
+                S += sj;
+                if (j < idx) Slt += sj;
+                if (j == idx) s_at = sj;
+            }
         }
         const float A = (g_lt * Slt + g_at * s_at) / S;
         const float ks = kappa / S;
-        for (int j = 0; j < K; ++j) {
-            const float a = pr[j];
-            const float gW = (j < idx) ? g_lt : ((j == idx) ? g_at : 0.f);
-            pr[j] = ks * (gW - A) * squareplus_grad(a);
+        if (KT > 0) {
+#pragma unroll
+            for (int j = 0; j < KS; ++j) {
+                const float a = pr[j];
+                const float gW = (j < idx) ? g_lt : ((j == idx) ? g_at : 0.f);
+                // d squareplus/da = 0.5*(1 + a/sqrt(a^2+4)) = s/(2s - a) ... use the rsqrt form
+                pr[j] = ks * (gW - A) * squareplus_grad(a);
+            }
+        } else {
+            for (int j = 0; j < K; ++j) {
+                const float a = pr[j];
+                const float gW = (j < idx) ? g_lt : ((j == idx) ? g_at : 0.f);
+                pr[j] = ks * (gW - A) * squareplus_grad(a);
+            }
         }
     }
     for (int j = 0; j < K - 1; ++j) row[2 * K + j] = 0.f;
@@ -504,31 +526,76 @@ struct SplineBwdArgs {
     float* gx;             // (M, D) out
     long long m0, Mb;
     int D, d, K, rot;
-    int TS;                // samples per tile
+    int TS;                // samples per tile (multiple of 4: tiles are 16-byte multiples)
+    int stages;
+    int use_bulk;
 };
 
+__device__ __forceinline__ void bulk_copy_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// theta tiles stream HBM -> smem ring (bulk copies) -> in-place VJP, one thread per (sample, dim) row ->
+// HBM (bulk store); same pipeline shape as rqs_stage_kernel.
+template <int KT>
 __global__ void __launch_bounds__(256) spline_bwd_kernel(const __grid_constant__ SplineBwdArgs a) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     const int tid = threadIdx.x;
-    const int P = 3 * a.K - 1, Pst = P | 1, d = a.d, D = a.D;
-    const KnotNorm kn = make_knot_norm(a.K);
+    const int K = KT > 0 ? KT : a.K;
+    const int P = 3 * K - 1, d = a.d, D = a.D, S = a.stages;
+    const int R = a.TS * d;
+    const int tile_floats = R * P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)S * tile_floats);
+    const KnotNorm kn = make_knot_norm(K);
     const long long n_tiles = (a.Mb + a.TS - 1) / a.TS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long s0 = tile * a.TS;
-        const int ns = (int)min((long long)a.TS, a.Mb - s0);
-        const int rows = ns * d;
-        float* src = a.theta + s0 * d * P;
-        for (int e = tid; e < rows * P; e += 256) {
-            const int r = e / P, p = e - r * P;
-            sm[r * Pst + p] = src[e];
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto tile_rows = [&](long long tile) { return (int)min((long long)a.TS, a.Mb - tile * a.TS) * d; };
+    auto issue = [&](long long tile, int stage) {
+        const uint32_t bytes = (uint32_t)tile_rows(tile) * P * 4u;
+        if (a.use_bulk && (bytes & 15u) == 0u) {
+            mbar_arrive_expect_tx(&bars[stage], bytes);
+            bulk_copy_g2s(sm + (size_t)stage * tile_floats, a.theta + tile * (long long)R * P, bytes, &bars[stage]);
         }
-        __syncthreads();
+    };
+    if (tid == 0)
+        for (int s = 0; s < S; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < n_tiles) issue(t, s);
+        }
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % S;
+        const uint32_t parity = (uint32_t)(it / S) & 1u;
+        const long long s0 = tile * a.TS;
+        const int rows = tile_rows(tile);
+        const int ns = rows / d;
+        const uint32_t bytes = (uint32_t)rows * P * 4u;
+        const bool bulk = a.use_bulk && (bytes & 15u) == 0u;
+        float* buf = sm + (size_t)stage * tile_floats;
+        float* src = a.theta + s0 * d * P;
+        if (bulk) {
+            mbar_wait(&bars[stage], parity);
+        } else {
+            for (int e = tid; e < rows * P; e += 256) buf[e] = src[e];
+            __syncthreads();
+        }
         for (int r = tid; r < rows; r += 256) {
             const int sidx = r / d, jj = r - sidx * d;
             const long long m = a.m0 + s0 + sidx;
             const float x = a.x_in[m * D + jj];
             const float gy = a.gy[m * D + (jj + a.rot) % D];
-            a.gx[m * D + jj] = rqs_row_backward(sm + r * Pst, a.K, x, gy, a.glp[m], kn);
+            a.gx[m * D + jj] = rqs_row_backward<KT>(buf + (size_t)r * P, K, x, gy, a.glp[m], kn);
         }
         // conditioning columns pass through unchanged: d y[:, j] / d x[:, j] = 1   (bijectors.py:364)
         for (int e = tid; e < ns * (D - d); e += 256) {
@@ -536,12 +603,24 @@ __global__ void __launch_bounds__(256) spline_bwd_kernel(const __grid_constant__
             const long long m = a.m0 + s0 + sidx;
             a.gx[m * D + j] = a.gy[m * D + (j + a.rot) % D];
         }
+        fence_proxy_async_smem();
         __syncthreads();
-        for (int e = tid; e < rows * P; e += 256) {
-            const int r = e / P, p = e - r * P;
-            src[e] = sm[r * Pst + p];
+        if (bulk) {
+            if (tid == 0) {
+                bulk_copy_s2g(src, buf, bytes);
+                bulk_commit();
+                bulk_wait_read<0>();   // the store has read the buffer: it may be refilled
+                const long long next = tile + (long long)S * gridDim.x;
+                if (next < n_tiles) issue(next, stage);
+            }
+        } else {
+            for (int e = tid; e < rows * P; e += 256) src[e] = buf[e];
+            __syncthreads();
+            if (tid == 0) {
+                const long long next = tile + (long long)S * gridDim.x;
+                if (next < n_tiles) issue(next, stage);
+            }
         }
-        __syncthreads();
     }
 }
 
@@ -681,14 +760,17 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
 
-    // spline tile: TS samples x d rows, ~256 rows, bounded by shared memory
-    const int Pst = P | 1;
-    int TS = std::max(1, 256 / d);
-    while (TS > 1 && (size_t)TS * d * Pst * 4 > 160 * 1024) TS /= 2;
-    const size_t sp_smem = (size_t)TS * d * Pst * 4;
-    if (sp_smem > (size_t)di.max_smem_optin)
-        return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
-    ZF_CUDA_CHECK(cudaFuncSetAttribute(spline_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+    // spline tile: TS samples (multiple of 4) x d rows, ~256 rows; two or three ring stages
+    int TS = std::max(4, (256 / d) & ~3);
+    while (TS > 4 && (size_t)TS * d * P * 4 > 96 * 1024) TS -= 4;
+    const size_t tile_bytes = (size_t)TS * d * P * 4;
+    int sp_stages = (int)std::min<size_t>(3, ((size_t)di.max_smem_optin - 256) / tile_bytes);
+    int sp_bps = 1;
+    if (2 * (2 * tile_bytes + 256) + 2048 <= (size_t)di.max_smem_optin) { sp_stages = 2; sp_bps = 2; }
+    if (sp_stages < 1) return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
+    const size_t sp_smem = (size_t)sp_stages * tile_bytes + 64;
+    auto sp_kernel = (K == 16) ? spline_bwd_kernel<16> : (K == 32) ? spline_bwd_kernel<32> : spline_bwd_kernel<0>;
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
 
     ZF_CUDA_CHECK(cudaMemsetAsync(bn_sums, 0, 2 * F * sizeof(double), st));
     float* ws = static_cast<float*>(workspace);
@@ -726,8 +808,10 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             SplineBwdArgs a{};
             a.theta = act[L + 1]; a.x_in = x_in; a.gy = gy; a.glp = glp; a.gx = gx;
             a.m0 = m0; a.Mb = Mb; a.D = D; a.d = d; a.K = K; a.rot = ((gy_rot % D) + D) % D; a.TS = TS;
+            a.stages = sp_stages;
+            a.use_bulk = ((reinterpret_cast<uintptr_t>(a.theta) & 15) == 0) ? 1 : 0;
             const long long tiles = (Mb + TS - 1) / TS;
-            spline_bwd_kernel<<<(unsigned)std::min<long long>(tiles, (long long)di.sm_count * 2), 256, sp_smem, st>>>(a);
+            sp_kernel<<<(unsigned)std::min<long long>(tiles, (long long)di.sm_count * sp_bps), 256, sp_smem, st>>>(a);
             count_launch();
         }
         // backward through the dense layers

@@ -123,14 +123,14 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
             for (int q = 0; q < UA; ++q) {
                 const int u = tid + q * 256;
                 int row, r4;
-                if (A_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u & 127; r4 = u >> 7; }
+                row = u & 127; r4 = u >> 7;  // lanes vary the row: 8 lanes fill one 128-byte core matrix
                 ra[q] = ug_load_unit<A_RCONTIG>(g.A, g.lda, i0 + row, g.I, r0 + r4 * 4, rend, vecA);
             }
 #pragma unroll
             for (int q = 0; q < UB; ++q) {
                 const int u = tid + q * 256;
                 int row, r4;
-                if (B_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u % TN; r4 = u / TN; }
+                row = u % TN; r4 = u / TN;
                 rb[q] = ug_load_unit<B_RCONTIG>(g.B, g.ldb, j0 + row, g.J, r0 + r4 * 4, rend, vecB);
             }
         };
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
             for (int q = 0; q < UA; ++q) {
                 const int u = tid + q * 256;
                 int row, r4;
-                if (A_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u & 127; r4 = u >> 7; }
+                row = u & 127; r4 = u >> 7;  // lanes vary the row: 8 lanes fill one 128-byte core matrix
                 float4 v = ra[q];
                 if (g.a_swish) { v.x = ug_swish(v.x); v.y = ug_swish(v.y); v.z = ug_swish(v.z); v.w = ug_swish(v.w); }
                 float4 hi, lo;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
             for (int q = 0; q < UB; ++q) {
                 const int u = tid + q * 256;
                 int row, r4;
-                if (B_RCONTIG) { r4 = u & 7; row = u >> 3; } else { row = u % TN; r4 = u / TN; }
+                row = u % TN; r4 = u / TN;
                 const float4 v = rb[q];
                 if (MODE == 2) csum += (v.x + v.y) + (v.z + v.w);
                 float4 hi, lo;

@@ -24,7 +24,7 @@ def to64(tree):
     return np.asarray(tree, np.float64)
 
 
-def trained_variables(ops, x, c, seed=0, weight_scale=2.0):
+def trained_variables(ops, x, c, seed=0, weight_scale=2.0):  # noqa: D401
     """Oracle-initialised variables with ShiftBounds/BatchNorm statistics set by one oracle
     train-mode pass over (x, c), BatchNorm params/biases randomised so every term matters."""
     D = x.shape[1]

@@ -187,3 +187,127 @@ def test_batch_permutation_is_bit_exact_at_full_size():
     x2 = chain.apply(v, y, ct, method="inverse")
     inside = (y > 1e-3).all(1) & (y < 1 - 1e-3).all(1)
     assert float((x2 - xt)[inside].abs().max()) < 5e-4 * float(xt.abs().max())
+
+
+def test_empty_and_tiny_batches():
+    """Edge sizes: M = 0, 1 and a ragged tile through both chain kernels."""
+    from zenflow_b200 import Flow
+
+    ops = zo.make_chain(2)
+    rng = np.random.default_rng(0)
+    xs, cs = rng.normal(size=(300, 2)).astype(np.float32), rng.uniform(size=(300, 1)).astype(np.float32)
+    v = trained_variables(ops, xs, cs)
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    assert flow.apply(fv, xs[:0], cs[:0]).shape == (0,)
+    for M in (1, 127, 129):
+        lp = flow.apply(fv, xs[:M], cs[:M])
+        lpo, _ = zo.flow_log_prob(ops, v, xs[:M], cs[:M])
+        np.testing.assert_allclose(lp, lpo, rtol=2e-5, atol=2e-4)
+    y, ld = flow.bijector.apply(v, xs[:0], cs[:0])
+    assert y.shape == (0, 2) and ld.shape == (0,)
+
+
+def test_nan_and_out_of_support_inputs():
+    """flow.py:47: NaN log-probs become finfo.min; values outside the latent support give zero density."""
+    from zenflow_b200 import Flow
+
+    ops = zo.make_chain(2)
+    rng = np.random.default_rng(1)
+    xs = rng.normal(size=(512, 2)).astype(np.float32)
+    v = trained_variables(ops, xs, None)
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    bad = xs.copy()
+    bad[0, 0] = np.nan
+    bad[1, 1] = 1e6   # clipped to the cube's edge by ShiftBounds -> Beta density exactly 0
+    bad[2, 0] = -1e6
+    lp = flow.apply(fv, bad)
+    lpo, _ = zo.flow_log_prob(ops, v, bad)
+    fmin = np.finfo(np.float32).min
+    assert lp[0] == fmin and lp[1] == fmin and lp[2] == fmin
+    assert (lpo[:3] == fmin).all()
+    np.testing.assert_allclose(lp[3:], lpo[3:], rtol=2e-5, atol=2e-4)
+
+
+def test_bounded16_at_full_size():
+    """BASELINE configs[3]: 16-D flow, 8 couplings, K=32 at 16*2^20 events: size-independent properties
+    (batch-permutation bit-exactness on slices, forward/inverse round trip) + oracle parity on the ends."""
+    import torch
+    from zenflow_b200 import Flow
+
+    D, K, M = 16, 32, 16 * 2 ** 20
+    ops = zo.make_chain(D, K, (128, 128), n_couplings=8, roll_shift=2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xt = torch.rand(M, D, device="cuda", generator=g) * 2 - 0.5
+    xs = xt[:4096].cpu().numpy()
+    v = trained_variables(ops, xs, None, weight_scale=1.0)
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    fv = torch.utils._pytree.tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda(), fv)
+    lp = flow.apply(fv, xt)
+    assert lp.shape == (M,)
+    sub = torch.cat([torch.arange(0, 3000), torch.arange(M - 3000, M), torch.randint(0, M, (3000,))]).cuda()
+    assert torch.equal(flow.apply(fv, xt[sub]), lp[sub])          # tiling / scheduling independent
+    ends = np.r_[0:1024, M - 1024:M]
+    xe = xt[ends].cpu().numpy()
+    lp64, _ = zo.flow_log_prob(ops, to64(v), xe.astype(np.float64))
+    lp32, _ = zo.flow_log_prob(ops, v, xe)
+    assert_fp32_parity(lp[ends].cpu().numpy(), lp64, lp32, "log_prob@16M", atol=5e-5, slack=4.0)
+    chain = flow.bijector
+    vb = {"params": fv["params"]["bijector"], "batch_stats": fv["batch_stats"]["bijector"]}
+    y, _ = chain.apply(vb, xt[: 2 ** 20])
+    x2 = chain.apply(vb, y, None, method="inverse")
+    inside = (y > 1e-3).all(1) & (y < 1 - 1e-3).all(1)
+    assert float((x2 - xt[: 2 ** 20])[inside].abs().max()) < 2e-3
+
+
+def test_latent_samplers_moments():
+    """tests/test_distributions.py:39-43,57-61,76-81: sample shapes, moments and support."""
+    from zenflow_b200 import distributions as dist
+
+    for d in (dist.Normal(), dist.TruncatedNormal(), dist.Beta(), dist.Uniform()):
+        d._latch_dim(3)
+        x = d.sample(20000, 0).cpu().numpy()
+        assert x.shape == (20000, 3)
+        np.testing.assert_allclose(x.mean(0), 0.5, atol=5e-2)
+        if isinstance(d, (dist.Normal, dist.TruncatedNormal)):
+            np.testing.assert_allclose(np.cov(x.T), 0.1 ** 2 * np.identity(3), atol=5e-2)
+        if isinstance(d, dist.Beta):
+            assert (x > 0).all() and (x < 1).all()
+        if isinstance(d, dist.Uniform):
+            assert x.min() >= 0 and x.max() < 1
+        x2 = d.sample(16, 0).cpu().numpy()
+        x3 = d.sample(16, 1).cpu().numpy()
+        assert np.array_equal(x2, d.sample(16, 0).cpu().numpy()) and not np.array_equal(x2, x3)  # seeded
+
+
+def test_flow_sample_and_steps():
+    """tests/test_flow.py:7-29 + flow.py:80-95."""
+    from zenflow_b200 import Flow
+    from zenflow_b200.bijectors import ShiftBounds, rolling_spline_coupling
+    from zenflow_b200.distributions import Uniform
+
+    flow = Flow(ShiftBounds(), latent=Uniform())
+    x = np.array([[3.0, 2.0], [1.0, 4.0], [5.0, 6.0]], dtype=np.float32)
+    variables = flow.init(0, x)
+    log_prob, variables = flow.apply(variables, x, train=True, mutable=["batch_stats"])
+    assert log_prob.shape == (3,)
+    x2 = flow.apply(variables, 1000, method="sample").cpu().numpy()
+    assert x2.shape == (1000, 2)
+    assert x2[:, 0].min() >= 1 - 0.21 and x2[:, 0].max() <= 5 + 0.21 and x2[:, 1].min() >= 2 - 0.21
+    c = np.array([1.0, 2.0, 3.0], dtype=np.float32)
+    flow2 = Flow(ShiftBounds(), latent=Uniform())
+    v2 = flow2.init(0, x)
+    _, v2 = flow2.apply(v2, x, c, train=True, mutable=["batch_stats"])
+    assert flow2.apply(v2, c, method="sample").shape == (3, 2)
+    with pytest.raises(ValueError):
+        flow2.apply(v2, x, method="_steps")
+    f3 = Flow(rolling_spline_coupling(2), latent=Uniform())
+    v3 = f3.init(0, x)
+    _, upd = f3.apply(v3, x, train=True, mutable=["batch_stats"])
+    v3 = {"params": v3["params"], "batch_stats": upd["batch_stats"]}
+    steps = f3.apply(v3, x, method="_steps")
+    assert len(steps) == 4 and all(s.shape == (3, 2) for s in steps)
+    back = f3.apply(v3, steps[-1], method="_steps", inverse=True)
+    np.testing.assert_allclose(back[-1], x, rtol=2e-4, atol=2e-4)

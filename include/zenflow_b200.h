@@ -124,7 +124,8 @@ int zf_selftest_exact_math(void* stream, uint64_t* mismatches);
 
 /* Self-test of the tcgen05 building blocks (3xTF32 split GEMM, A in tensor memory, B image in
  * shared memory): out (128, N) = A (128, K) * B (N, K)^T, N % 16 == 0 <= 128, K % 8 == 0 <= 128. */
-int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out);
+int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
+                     int32_t mask_mode /* 0: all lanes; 1: lanes 64-127 keep a 777 sentinel; 2: lanes 0-63 do */);
 
 /* Self-test of the tcgen05 GEMM family used by the train step (zf_umma_gemm.cu), fp32 in/out:
  * mode 0: C[I][J] = opA(A[I][R]) B[R][J] + bias; mode 1: C[I][J] = (A[I][R] B[J][R]^T) * swish'(Z[I][J]);

@@ -18,7 +18,7 @@ def test_umma_3xtf32_gemm(N, K):
     At, Bt = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     out = torch.full((128, N), float("nan"), device="cuda")
     _lib.check(lib.zf_selftest_umma(torch.cuda.current_stream().cuda_stream, At.data_ptr(), Bt.data_ptr(), N, K,
-                                    out.data_ptr()))
+                                    out.data_ptr(), 0))
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     ref64 = A.astype(np.float64) @ B.astype(np.float64).T
@@ -42,7 +42,7 @@ def test_umma_error_budget():
         At, Bt = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
         out = torch.empty((128, N), device="cuda")
         _lib.check(lib.zf_selftest_umma(torch.cuda.current_stream().cuda_stream, At.data_ptr(), Bt.data_ptr(), N, K,
-                                        out.data_ptr()))
+                                        out.data_ptr(), 0))
         return out.cpu().numpy()
 
     def tf32(a):
@@ -112,3 +112,26 @@ def test_umma_gemm_family(mode, I, J, R, a_swish):
     err = np.abs(got - ref).max() / scale
     print(f"\nmode {mode} I={I} J={J} R={R}: max err / max|ref| = {err:.2e}")
     assert err < 5e-6
+
+
+@pytest.mark.parametrize("mask_mode", [1, 2])
+def test_umma_output_lane_mask(mask_mode):
+    """The MMA's output-lane mask: masked tensor-memory lanes keep their previous contents (the half-tile
+    chain kernel relies on it to run two 64-event pipelines on disjoint lanes of the same columns)."""
+    from zenflow_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    N = K = 64
+    A = rng.normal(size=(128, K)).astype(np.float32)
+    B = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    At, Bt = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    out = torch.zeros((128, N), device="cuda")
+    _lib.check(lib.zf_selftest_umma(torch.cuda.current_stream().cuda_stream, At.data_ptr(), Bt.data_ptr(), N, K,
+                                    out.data_ptr(), mask_mode))
+    got = out.cpu().numpy()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    live = slice(0, 64) if mask_mode == 1 else slice(64, 128)
+    kept = slice(64, 128) if mask_mode == 1 else slice(0, 64)
+    assert np.abs(got[live] - ref[live]).max() < 1e-5
+    assert (got[kept] == 777.0).all()

@@ -6,7 +6,7 @@ namespace zf {
 void count_launch();
 
 __global__ void __launch_bounds__(160) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                            int N, int K, float* __restrict__ out) {
+                                                            int N, int K, float* __restrict__ out, int mask_mode) {
     extern __shared__ __align__(128) float sB[];  // hi image then lo image, N*K floats each
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar;
@@ -34,6 +34,10 @@ __global__ void __launch_bounds__(160) umma_selftest_kernel(const float* __restr
             umma::st8(umma::taddr(tb, warp * 32, colAhi + k0), hi);
             umma::st8(umma::taddr(tb, warp * 32, colAlo + k0), lo);
         }
+        if (mask_mode) {  // sentinel in D: masked lanes must keep it
+            float sv[8] = {777.f, 777.f, 777.f, 777.f, 777.f, 777.f, 777.f, 777.f};
+            for (int n0 = 0; n0 < N; n0 += 8) umma::st8(umma::taddr(tb, warp * 32, colD + n0), sv);
+        }
         umma::wait_st();
     }
     fence_proxy_async_smem();  // B images were written through the generic proxy
@@ -48,9 +52,10 @@ __global__ void __launch_bounds__(160) umma_selftest_kernel(const float* __restr
             for (int ks = 0; ks < K / 8; ++ks) {
                 const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, sbo);
                 const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, sbo);
-                umma::mma_tf32_ts(tb + colD, tb + colAlo + ks * 8, dhi, idesc, ks > 0);
-                umma::mma_tf32_ts(tb + colD, tb + colAhi + ks * 8, dlo, idesc, true);
-                umma::mma_tf32_ts(tb + colD, tb + colAhi + ks * 8, dhi, idesc, true);
+                const uint32_t lo_m = mask_mode == 2 ? 0xffffffffu : 0u, hi_m = mask_mode == 1 ? 0xffffffffu : 0u;
+                umma::mma_tf32_ts_masked(tb + colD, tb + colAlo + ks * 8, dhi, idesc, ks > 0, lo_m, lo_m, hi_m, hi_m);
+                umma::mma_tf32_ts_masked(tb + colD, tb + colAhi + ks * 8, dlo, idesc, true, lo_m, lo_m, hi_m, hi_m);
+                umma::mma_tf32_ts_masked(tb + colD, tb + colAhi + ks * 8, dhi, idesc, true, lo_m, lo_m, hi_m, hi_m);
             }
             umma::commit(&bar);
         }
@@ -74,12 +79,13 @@ __global__ void __launch_bounds__(160) umma_selftest_kernel(const float* __restr
 }
 }  // namespace zf
 
-extern "C" int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out) {
+extern "C" int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
+                                int32_t mask_mode) {
     ZF_REQUIRE(A && B && out, "selftest_umma: null argument");
     ZF_REQUIRE(N >= 16 && N <= 128 && N % 16 == 0 && K >= 8 && K <= 128 && K % 8 == 0, "selftest_umma: bad N/K");
     const size_t smem = (size_t)2 * N * K * sizeof(float);
     ZF_CUDA_CHECK(cudaFuncSetAttribute(zf::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    zf::umma_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, N, K, out);
+    zf::umma_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, N, K, out, mask_mode);
     zf::count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;

@@ -830,6 +830,309 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
     if (warp == 9) umma::tmem_dealloc(tb, 512);
 }
 
+// =============================================================================================
+// Two-pipeline variant: tensor memory is full with one tile's operands and accumulators, so a second
+// 128-event tile cannot be in flight and the MMA and epilogue phases of a tile serialise.  Here a CTA
+// runs TWO independent pipelines ("contexts") over 64-event half-tiles that share the same TMEM columns
+// on disjoint lanes (context 0: lanes 0-63, context 1: lanes 64-127).  Every MMA is issued for all 128
+// lanes with the other context's lanes masked out of the write (tcgen05.mma disable-output-lane), so
+// the contexts never touch each other's rows; while one waits for its MMAs the other runs its epilogue.
+// Per context: 4 epilogue warps (lane quarters 2c, 2c+1 x 2 column halves), 1 producer warp with its own
+// 2-stage weight ring, 1 MMA warp, its own barriers and tile-state buffers.  384 threads.
+// =============================================================================================
+constexpr int U2M = 64;           // events per half-tile
+constexpr int U2THREADS = 384;
+constexpr int U2RING = 2;
+enum U2Bar : int { C_FULL = 0, C_EMPTY = 2, C_AREADY = 4, C_DFULL_H = 5, C_DFULL_D = 6, C_DEMPTY_H = 8, C_DEMPTY_D = 9, C_COUNT = 12 };
+
+struct U2Layout {   // per-context shared-memory carve-up in floats (host and device agree through this)
+    int xs, cs, hs, w0, b0, bn, bh, bl, ldx, ring, bars, total;
+};
+__host__ __device__ inline U2Layout u2_layout(int D, int C, int Fmax, int Hmax, int BLmax) {
+    U2Layout l;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 31) / 32 * 32; return r; };
+    l.xs = take(D * U2M); l.cs = take(C * U2M); l.hs = take(Fmax * U2M); l.w0 = take(Fmax * 128); l.b0 = take(128);
+    l.bn = take(96); l.bh = take(Hmax * 128); l.bl = take(BLmax); l.ldx = take(U2M);
+    l.ring = take(U2RING * URING_FLOATS); l.bars = take(2 * C_COUNT);
+    l.total = o;
+    return l;
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(U2THREADS, 1) chain_umma2_kernel(const __grid_constant__ ChainArgs a, int Fmax, int Hmax, int BLmax) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = a.D, C = a.C;
+    const U2Layout L2 = u2_layout(D, C, Fmax, Hmax, BLmax);
+    // role and context of this warp
+    const int ctx = (warp < 8) ? ((warp & 3) >> 1) : ((warp - 8) & 1);
+    float* base = smem + (size_t)ctx * L2.total;
+    float* xs = base + L2.xs;
+    float* cs = base + L2.cs;
+    float* hs = base + L2.hs;
+    float* w0s = base + L2.w0;
+    float* b0s = base + L2.b0;
+    float* bns = base + L2.bn;
+    float* bhs = base + L2.bh;
+    float* bls = base + L2.bl;
+    float* ldx = base + L2.ldx;
+    float* ring = base + L2.ring;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + L2.bars);
+    const StepDesc* steps = reinterpret_cast<const StepDesc*>(a.ws);
+    const float* wsf = a.ws;
+
+    if (tid < 2) {  // one thread per context initialises that context's barriers
+        uint64_t* b = reinterpret_cast<uint64_t*>(smem + (size_t)tid * L2.total + L2.bars);
+        for (int i = 0; i < U2RING; ++i) { mbar_init(&b[C_FULL + i], 1); mbar_init(&b[C_EMPTY + i], 1); }
+        mbar_init(&b[C_AREADY], 128);
+        mbar_init(&b[C_DFULL_H], 1);
+        mbar_init(&b[C_DFULL_D + 0], 1);
+        mbar_init(&b[C_DFULL_D + 1], 1);
+        mbar_init(&b[C_DEMPTY_H], 128);
+        mbar_init(&b[C_DEMPTY_D + 0], 64);
+        mbar_init(&b[C_DEMPTY_D + 1], 64);
+        mbar_fence_init();
+    }
+    if (warp == 10) umma::tmem_alloc(&tmem_slot, 512);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_slot;
+    const long long n_tiles = (a.M + U2M - 1) / U2M;
+    const long long tile0 = 2ll * blockIdx.x + ctx, tstride = 2ll * gridDim.x;
+
+    if (warp == 8 || warp == 9) {
+        // ------------------------------------------------------------------ weight producer of this context
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long tile = tile0; tile < n_tiles; tile += tstride) {
+                for (int si = 0; si < a.n_steps; ++si) {
+                    const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+                    if (s.kind != kStepKindCoupling) continue;
+                    const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                    for (int u = 0; u < (L - 1) + s.d; ++u) {
+                        const bool hid = u < L - 1;
+                        const int N = hid ? 128 : NL;
+                        const float* src = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L] + (size_t)(u - (L - 1)) * NL * 256;
+                        const uint32_t bytes = (uint32_t)N * 256u;
+                        for (int c = 0; c < 4; ++c) {
+                            mbar_wait(&bars[C_EMPTY + stage], phase ^ 1u);
+                            mbar_arrive_expect_tx(&bars[C_FULL + stage], bytes);
+                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, src + (size_t)c * N * 64, bytes,
+                                          &bars[C_FULL + stage]);
+                            if (++stage == U2RING) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 10) {
+        // ------------------------------------------------------------------ MMA issuer of this context
+        const uint32_t mlo = ctx ? 0xffffffffu : 0u, mhi = ctx ? 0u : 0xffffffffu;  // lanes NOT written
+        uint32_t stage = 0, phase = 0, p_ar = 0, p_eh = 0, p_ed0 = 0, p_ed1 = 0;
+        bool hid_pending = false, dim_pending0 = false, dim_pending1 = false;
+        for (long long tile = tile0; tile < n_tiles; tile += tstride) {
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+                if (s.kind != kStepKindCoupling) continue;
+                const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                for (int u = 0; u < (L - 1) + s.d; ++u) {
+                    const bool hid = u < L - 1;
+                    const int N = hid ? 128 : NL;
+                    const int b = hid ? 0 : ((u - (L - 1)) & 1);
+                    if (hid || u == L - 1) { mbar_wait(&bars[C_AREADY], p_ar); p_ar ^= 1u; }
+                    if (hid_pending) { mbar_wait(&bars[C_DEMPTY_H], p_eh); p_eh ^= 1u; hid_pending = false; }
+                    if ((hid || b == 0) && dim_pending0) { mbar_wait(&bars[C_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; dim_pending0 = false; }
+                    if ((hid || b == 1) && dim_pending1) { mbar_wait(&bars[C_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; dim_pending1 = false; }
+                    umma::fence_after_sync();
+                    const uint32_t dmain = tb + 256u + (uint32_t)b * 128u;
+                    const bool split_acc = hid || (2 * NL <= 128);
+                    const uint32_t dcross = hid ? (tb + 384u) : (split_acc ? dmain + (uint32_t)NL : dmain);
+                    const uint32_t idesc = umma::instr_desc_tf32(N);
+                    const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+                    for (int c = 0; c < 4; ++c) {
+                        mbar_wait(&bars[C_FULL + stage], phase);
+                        umma::fence_after_sync();
+                        if (umma::elect_one()) {
+                            const uint32_t bhi = smem_u32(ring + (size_t)stage * URING_FLOATS);
+                            const uint32_t blo = bhi + (uint32_t)N * 128u;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, 128u);
+                                const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, 128u);
+                                const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                                const bool first = (c | ks) == 0;
+                                umma::mma_tf32_ts_masked(dcross, tb + 128u + acol, dhi, idesc, !first, mlo, mlo, mhi, mhi);
+                                umma::mma_tf32_ts_masked(dcross, tb + acol, dlo, idesc, true, mlo, mlo, mhi, mhi);
+                                umma::mma_tf32_ts_masked(dmain, tb + acol, dhi, idesc, split_acc ? !first : true, mlo, mlo, mhi, mhi);
+                            }
+                            umma::commit(&bars[C_EMPTY + stage]);
+                            if (c == 3) umma::commit(&bars[hid ? C_DFULL_H : (C_DFULL_D + b)]);
+                        }
+                        __syncwarp();
+                        if (++stage == U2RING) { stage = 0; phase ^= 1u; }
+                    }
+                    if (hid) hid_pending = true;
+                    else if (b) dim_pending1 = true;
+                    else dim_pending0 = true;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue / SIMT warps of this context
+        const int q = warp & 3, half = warp >> 2;
+        const int m = (q & 1) * 32 + lane;                 // event within the half-tile
+        const int etid = half * 64 + m;                    // 0..127 within the context
+        const uint32_t lane_base = (uint32_t)(q * 32);     // TMEM lane quarter of this warp
+        auto ctx_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + ctx) : "memory"); };
+        uint32_t p_fh = 0, p_fd = 0;
+        for (long long tile = tile0; tile < n_tiles; tile += tstride) {
+            const long long m0 = tile * U2M;
+            const int nm = (int)min((long long)U2M, a.M - m0);
+            const int rot_in = INVERSE ? a.rot_total : 0;
+            for (int e = etid; e < U2M * D; e += 128) {
+                const int mm = e / D, j = e - mm * D;
+                xs[pmod(j - rot_in, D) * U2M + mm] = (mm < nm) ? a.x[m0 * D + e] : 0.5f;
+            }
+            for (int e = etid; e < U2M * C; e += 128) {
+                const int mm = e / C, j = e - mm * C;
+                cs[j * U2M + mm] = (mm < nm) ? a.c[m0 * C + e] : 0.f;
+            }
+            ctx_barrier();
+
+            float ld_acc = 0.f;
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+                if (s.kind == kStepKindShiftBounds) {
+                    if (half == 0) shift_bounds_row<INVERSE>(s, wsf, D, xs, U2M, m, ld_acc);
+                    ctx_barrier();
+                    continue;
+                }
+                const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
+                const int K = s.K, P = 3 * K - 1, NL = ru(P, 16), Pp4 = ru(P, 4);
+                for (int i = etid; i < 3 * F_p; i += 128) bns[i] = wsf[s.off_bn + i];
+                for (int i = etid; i < F * 128; i += 128) w0s[i] = wsf[s.off_W[0] + i];
+                b0s[etid] = wsf[s.off_b[0] + etid];
+                for (int i = etid; i < (L - 1) * 128; i += 128) bhs[i] = wsf[s.off_b[1 + (i >> 7)] + (i & 127)];
+                for (int i = etid; i < d * NL; i += 128) {
+                    const int jj = i / NL, pp = i - jj * NL;
+                    bls[i] = pp < Pp4 ? wsf[s.off_b[L] + jj * Pp4 + pp] : 0.f;
+                }
+                ctx_barrier();
+                for (int f = half; f < F; f += 2) {
+                    const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * U2M + m] : cs[(f - (D - d)) * U2M + m];
+                    hs[f * U2M + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+                }
+                ctx_barrier();
+#pragma unroll 1
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int n0 = half * 64 + nb * 16;
+                    float acc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = b0s[n0 + i];
+                    for (int f = 0; f < F; ++f) {
+                        const float h = hs[f * U2M + m];
+                        const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4) {
+                            const float4 wv = w[g4];
+                            acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
+                            acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
+                            acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
+                            acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
+                        }
+                    }
+                    store_activation16(tb, lane_base, n0, acc);
+                }
+                umma::wait_st();
+                umma::fence_before_sync();
+                umma::mbar_arrive(&bars[C_AREADY]);
+                for (int l = 1; l < L; ++l) {
+                    mbar_wait(&bars[C_DFULL_H], p_fh);
+                    p_fh ^= 1u;
+                    umma::fence_after_sync();
+                    const float* bh = bhs + (l - 1) * 128;
+#pragma unroll 1
+                    for (int nb = 0; nb < 2; ++nb) {
+                        const int n0 = half * 64 + nb * 32;
+                        float v[32], w[32];
+                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);
+                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0 + 16), v + 16);
+                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0), w);
+                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0 + 16), w + 16);
+                        umma::wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = (v[i] + w[i]) + bh[n0 + i];
+                        float lo16[16], hi16[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { lo16[i] = v[i]; hi16[i] = v[16 + i]; }
+                        store_activation16(tb, lane_base, n0, lo16);
+                        store_activation16(tb, lane_base, n0 + 16, hi16);
+                    }
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[C_AREADY]);
+                    umma::mbar_arrive(&bars[C_DEMPTY_H]);
+                }
+                float ldc = 0.f;
+                for (int jj = half; jj < d; jj += 2) {
+                    mbar_wait(&bars[C_DFULL_D + half], p_fd);
+                    p_fd ^= 1u;
+                    umma::fence_after_sync();
+                    const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * 128);
+                    float* px = xs + pmod(jj - rot, D) * U2M + m;
+                    const float v = *px;
+                    RqsBin bin;
+                    auto release = [&]() {
+                        umma::fence_before_sync();
+                        umma::mbar_arrive(&bars[C_DEMPTY_D + half]);
+                    };
+                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, bls + jj * NL, v, bin, release);
+                    else spline_row_tmem<32, INVERSE>(dbase, bls + jj * NL, v, bin, release);
+                    if (!INVERSE) {
+                        float y, ld;
+                        rqs_eval_forward(v, bin, y, ld);
+                        *px = y;
+                        ldc += ld;
+                    } else {
+                        *px = rqs_eval_inverse(v, bin);
+                    }
+                }
+                if (half == 1) ldx[m] = ldc;
+                ctx_barrier();
+                if (half == 0) ld_acc += ldc + ldx[m];
+                ctx_barrier();
+            }
+
+            if (a.mode == kModeLogProb) {
+                if (half == 0 && m < nm) {
+                    float lat = 0.f;
+                    for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * U2M + m], a.lc);
+                    a.lp[m0 + m] = nan_to_num_lp(lat + ld_acc);
+                }
+            } else {
+                const int rot_out = INVERSE ? 0 : a.rot_total;
+                if (a.y) {
+                    for (int e = etid; e < nm * D; e += 128) {
+                        const int mm = e / D, j = e - mm * D;
+                        a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * U2M + mm];
+                    }
+                }
+                if (!INVERSE && a.log_det && half == 0 && m < nm)
+                    a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
+            }
+            ctx_barrier();
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 10) umma::tmem_dealloc(tb, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------
 
 struct Plan {
@@ -839,6 +1142,7 @@ struct Plan {
     size_t ws_floats = 0;
     bool umma_ok = true;   // every coupling fits the tensor-core kernel
     int n_couplings = 0;
+    int Fmax = 1, Hmax = 1, BLmax = 32;   // shared-memory sizing of the two-pipeline kernel
 };
 
 static int build_plan(const zf_chain* chain, Plan& plan) {
@@ -891,6 +1195,9 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
                 for (int l = 0; l < cp.n_hidden; ++l) ok = ok && cp.hidden[l] == 128;
                 job.desc.umma_ok = ok ? 1 : 0;
                 plan.umma_ok = plan.umma_ok && ok;
+                plan.Fmax = std::max(plan.Fmax, D - d + C);
+                plan.Hmax = std::max(plan.Hmax, std::max(1, cp.n_hidden - 1));
+                plan.BLmax = std::max(plan.BLmax, d * ru(3 * cp.knots - 1, 16));
             }
             job.desc.K = cp.knots;
             job.desc.n_hidden = cp.n_hidden;
@@ -1008,6 +1315,24 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     const bool want_umma = plan.umma_ok && plan.n_couplings > 0 && !(impl && impl[0] == 's');
     if (impl && impl[0] == 'u' && !want_umma)
         return fail(ZF_ERR_UNSUPPORTED, "ZF_CHAIN_IMPL=umma but this chain does not fit the tensor-core kernel");
+    if (want_umma && !(impl && impl[0] == 'u' && impl[1] == 'm' && impl[2] == 'm' && impl[3] == 'a' && impl[4] == '1')) {
+        const U2Layout lay = u2_layout(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax);
+        const size_t smem2 = (size_t)2 * lay.total * sizeof(float);
+        if (smem2 + 256 <= (size_t)di.max_smem_optin) {
+            const long long tiles = (M + U2M - 1) / U2M;
+            const unsigned g2 = (unsigned)std::min<long long>((tiles + 1) / 2, (long long)di.sm_count);
+            if (mode == kModeInverse) {
+                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                chain_umma2_kernel<true><<<g2, U2THREADS, smem2, stream>>>(a, plan.Fmax, plan.Hmax, plan.BLmax);
+            } else {
+                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                chain_umma2_kernel<false><<<g2, U2THREADS, smem2, stream>>>(a, plan.Fmax, plan.Hmax, plan.BLmax);
+            }
+            count_launch();
+            ZF_CUDA_CHECK(cudaGetLastError());
+            return ZF_OK;
+        }
+    }
     if (want_umma) {
         const size_t usmem = umma_smem_floats(a.D, a.C) * sizeof(float);
         if (usmem <= (size_t)di.max_smem_optin) {

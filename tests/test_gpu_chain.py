@@ -37,11 +37,12 @@ CONFIGS = [
 ]
 
 
-@pytest.fixture(params=["auto", "simt"])
+@pytest.fixture(params=["auto", "simt", "umma2"])
 def chain_impl(request, monkeypatch):
-    """auto = tensor-core (tcgen05) kernel when the chain fits it, else the FFMA kernel; simt = force FFMA."""
-    if request.param == "simt":
-        monkeypatch.setenv("ZF_CHAIN_IMPL", "simt")
+    """auto = tensor-core (tcgen05) kernel when the chain fits it, else the FFMA kernel; simt = force FFMA;
+    umma2 = the opt-in two-pipeline tensor-core variant (falls back like auto when the chain does not fit)."""
+    if request.param in ("simt", "umma2"):
+        monkeypatch.setenv("ZF_CHAIN_IMPL", request.param)
     else:
         monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
     return request.param
@@ -54,7 +55,7 @@ def test_chain_forward_logprob_inverse(cfg, chain_impl):
     name, D, C, K, layers, ncoup, shift, M = cfg
     # the tensor-core kernel computes the conditioner with 3xTF32 split products: fp32-class, but
     # 22-bit operands and tensor-core accumulation leave ~3x the error of an fp32 FFMA chain
-    tc = chain_impl == "auto"
+    tc = chain_impl != "simt"
     slack, atol_lp = (4.0, 5e-5) if tc else (3.0, LP_ATOL)
     ops = zo.make_chain(D, K, layers, n_couplings=ncoup, roll_shift=shift)
     x, c = _data(M, D, C, seed=len(name))

@@ -22,6 +22,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 namespace zf {
@@ -1315,7 +1316,9 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     const bool want_umma = plan.umma_ok && plan.n_couplings > 0 && !(impl && impl[0] == 's');
     if (impl && impl[0] == 'u' && !want_umma)
         return fail(ZF_ERR_UNSUPPORTED, "ZF_CHAIN_IMPL=umma but this chain does not fit the tensor-core kernel");
-    if (want_umma && !(impl && impl[0] == 'u' && impl[1] == 'm' && impl[2] == 'm' && impl[3] == 'a' && impl[4] == '1')) {
+    // ZF_CHAIN_IMPL=umma2 opts into the two-pipeline variant (measured slower on B200: 602M vs 692M events/s on
+    // two_moons_conditional, 61M vs 80M on the 16-D config - each MMA computes 128 lanes for 64 useful ones)
+    if (want_umma && impl && strcmp(impl, "umma2") == 0) {
         const U2Layout lay = u2_layout(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax);
         const size_t smem2 = (size_t)2 * lay.total * sizeof(float);
         if (smem2 + 256 <= (size_t)di.max_smem_optin) {

@@ -1314,7 +1314,7 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     // tensor-core kernel when every coupling fits it (ZF_CHAIN_IMPL=simt forces the FFMA kernel)
     const char* impl = getenv("ZF_CHAIN_IMPL");
     const bool want_umma = plan.umma_ok && plan.n_couplings > 0 && !(impl && impl[0] == 's');
-    if (impl && impl[0] == 'u' && !want_umma)
+    if (impl && strcmp(impl, "umma") == 0 && !want_umma)
         return fail(ZF_ERR_UNSUPPORTED, "ZF_CHAIN_IMPL=umma but this chain does not fit the tensor-core kernel");
     // ZF_CHAIN_IMPL=umma2 opts into the two-pipeline variant (measured slower on B200: 602M vs 692M events/s on
     // two_moons_conditional, 61M vs 80M on the 16-D config - each MMA computes 128 lanes for 64 useful ones)

@@ -152,6 +152,12 @@ int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t latent_kind, f
                      const float* x, const float* c, int64_t M, float* log_prob, void* workspace,
                      size_t workspace_bytes);
 
+/* Flow.sample(size | conditions, seed), flow.py:50-78: the latent draw (distributions.py samplers;
+ * counter-based Philox streams keyed by (seed, event, column), see zf_rng.cuh) happens inside the
+ * inverse chain kernel's tile load, then bijector.inverse.  x (M,D) out; c (M,C) or NULL. */
+int zf_flow_sample(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness, uint64_t seed,
+                   const float* c, int64_t M, float* x, void* workspace, size_t workspace_bytes);
+
 /* Same as zf_chain_forward but log_det[m] += (this chain's log-det): Chain's running sum
  * (bijectors.py:107-110) when the train step applies the bijectors one phase at a time. */
 int zf_chain_forward_acc(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,

@@ -281,6 +281,21 @@ def test_latent_samplers_moments():
         x2 = d.sample(16, 0).cpu().numpy()
         x3 = d.sample(16, 1).cpu().numpy()
         assert np.array_equal(x2, d.sample(16, 0).cpu().numpy()) and not np.array_equal(x2, x3)  # seeded
+        assert np.array_equal(x2, x[:16])  # counter-based: a draw depends on (seed, row, column) only
+    # distribution shape: Kolmogorov-Smirnov against the closed forms
+    from scipy import stats as sps
+
+    n = 200_000
+    ref = {"normal": sps.norm(0.5, 0.1), "truncnorm": sps.truncnorm(-5, 5, 0.5, 0.1), "beta": sps.beta(12, 12),
+           "uniform": sps.uniform(0, 1)}
+    for d in (dist.Normal(), dist.TruncatedNormal(), dist.Beta(), dist.Uniform(), dist.Beta(2.5)):
+        d._latch_dim(2)
+        x = d.sample(n, 7).cpu().numpy()
+        r = ref[d._kind] if getattr(d, "peakness", 12.0) == 12.0 else sps.beta(d.peakness, d.peakness)
+        for j in range(2):
+            ks = sps.kstest(x[:, j], r.cdf)
+            assert ks.statistic < 4.0 / np.sqrt(n), (d, j, ks)
+        assert abs(np.corrcoef(x.T)[0, 1]) < 0.01  # columns are independent streams
 
 
 def test_flow_sample_and_steps():
@@ -296,6 +311,10 @@ def test_flow_sample_and_steps():
     assert log_prob.shape == (3,)
     x2 = flow.apply(variables, 1000, method="sample").cpu().numpy()
     assert x2.shape == (1000, 2)
+    # the fused pass equals "draw the latent, then bijector.inverse" (flow.py:76-77) bit for bit
+    u = flow.latent.sample(1000, 0)
+    assert np.array_equal(flow.apply(variables, u, method="inverse").cpu().numpy(), x2)
+    assert not np.array_equal(flow.apply(variables, 1000, method="sample", seed=1).cpu().numpy(), x2)
     assert x2[:, 0].min() >= 1 - 0.21 and x2[:, 0].max() <= 5 + 0.21 and x2[:, 1].min() >= 2 - 0.21
     c = np.array([1.0, 2.0, 3.0], dtype=np.float32)
     flow2 = Flow(ShiftBounds(), latent=Uniform())

@@ -147,3 +147,23 @@ class ChainSpec:
         _lib.check(lib.zf_flow_log_prob(stream_ptr(), C.byref(ch), int(latent_kind), float(peakness), ptr(xd),
                                         ptr(cd), M, ptr(lp), ptr(ws), nbytes), "zf_flow_log_prob")
         return lp
+
+    def sample(self, n: int, c, latent_kind: int, peakness: float, seed: int):
+        """Flow.sample: latent draw inside the inverse chain kernel (zf_flow_sample)."""
+        lib = _lib.load()
+        cd = None
+        if self.cdim:
+            if c is None:
+                raise ValueError("this chain is conditional: pass one condition vector per sample")
+            cd = to_device_f32(c, self.device)
+            if cd.ndim == 1:
+                cd = cd.reshape(-1, 1)
+            if cd.shape != (n, self.cdim):
+                raise ValueError(f"c must have shape ({n}, {self.cdim}), got {tuple(cd.shape)}")
+        ch = self._chain()
+        ws, nbytes = self._workspace(lib, ch, n)
+        x = torch.empty((n, self.dim), dtype=torch.float32, device=self.device)
+        _lib.check(lib.zf_flow_sample(stream_ptr(), C.byref(ch), int(latent_kind), float(peakness),
+                                      int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(cd), n, ptr(x), ptr(ws), nbytes),
+                   "zf_flow_sample")
+        return x

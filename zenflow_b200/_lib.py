@@ -98,6 +98,8 @@ SIGNATURES = {
     "zf_chain_workspace_bytes": (C.c_size_t, [C.POINTER(ZfChain), C.c_int64]),
     "zf_chain_forward": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_flow_sample": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_int32, C.c_float, C.c_uint64, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_size_t]),
     "zf_chain_forward_acc": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "zf_shift_bounds_minmax": (C.c_int, [C.c_void_p, C.POINTER(ZfShiftBounds), C.c_void_p, C.c_int64, C.c_int32,

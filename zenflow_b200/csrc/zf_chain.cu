@@ -18,6 +18,7 @@
 #include "zf_common.cuh"
 #include "zf_math.cuh"
 #include "zf_umma.cuh"
+#include "zf_rng.cuh"
 
 #include <float.h>
 #include <math.h>
@@ -179,6 +180,9 @@ struct ChainArgs {
     int act_rows;
     int mode;
     int acc_log_det;    // log_det[m] += instead of =
+    int sample;         // inverse mode: draw z from the latent (seed) instead of reading a.x
+    unsigned long long seed;
+    float peakness;
     LatentConst lc;
 };
 
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
         const int rot_in = INVERSE ? a.rot_total : 0;
         for (int e = tid; e < TM * D; e += kChainThreads) {
             const int m = e / D, j = e - m * D;
-            const float v = (m < nm) ? a.x[m0 * D + e] : 0.5f;
+            const float v = (m < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + m, j) : a.x[m0 * D + e]) : 0.5f;
             xs[pmod(j - rot_in, D) * TM + m] = v;
         }
         for (int e = tid; e < TM * C; e += kChainThreads) {
@@ -687,7 +691,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
             const int rot_in = INVERSE ? a.rot_total : 0;
             for (int e = tid; e < UM * D; e += 256) {
                 const int mm = e / D, j = e - mm * D;
-                xs[pmod(j - rot_in, D) * UM + mm] = (mm < nm) ? a.x[m0 * D + e] : 0.5f;
+                xs[pmod(j - rot_in, D) * UM + mm] =
+                    (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : a.x[m0 * D + e]) : 0.5f;
             }
             for (int e = tid; e < UM * C; e += 256) {
                 const int mm = e / C, j = e - mm * C;
@@ -996,7 +1001,8 @@ __global__ void __launch_bounds__(U2THREADS, 1) chain_umma2_kernel(const __grid_
             const int rot_in = INVERSE ? a.rot_total : 0;
             for (int e = etid; e < U2M * D; e += 128) {
                 const int mm = e / D, j = e - mm * D;
-                xs[pmod(j - rot_in, D) * U2M + mm] = (mm < nm) ? a.x[m0 * D + e] : 0.5f;
+                xs[pmod(j - rot_in, D) * U2M + mm] =
+                    (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : a.x[m0 * D + e]) : 0.5f;
             }
             for (int e = etid; e < U2M * C; e += 128) {
                 const int mm = e / C, j = e - mm * C;
@@ -1275,13 +1281,18 @@ static LatentConst make_latent(int kind, float peakness) {
 
 static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int latent_kind, float peakness,
                      const float* x, const float* c, long long M, float* y, float* log_det, float* lp,
-                     void* workspace, size_t workspace_bytes, int acc_log_det = 0) {
+                     void* workspace, size_t workspace_bytes, int acc_log_det = 0, int sample = 0,
+                     unsigned long long seed = 0) {
     Plan plan;
     if (int rc = build_plan(chain, plan)) return rc;
     ZF_REQUIRE(M >= 0, "M must be >= 0");
     if (M == 0) return ZF_OK;
-    ZF_REQUIRE(x != nullptr, "input tensor is NULL");
+    ZF_REQUIRE(x != nullptr || sample, "input tensor is NULL");
     ZF_REQUIRE(chain->cdim == 0 || c != nullptr, "chain has cdim=%d but c is NULL", chain->cdim);
+    if (sample) {
+        ZF_REQUIRE(latent_kind >= 0 && latent_kind <= 3, "unknown latent kind %d", latent_kind);
+        ZF_REQUIRE(latent_kind != ZF_LATENT_BETA || peakness >= 1.f, "peakness must be at least 1 (distributions.py:96-97)");
+    }
     if (mode == kModeLogProb) {
         ZF_REQUIRE(lp != nullptr, "log_prob output is NULL");
         ZF_REQUIRE(latent_kind >= 0 && latent_kind <= 3, "unknown latent kind %d", latent_kind);
@@ -1309,6 +1320,9 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     a.act_rows = plan.act_rows;
     a.mode = mode;
     a.acc_log_det = acc_log_det;
+    a.sample = sample;
+    a.seed = seed;
+    a.peakness = peakness;
     a.lc = make_latent(latent_kind, peakness);
 
     // tensor-core kernel when every coupling fits it (ZF_CHAIN_IMPL=simt forces the FFMA kernel)
@@ -1399,6 +1413,13 @@ extern "C" int zf_chain_inverse(void* stream, const zf_chain* chain, const float
     ZF_REQUIRE(x != nullptr || M == 0, "output tensor is NULL");
     return zf::run_chain((cudaStream_t)stream, chain, zf::kModeInverse, 0, 0.f, z, c, (long long)M, x, nullptr,
                          nullptr, workspace, workspace_bytes);
+}
+
+extern "C" int zf_flow_sample(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness, uint64_t seed,
+                              const float* c, int64_t M, float* x, void* workspace, size_t workspace_bytes) {
+    ZF_REQUIRE(x != nullptr || M == 0, "output tensor is NULL");
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeInverse, latent_kind, peakness, nullptr, c, (long long)M, x,
+                         nullptr, nullptr, workspace, workspace_bytes, 0, 1, (unsigned long long)seed);
 }
 
 extern "C" int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness,

@@ -1,13 +1,14 @@
 """Base distributions of the flow — host-side mirror of zenflow/distributions.py.
 
 ``log_prob`` runs the latent log-pdf kernel (the same device code the fused
-``Flow.__call__`` pass ends with); ``sample`` draws on the device.  The reference samples
-with ``jax.random`` streams that cannot be reproduced without JAX, so samplers here are
-checked statistically, as the reference's own tests do (tests/test_distributions.py:39-81).
+``Flow.__call__`` pass ends with); ``sample`` draws inside the CUDA library with counter-based
+Philox streams (csrc/zf_rng.cuh).  The reference samples with ``jax.random`` streams that cannot
+be reproduced without JAX, so the samplers are checked statistically, as the reference's own
+tests do (tests/test_distributions.py:39-81).
 """
 from __future__ import annotations
 
-from abc import ABC, abstractmethod
+from abc import ABC
 from typing import Optional
 
 import numpy as np
@@ -15,21 +16,18 @@ import torch
 
 from . import _lib
 from ._chain import ChainSpec
-from ._device import like_input, require_cuda
+from ._device import like_input
 
 __all__ = ["Distribution", "Normal", "TruncatedNormal", "Beta", "Uniform"]
 
 
-def _generator(rngkey, device) -> torch.Generator:
-    g = torch.Generator(device=device)
-    if isinstance(rngkey, torch.Generator):
-        return rngkey
+def _seed_of(rngkey) -> int:
+    """A 64-bit seed from what callers pass as a PRNG key (int, or the words of a jax PRNGKey)."""
     arr = np.asarray(0 if rngkey is None else rngkey).reshape(-1)
     seed = 0
     for v in arr:
-        seed = (seed * 0x9E3779B1 + int(v)) & 0x7FFFFFFFFFFFFFFF
-    g.manual_seed(seed)
-    return g
+        seed = (seed * 0x9E3779B97F4A7C15 + int(v) + 1) & 0xFFFFFFFFFFFFFFFF
+    return seed
 
 
 class Distribution(ABC):
@@ -61,8 +59,14 @@ class Distribution(ABC):
         spec = ChainSpec(x.shape[-1], 0)  # an empty chain: only the latent log-pdf tail runs
         return like_input(spec.log_prob(x, None, kind, peak), x)
 
-    @abstractmethod
-    def sample(self, nsamples: int, rngkey): ...
+    def sample(self, nsamples: int, rngkey=None):
+        """(nsamples, dim) draws on the device: counter-based Philox streams keyed by (seed, row, column)
+        inside the CUDA library (csrc/zf_rng.cuh); needs ``dim`` (latched by an earlier log_prob)."""
+        if self.dim is None:
+            raise ValueError("dim is not set yet: call log_prob (or evaluate the flow) once before sampling")
+        kind, peak = self._native()
+        spec = ChainSpec(self.dim, 0)  # an empty chain: the sampler is the inverse pass's tile load
+        return spec.sample(int(nsamples), None, kind, peak, _seed_of(rngkey))
 
     def __repr__(self):
         """Return string representation."""
@@ -74,26 +78,11 @@ class Normal(Distribution):
 
     _kind = "normal"
 
-    def sample(self, nsamples: int, rngkey=None):
-        dev = require_cuda()
-        z = torch.randn((nsamples, self.dim), generator=_generator(rngkey, dev), device=dev)
-        return 0.5 + 0.1 * z
-
 
 class TruncatedNormal(Distribution):
     """Like :class:`Normal`, but truncated to the interval [0, 1] (distributions.py:65-78)."""
 
     _kind = "truncnorm"
-
-    def sample(self, nsamples: int, rngkey=None):
-        dev = require_cuda()
-        g = _generator(rngkey, dev)
-        # inverse-cdf draw of a standard normal truncated to [-5, 5]
-        lo = 0.5 * (1 + torch.erf(torch.tensor(-5.0 / 2 ** 0.5, device=dev)))
-        hi = 0.5 * (1 + torch.erf(torch.tensor(5.0 / 2 ** 0.5, device=dev)))
-        u = torch.rand((nsamples, self.dim), generator=g, device=dev, dtype=torch.float64)
-        z = torch.erfinv(2 * (lo + u * (hi - lo)) - 1) * 2 ** 0.5
-        return (0.5 + 0.1 * z.clamp(-5, 5)).to(torch.float32)
 
 
 class Beta(Distribution):
@@ -111,16 +100,6 @@ class Beta(Distribution):
     def _native(self):
         return _lib.LATENT_KINDS["beta"], float(self.peakness)
 
-    def sample(self, nsamples: int, rngkey=None):
-        dev = require_cuda()
-        g = _generator(rngkey, dev)
-        # Beta(p, p) = G1 / (G1 + G2) with G ~ Gamma(p) (the construction jax.random.beta uses)
-        conc = torch.full((nsamples, self.dim), float(self.peakness), device=dev)
-        torch.manual_seed(int(g.initial_seed()) & 0x7FFFFFFF)
-        g1 = torch._standard_gamma(conc)
-        g2 = torch._standard_gamma(conc)
-        return g1 / (g1 + g2)
-
     def __repr__(self):
         """Return string representation."""
         return f"{self.__class__.__name__}(peakness={self.peakness})"
@@ -131,6 +110,3 @@ class Uniform(Distribution):
 
     _kind = "uniform"
 
-    def sample(self, nsamples: int, rngkey=None):
-        dev = require_cuda()
-        return torch.rand((nsamples, self.dim), generator=_generator(rngkey, dev), device=dev)

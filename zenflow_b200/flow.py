@@ -66,10 +66,13 @@ class Flow(Module):
             c = _normalize_c(conditions_or_size)
         if self.latent.dim is None:
             raise ValueError("latent.dim is not set yet: evaluate the flow (init/apply) once before sampling")
-        u = self.latent.sample(size, seed)
+        from .distributions import _seed_of
+
         spec = ChainSpec(self.latent.dim, _cdim(c))
         self.bijector._emit(spec, self.scope.child("bijector"))
-        x = spec.inverse(u, c)
+        kind, peak = self.latent._native()
+        # latent.sample(size, PRNGKey(seed)) and bijector.inverse in one fused pass (flow.py:76-77)
+        x = spec.sample(size, c, kind, peak, _seed_of(seed))
         return x if (c is None or isinstance(c, torch.Tensor)) else x.cpu().numpy()
 
     def inverse(self, u, c=None):

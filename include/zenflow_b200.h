@@ -223,6 +223,14 @@ int zf_bn_backward_apply(void* stream, const zf_coupling* cp, int32_t D, int32_t
 int zf_nadamw_update(void* stream, int64_t n, float* params, const float* grads, float* mu, float* nu,
                      int64_t count, float lr, float b1, float b2, float eps, float weight_decay, int32_t nesterov);
 
+/* ---- train() epoch loop helpers (train.py:101-121) ----------------------------------------------
+ * X_perm = X_train[perm] (train.py:104-108): out (N,D) = rows of x (N,D) in a pseudo-random order that
+ * is a permutation of [0,N) fully determined by `seed` (fold the epoch into it); call with the same
+ * seed for x and c to keep rows paired.  Out of place. */
+int zf_permute_rows(void* stream, const float* x, int64_t N, int32_t D, uint64_t seed, float* out);
+/* *out = -sum(lp[0..M)) in double (metric_fn / loss: divide by M, train.py:73,78). */
+int zf_neg_sum(void* stream, const float* lp, int64_t M, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,3 +194,30 @@ def test_bad_input_distribution():
     X = np.column_stack((x, x)).astype(np.float32)
     loss_train = train(flow, X, X, epochs=30, progress=False)[2]
     assert np.all(np.isfinite(loss_train))
+
+
+def test_epoch_shuffle_is_a_permutation():
+    """zf_permute_rows (X_train[perm], train.py:104-108): a permutation of the rows, keyed by the seed,
+    identical row pairing for x and c."""
+    from zenflow_b200 import _lib
+
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for N, D in [(1, 3), (2, 1), (1000, 2), (4097, 16), (100_003, 5)]:
+        x = torch.arange(N * D, dtype=torch.float32, device="cuda").reshape(N, D)
+        c = torch.arange(N, dtype=torch.float32, device="cuda").reshape(N, 1)
+        out, outc, out2 = torch.empty_like(x), torch.empty_like(c), torch.empty_like(x)
+        _lib.check(lib.zf_permute_rows(st, x.data_ptr(), N, D, 42, out.data_ptr()))
+        _lib.check(lib.zf_permute_rows(st, c.data_ptr(), N, 1, 42, outc.data_ptr()))
+        _lib.check(lib.zf_permute_rows(st, x.data_ptr(), N, D, 43, out2.data_ptr()))
+        rows = (out[:, 0] / D).long()
+        assert torch.equal(torch.sort(rows).values, torch.arange(N, device="cuda"))     # a permutation
+        assert torch.equal(out, x[rows]) and torch.equal(outc[:, 0].long(), rows)        # whole rows, same pairing
+        if N > 100:
+            assert not torch.equal(out, out2) and not torch.equal(rows, torch.arange(N, device="cuda"))
+            # well mixed: neighbouring outputs come from far-apart inputs
+            assert float((rows[1:] - rows[:-1]).abs().float().mean()) > N / 5
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lp = torch.randn(100_001, device="cuda")
+    _lib.check(lib.zf_neg_sum(st, lp.data_ptr(), lp.numel(), acc.data_ptr()))
+    assert abs(acc.item() + lp.double().sum().item()) < 1e-6

@@ -646,6 +646,58 @@ __global__ void __launch_bounds__(256) nadamw_kernel(long long n, float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// epoch shuffle (train.py:104-108): X_perm = X_train[perm].  perm is a keyed pseudo-random
+// permutation of [0, N): a 4-round balanced Feistel network on 2h >= log2(N) bits with cycle
+// walking, so row i of the output can be located without materialising or sorting anything.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
+    x ^= k;
+    x *= 0x9E3779B1u; x ^= x >> 15;
+    x *= 0x85EBCA77u; x ^= x >> 13;
+    x *= 0xC2B2AE3Du; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ unsigned long long feistel_perm(unsigned long long i, unsigned long long N, int h, uint4 keys) {
+    const uint32_t mask = (h >= 32) ? 0xffffffffu : ((1u << h) - 1u);
+    unsigned long long v = i;
+    do {
+        uint32_t L = (uint32_t)(v >> h) & mask, R = (uint32_t)v & mask;
+        uint32_t t;
+        t = L ^ (mix32(R, keys.x) & mask); L = R; R = t;
+        t = L ^ (mix32(R, keys.y) & mask); L = R; R = t;
+        t = L ^ (mix32(R, keys.z) & mask); L = R; R = t;
+        t = L ^ (mix32(R, keys.w) & mask); L = R; R = t;
+        v = ((unsigned long long)L << h) | R;
+    } while (v >= N);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) permute_rows_kernel(const float* __restrict__ x, long long N, int D, int h, uint4 keys,
+                                                           float* __restrict__ out) {
+    const long long n = N * D;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / D;
+        const int j = (int)(e - i * D);
+        out[e] = x[feistel_perm((unsigned long long)i, (unsigned long long)N, h, keys) * D + j];
+    }
+}
+
+// -mean over finite-or-not entries exactly as jnp.mean would see them (train.py:73,78)
+__global__ void __launch_bounds__(256) neg_sum_kernel(const float* __restrict__ lp, long long M, double* out) {
+    __shared__ double red[256];
+    double local = 0.0;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x)
+        local -= (double)lp[m];
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+
 static unsigned grid_for(long long n, int per_block, int cap) {
     long long b = (n + per_block - 1) / per_block;
     if (b < 1) b = 1;
@@ -880,6 +932,39 @@ extern "C" int zf_nadamw_update(void* stream, int64_t n, float* params, const fl
     const float bc2_t = (float)(1.0 - pow((double)b2, t));
     nadamw_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(n, params, grads, mu, nu, lr, b1, b2, eps,
                                                                                   weight_decay, bc1_t, bc1_t1, bc2_t, nesterov);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_permute_rows(void* stream, const float* x, int64_t N, int32_t D, uint64_t seed, float* out) {
+    ZF_REQUIRE(N >= 0 && D >= 1, "permute_rows: bad shape");
+    if (N == 0) return ZF_OK;
+    ZF_REQUIRE(x && out && x != out, "permute_rows: null or aliased tensors (the gather is out of place)");
+    int bits = 1;
+    while ((1ull << bits) < (unsigned long long)N) ++bits;
+    const int h = (bits + 1) / 2;
+    // four round keys from the seed (splitmix64)
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull;
+    auto next = [&]() {
+        unsigned long long r = (z += 0x9E3779B97F4A7C15ull);
+        r = (r ^ (r >> 30)) * 0xBF58476D1CE4E5B9ull;
+        r = (r ^ (r >> 27)) * 0x94D049BB133111EBull;
+        return (unsigned)((r ^ (r >> 31)) >> 16);
+    };
+    uint4 keys = make_uint4(next(), next(), next(), next());
+    permute_rows_kernel<<<grid_for(N * D, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, N, D, h, keys, out);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_neg_sum(void* stream, const float* lp, int64_t M, double* out) {
+    ZF_REQUIRE(out != nullptr && M >= 0 && (lp || M == 0), "neg_sum: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ZF_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (M == 0) return ZF_OK;
+    neg_sum_kernel<<<grid_for(M, 256 * 8, 148 * 4), 256, 0, st>>>(lp, M, out);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;

@@ -16,7 +16,8 @@ from typing import List, Optional, Tuple
 import numpy as np
 import torch
 
-from ._device import require_cuda, to_device_f32
+from . import _lib
+from ._device import ptr, require_cuda, stream_ptr, to_device_f32
 from ._train import TrainEngine
 from .flow import Flow
 
@@ -103,9 +104,19 @@ def train(
     engine = TrainEngine(flow, variables, int(X_train.shape[1]), _cdim(C_train), lr=optimizer.learning_rate, b1=optimizer.b1, b2=optimizer.b2,
                          eps=optimizer.eps, weight_decay=optimizer.weight_decay, nesterov=optimizer.nesterov, group=group)
 
+    lib = _lib.load()
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+
     def metric_fn(vs, x, c) -> float:  # train.py:75-78
         lp = flow.apply(vs, x, c)
-        return float(-(lp.double().sum() / lp.shape[0]).item())
+        _lib.check(lib.zf_neg_sum(stream_ptr(), ptr(lp), lp.shape[0], ptr(acc)), "zf_neg_sum")
+        return float(acc.item()) / lp.shape[0]
+
+    def shuffled(t, epoch_seed, out):  # X_train[perm], train.py:104-108
+        tt = t if t.ndim == 2 else t.reshape(-1, 1)
+        _lib.check(lib.zf_permute_rows(stream_ptr(), ptr(tt), tt.shape[0], tt.shape[1], epoch_seed, ptr(out)),
+                   "zf_permute_rows")
+        return out
 
     loss_train: List[float] = []
     loss_test: List[float] = []
@@ -118,15 +129,16 @@ def train(
     else:
         loop = range(epochs)
 
-    gen = torch.Generator(device=dev)
+    X_perm = torch.empty_like(X_train)
+    C_perm = None if C_train is None else torch.empty_like(C_train if C_train.ndim == 2 else C_train.reshape(-1, 1))
     best_epoch = 0
     best_variables = engine.snapshot()
     N = X_train.shape[0]
     for epoch in loop:
-        gen.manual_seed((int(seed) * 1_000_003 + epoch) & 0x7FFFFFFFFFFFFFFF)  # fold_in(iter_key, epoch)
-        perm = torch.randperm(N, generator=gen, device=dev)
-        X_perm = X_train[perm]
-        C_perm = C_train[perm] if C_train is not None else None
+        epoch_seed = (int(seed) * 0x9E3779B97F4A7C15 + epoch + 1) & 0xFFFFFFFFFFFFFFFF  # fold_in(iter_key, epoch)
+        shuffled(X_train, epoch_seed, X_perm)
+        if C_train is not None:
+            shuffled(C_train, epoch_seed, C_perm)
 
         X = C = None
         for batch_idx in range(0, N, batch_size):

@@ -14,6 +14,7 @@
 #include "zf_umma.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace zf {
 
@@ -32,7 +33,7 @@ struct UGemmArgs {
 };
 
 constexpr int UG_THREADS = 288;  // 8 loader/epilogue warps + 1 MMA warp
-constexpr int UG_KC = 32;        // reduction depth per ring stage
+template <int TN> struct UgCfg { static constexpr int KC = (TN == 256) ? 32 : 16; static constexpr int STAGES = (TN == 256) ? 2 : 3; };
 
 __device__ __forceinline__ float ug_swish(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ug_swish_grad(float z) {
@@ -75,11 +76,12 @@ __device__ __forceinline__ float4 ug_load_unit(const float* __restrict__ X, long
 }
 
 template <int MODE, int TN>
-__global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_constant__ UGemmArgs g) {
+__global__ void __launch_bounds__(UG_THREADS, (TN == 256) ? 1 : 2) umma_gemm_kernel(const __grid_constant__ UGemmArgs g) {
+    constexpr int UG_KC = UgCfg<TN>::KC;       // reduction depth per ring stage
     constexpr int A_FLOATS = 128 * UG_KC;      // one image (hi or lo) of the A chunk
     constexpr int B_FLOATS = TN * UG_KC;
     constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
-    constexpr int STAGES = (TN == 256) ? 2 : 3;
+    constexpr int STAGES = UgCfg<TN>::STAGES;
     constexpr bool A_RCONTIG = (MODE != 2);    // NN, NT: A[m][r]; TN: A[r][i]
     constexpr bool B_RCONTIG = (MODE == 1);    // NT: B[k][n] = [j][r]; NN, TN: B[r][j]
 
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
     if (warp < 8) {
         // ------------------------------------------------------------------ loaders
         float csum = 0.f;  // mode 2: column sum of B for this thread's fixed column
-        constexpr int UA = 128 * 8 / 256, UB = TN * 8 / 256;   // 16-byte units per thread per chunk
+        constexpr int R4 = UG_KC / 4;                               // 16-byte units per image row per chunk
+        constexpr int UA = 128 * R4 / 256, UB = TN * R4 / 256;      // units per thread per chunk
         const bool vecA = ((g.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((rbeg & 3) == 0);
         const bool vecB = ((g.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && ((rbeg & 3) == 0);
         // the whole next chunk is fetched into registers while the current one is converted and stored
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
                 const uint32_t a_hi = base, a_lo = base + A_FLOATS * 4u;
                 const uint32_t b_hi = base + 2u * A_FLOATS * 4u, b_lo = b_hi + B_FLOATS * 4u;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < UG_KC / 8; ++ks) {
                     const uint64_t dah = umma::smem_desc_kmajor(a_hi + ks * 2 * lbo_a, lbo_a, 128u);
                     const uint64_t dal = umma::smem_desc_kmajor(a_lo + ks * 2 * lbo_a, lbo_a, 128u);
                     const uint64_t dbh = umma::smem_desc_kmajor(b_hi + ks * 2 * lbo_b, lbo_b, 128u);
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(UG_THREADS, 1) umma_gemm_kernel(const __grid_c
 
 template <int MODE, int TN>
 static int launch_one(cudaStream_t st, const UGemmArgs& g) {
-    constexpr int STAGES = (TN == 256) ? 2 : 3;
+    constexpr int STAGES = UgCfg<TN>::STAGES, UG_KC = UgCfg<TN>::KC;
     const size_t smem = ((size_t)STAGES * (2 * 128 * UG_KC + 2 * TN * UG_KC)) * sizeof(float) + 8 * 8 + 16;
     dim3 grid((unsigned)((g.I + 127) / 128), (unsigned)((g.J + TN - 1) / TN), 1);
     if (MODE == 2) grid.z = (unsigned)((g.R + g.r_slab - 1) / g.r_slab);
@@ -303,7 +306,17 @@ int launch_umma_gemm(cudaStream_t st, int mode, const float* A, long long lda, c
                      long long ldc, const float* bias, float* colsum, const float* Z, long long ldz, int a_swish,
                      long long I, long long J, long long R, long long r_slab) {
     UGemmArgs g{A, lda, B, ldb, C, ldc, bias, colsum, Z, ldz, a_swish, I, J, R, r_slab};
-    const bool wide = J > 128;
+    const char* w = getenv("ZF_GEMM_WIDE");
+    const bool wide = J > 128 && !(w && w[0] == '0');
+    if (mode == 2) {
+        // grad-weight: the output is tiny, the reduction (samples) is split into slabs so that at least
+        // ~3 waves of CTAs are in flight; each CTA adds its partial tile with atomics
+        const long long tiles = ((I + 127) / 128) * ((J + (wide ? 255 : 127)) / (wide ? 256 : 128));
+        long long slabs = std::max<long long>(1, (3 * 148 + tiles - 1) / tiles);
+        long long rs = (R + slabs - 1) / slabs;
+        rs = std::max<long long>(256, (rs + 31) / 32 * 32);
+        g.r_slab = rs;
+    }
     if (mode == 0) return wide ? launch_one<0, 256>(st, g) : launch_one<0, 128>(st, g);
     if (mode == 1) return wide ? launch_one<1, 256>(st, g) : launch_one<1, 128>(st, g);
     return wide ? launch_one<2, 256>(st, g) : launch_one<2, 128>(st, g);

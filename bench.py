@@ -485,7 +485,8 @@ def bench_train(args, world, rank, dev):
             "config": {"workload": "cond16_train", "D": D, "C": C, "K": K, "couplings": n_c, "layers": [128, 128],
                        "optimizer": "nadamw(1e-3)", "collectives": "NCCL all-reduce: ShiftBounds min/max, BatchNorm moments fwd+bwd, flat gradient"},
             "tflops_algorithmic": 3 * flops_fwd * local * world / (ms / steps * 1e-3) / 1e12,
-            "note": "BASELINE configs[4] names 64M/step; this extra uses --train-batch events/step (fp32 FFMA GEMMs this round)"}
+            "note": "BASELINE configs[4] names 64M/step; this extra uses --train-batch events/step; conditioner GEMMs of "
+                    "forward, recompute and VJP on tcgen05 (3xTF32), micro-batches of 262144 events"}
 
 
 def main():

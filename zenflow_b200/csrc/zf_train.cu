@@ -51,15 +51,10 @@ __global__ void __launch_bounds__(256) minmax_kernel(const __grid_constant__ SbC
     if (threadIdx.x < D) { smin[threadIdx.x] = 0xffffffffu; smax[threadIdx.x] = 0u; }
     __syncthreads();
     const long long n = M * D;
-    // a thread always sees the same column when the stride is a multiple of D
-    const long long stride = (long long)gridDim.x * blockDim.x * D;
-    for (int j = 0; j < D; ++j) {
-        // thread handles rows m = gtid, gtid + G, ... for column j (coalescing across j is lost,
-        // this pass is tiny next to the conditioner GEMMs)
-    }
     const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long gsz = (long long)gridDim.x * blockDim.x;
-    (void)stride;
+    // coalesced sweep over the row-major batch; per-column results meet in shared-memory atomics
+    // (this pass is tiny next to the conditioner GEMMs)
     for (long long e = gtid; e < n; e += gsz) {
         const int j = (int)(e % D);
         float v = x[e];

@@ -5,6 +5,7 @@ import numpy as np, torch
 from oracle import zenflow_oracle as zo
 from tests.helpers import product_chain, trained_variables
 from zenflow_b200 import Flow
+from zenflow_b200.distributions import Beta
 from zenflow_b200._train import TrainEngine
 from zenflow_b200.utils import rqs_forward_raw, rqs_inverse_raw
 
@@ -19,7 +20,7 @@ for impl in ("", "simt", "umma2"):
         ops = zo.make_chain(D, K, layers, n_couplings=nc, roll_shift=roll)
         x = rng.normal(0.3, 1.1, (M, D)).astype(np.float32); c = rng.uniform(0, 1, (M, C)).astype(np.float32) if C else None
         v = trained_variables(ops, x, c)
-        flow = Flow(product_chain(ops)); flow.latent._latch_dim(D)
+        flow = Flow(product_chain(ops), latent=Beta()); flow.latent._latch_dim(D)  # fresh latent: the default one is shared
         fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
         flow.apply(fv, x, c); flow.apply(fv, x, c, method="inverse")
         flow.apply(fv, c if C else M, method="sample")
@@ -30,7 +31,7 @@ for gemm in ("", "simt"):
         ops = zo.make_chain(D, K, layers, n_couplings=nc, roll_shift=roll)
         x = rng.normal(0.3, 1.0, (M, D)).astype(np.float32); c = rng.uniform(0, 1, (M, C)).astype(np.float32) if C else None
         v = zo.init_variables(ops, D, C, 2, randomize_bn=True)
-        flow = Flow(product_chain(ops)); flow.latent._latch_dim(D)
+        flow = Flow(product_chain(ops), latent=Beta()); flow.latent._latch_dim(D)  # fresh latent: the default one is shared
         eng = TrainEngine(flow, {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}, D, C, micro_batch=256)
         eng.step(x, c); eng.step(x, c)
 torch.cuda.synchronize()

@@ -54,14 +54,16 @@ __device__ __forceinline__ void st8(uint32_t a, const float (&v)[8]) {
 }
 
 // ---- 3xTF32 split -------------------------------------------------------------------------------
+// hi = x rounded to tf32 (round to nearest, ties away from zero: exactly cvt.rna.tf32.f32, but as two
+// full-rate integer ops instead of a trip through the conversion unit); lo = x - hi is exact in fp32
+// (|lo| <= 2^-11 |x|, at most 13 significant bits) and is handed to the tensor core as is: reading it as
+// tf32 drops at most its last 3 bits, i.e. <= 2^-22 |x|, the same bound as rounding it.
 __device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = to_tf32(x);
-    lo = to_tf32(x - hi);
+    lo = x - hi;
 }
 
 // ---- descriptors ----------------------------------------------------------------------------------

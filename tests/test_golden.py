@@ -1,0 +1,74 @@
+"""Committed golden fixtures (tests/golden/): the reference's KAT vectors and frozen float64-oracle vectors.
+CPU: the oracle still reproduces them.  GPU: the CUDA path matches them through the host API."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import zenflow_oracle as zo
+from tests.helpers import product_chain
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["oracle_two_moons_cond", "oracle_dim5_k7", "oracle_dim16_k32"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = json.loads(str(z["cfg"]))
+    ops = zo.make_chain(cfg["D"], cfg["K"], tuple(cfg["layers"]), n_couplings=cfg["n"], roll_shift=cfg["roll"])
+    v = {"params": {}, "batch_stats": {}}
+    for key in z.files:
+        parts = key.split("/")
+        if parts[0] not in v:
+            continue
+        node = v[parts[0]]
+        for p in parts[1:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = z[key]
+    c = z["c"] if cfg["C"] else None
+    return cfg, ops, v, z, c
+
+
+def test_reference_kats_fixture():
+    k = json.load(open(os.path.join(GOLD, "reference_kats.json")))
+    a = k["_index"]
+    idx, _ = zo.index(np.array(a["x"]).reshape(1, -1), np.array(a["xk"]).reshape(1, -1))
+    assert idx[0, :, 0].tolist() == a["idx"]
+    assert np.allclose(zo.knots(np.array(k["_knots"]["dx"])), k["_knots"]["xk"])
+    assert (zo.roll_forward(np.array(k["roll"]["x"])) == np.array(k["roll"]["z"])).all()
+    sb = k["shift_bounds_margin_0.01"]
+    st = {}
+    zo.shift_bounds_forward(np.array(sb["x"]), st, margin=0.01, train=True)
+    assert np.allclose([st["xmin_0"][0], st["xmin_1"][0]], sb["xmin"]) and np.allclose([st["xmax_0"][0], st["xmax_1"][0]], sb["xmax"])
+    assert abs(-zo._betaln(12, 12) - k["beta_logpdf_norm"]["minus_betaln_12_12"]) < 1e-8
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden(name):
+    """Drift guard: the float32 oracle stays within fp32 tolerance of the frozen float64 vectors."""
+    cfg, ops, v, z, c = load_case(name)
+    lp, _ = zo.flow_log_prob(ops, v, z["x"], c)
+    np.testing.assert_allclose(lp, z["log_prob"], rtol=2e-5, atol=2e-3)
+    y, ld, _ = zo.chain_forward(ops, v, z["x"], c)
+    np.testing.assert_allclose(y, z["y"], atol=2e-5)
+    np.testing.assert_allclose(zo.chain_inverse(ops, v, z["u"], c), z["x_inverse"], atol=3e-4 * np.abs(z["x_inverse"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_golden(name):
+    from zenflow_b200 import Flow
+    from zenflow_b200.distributions import Beta
+
+    cfg, ops, v, z, c = load_case(name)
+    chain = product_chain(ops)
+    flow = Flow(chain, latent=Beta())
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    lp = flow.apply(fv, z["x"], c)
+    np.testing.assert_allclose(lp, z["log_prob"], rtol=2e-5, atol=2e-3)
+    y, ld = chain.apply(v, z["x"], c)
+    np.testing.assert_allclose(y, z["y"], atol=2e-5)
+    np.testing.assert_allclose(ld, z["log_det"], rtol=2e-5, atol=2e-3)
+    xi = chain.apply(v, z["u"], c, method="inverse")
+    np.testing.assert_allclose(xi, z["x_inverse"], atol=3e-4 * np.abs(z["x_inverse"]).max())

@@ -118,49 +118,56 @@ def train(
                    "zf_permute_rows")
         return out
 
-    loss_train: List[float] = []
-    loss_test: List[float] = []
-    if progress:
-        try:
-            from tqdm.auto import tqdm as track
-        except ModuleNotFoundError:  # pragma: no cover
-            from rich.progress import track
-        loop = track(range(epochs))
-    else:
-        loop = range(epochs)
+    history_train: List[float] = []
+    history_test: List[float] = []
+    epoch_iter = _progress_iter(epochs) if progress else range(epochs)
 
     X_perm = torch.empty_like(X_train)
     C_perm = None if C_train is None else torch.empty_like(C_train if C_train.ndim == 2 else C_train.reshape(-1, 1))
-    best_epoch = 0
-    best_variables = engine.snapshot()
-    N = X_train.shape[0]
-    for epoch in loop:
+    best_epoch, best_variables = 0, engine.snapshot()
+    n_rows = X_train.shape[0]
+    for epoch in epoch_iter:
+        # one pass over a fresh shuffle of the training set (train.py:104-117)
         epoch_seed = (int(seed) * 0x9E3779B97F4A7C15 + epoch + 1) & 0xFFFFFFFFFFFFFFFF  # fold_in(iter_key, epoch)
         shuffled(X_train, epoch_seed, X_perm)
         if C_train is not None:
             shuffled(C_train, epoch_seed, C_perm)
+        xb = cb = None
+        for lo in range(0, n_rows, batch_size):
+            xb = X_perm[lo:lo + batch_size]
+            cb = None if C_perm is None else C_perm[lo:lo + batch_size]
+            engine.step(xb, cb)
 
-        X = C = None
-        for batch_idx in range(0, N, batch_size):
-            X = X_perm[batch_idx:batch_idx + batch_size]
-            C = C_perm[batch_idx:batch_idx + batch_size] if C_perm is not None else None
-            engine.step(X, C)
+        # metrics on the last minibatch and on the test set (train.py:119-121)
+        current = engine.variables()
+        history_train.append(metric_fn(current, xb, cb))
+        history_test.append(metric_fn(current, X_test, C_test))
 
-        variables = engine.variables()
-        loss_train.append(metric_fn(variables, X, C))
-        loss_test.append(metric_fn(variables, X_test, C_test))
-
-        if not np.isfinite(loss_train[-1]):
-            msg = f"epoch {epoch}: loss[train] not finite, abort training"
-            warnings.warn(msg, RuntimeWarning)
+        if not np.isfinite(history_train[-1]):  # train.py:123-126
+            warnings.warn(f"epoch {epoch}: loss[train] not finite, abort training", RuntimeWarning)
+            break
+        if history_test[-1] <= history_test[best_epoch]:  # train.py:128-130
+            best_epoch, best_variables = epoch, engine.snapshot()
+        if _should_stop(history_test, epoch, warmup, patience):
             break
 
-        if loss_test[-1] <= loss_test[best_epoch]:
-            best_epoch = epoch
-            best_variables = engine.snapshot()
+    return best_variables, best_epoch, history_train, history_test
 
-        if epoch >= warmup and epoch >= 2 * patience and epoch % patience == 0:
-            if not np.min(loss_test[-patience:]) < np.min(loss_test[-2 * patience:-patience]):
-                break
 
-    return best_variables, best_epoch, loss_train, loss_test
+def _progress_iter(epochs: int):
+    try:
+        from tqdm.auto import tqdm as track
+    except ModuleNotFoundError:  # pragma: no cover
+        from rich.progress import track
+    return track(range(epochs))
+
+
+def _should_stop(history_test: List[float], epoch: int, warmup: int, patience: int) -> bool:
+    """Patience-window early stop (train.py:132-136): every `patience` epochs after the warm-up, stop unless the
+    best test loss of the last window beats the best of the window before it.  Like the reference, a patience that
+    rounds down to 0 (epochs < 20 with the default fraction) divides by zero here."""
+    if epoch < warmup or epoch < 2 * patience or epoch % patience != 0:
+        return False
+    recent = np.min(history_test[-patience:])
+    before = np.min(history_test[-2 * patience:-patience])
+    return not recent < before

@@ -2,6 +2,9 @@
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+if os.environ.get("ZF_LIB"):   # A/B against another build of the library (developer use)
+    from zenflow_b200 import build as _zb
+    _zb.LIB_PATH = os.path.abspath(os.environ["ZF_LIB"]); os.environ["ZENFLOW_B200_NO_BUILD"] = "1"
 from zenflow_b200 import _lib, Flow
 from zenflow_b200.utils import rqs_forward_raw, rqs_inverse_raw
 from zenflow_b200 import bijectors as bi
@@ -16,7 +19,7 @@ def timeit(fn, n=5, warm=2):
     return min(ts), sorted(ts)[len(ts)//2]
 
 out = {}
-for (M, d, K) in [(8_000_000, 1, 16), (2_000_000, 8, 32)]:
+for (M, d, K) in ([] if os.environ.get("QUICK_ONLY_FLOW") else [(8_000_000, 1, 16), (2_000_000, 8, 32)]):
     P = 3*K-1
     theta = torch.randn(M, d, P, device="cuda") * 1.0
     x = torch.rand(M, d, device="cuda")

@@ -50,12 +50,16 @@ struct StepDesc {
     int off_sb;
     int off_U[ZF_MAX_LAYERS + 1];   // tensor-core weight images (3xTF32 hi|lo, K-major core matrices), layers 1..L
     int umma_ok;                    // this coupling fits the tensor-core kernel
-    int pad[4];
+    int off_C;                      // tensor-core kernel: this coupling's small constants as one contiguous block
+    int pad[3];
 };
 static_assert(sizeof(StepDesc) % 16 == 0, "StepDesc must keep the packed blocks 16-byte aligned");
 
+struct UCst { int bn, w0, b0, bh, bl, total; };   // float offsets inside a constant block (ucst_layout)
+
 struct PackJob {
     StepDesc desc;
+    UCst cst;
     int step_index;
     int D;
     // coupling
@@ -142,6 +146,32 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
     // 4 K-chunks of 32, each [hi image | lo image], image = [k/4][n/8][n%8][k%4]  (zf_umma.cuh)
     if (s.umma_ok) {
         const int L = s.n_hidden, P = 3 * s.K - 1, NL = ru(P, 16), d = s.d;
+        {   // the constant block the producer warp fetches with one bulk copy per coupling
+            float* cb = ws + s.off_C;
+            const UCst& cl = job.cst;
+            for (int i = gtid; i < cl.total; i += gsz) {
+                float v = 0.f;
+                if (i < cl.w0) {                       // BatchNorm [mul | mean | bias], F_p each
+                    const int part = i / F_p, f = i - part * F_p;
+                    if (part < 3 && f < F) {
+                        if (part == 0) v = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(job.bn_var[f], 1e-5f))) * job.bn_scale[f];
+                        else v = part == 1 ? job.bn_mean[f] : job.bn_bias[f];
+                    }
+                } else if (i < cl.b0) {                // first Dense kernel [F][128]
+                    const int e = i - cl.w0;
+                    if (e < F * 128) v = job.kernel[0][e];
+                } else if (i < cl.bh) {                // first Dense bias
+                    v = job.bias[0][i - cl.b0];
+                } else if (i < cl.bl) {                // hidden biases, layers 1..L-1
+                    const int e = i - cl.bh, l = 1 + (e >> 7);
+                    if (l < L) v = job.bias[l][e & 127];
+                } else {                               // last-layer bias [d][NL], zero padded
+                    const int e = i - cl.bl, jj = e / NL, pp = e - jj * NL;
+                    if (jj < d && pp < P) v = job.bias[L][jj * P + pp];
+                }
+                cb[i] = v;
+            }
+        }
         for (int l = 1; l <= L; ++l) {
             const float* W = job.kernel[l];
             const int units = (l < L) ? 1 : d;
@@ -184,6 +214,7 @@ struct ChainArgs {
     unsigned long long seed;
     float peakness;
     LatentConst lc;
+    int u_fmax, u_hmax, u_blmax;   // tensor-core kernel: max conditioner inputs / hidden biases / last-layer bias floats
 };
 
 __device__ __forceinline__ int pmod(int a, int D) {
@@ -341,9 +372,9 @@ __device__ __forceinline__ void run_coupling(const StepDesc& s, const float* __r
 // ShiftBounds for one event m of a tile held as xs[col][stride] (bijectors.py:183-207 / :214-238)
 template <bool INVERSE>
 __device__ __forceinline__ void shift_bounds_row(const StepDesc& s, const float* __restrict__ wsf, int D, float* xs,
-                                                 int stride, int m, float& ld_acc) {
+                                                 int stride, int m, float& ld_acc, int i0 = 0, int istep = 1) {
     float ldc = 0.f;
-    for (int i = 0; i < D; ++i) {
+    for (int i = i0; i < D; i += istep) {
         const float* t = wsf + s.off_sb + i * kSbStride;
         const int kind = (int)t[0];
         const float a = t[1], b = t[2], xmin = t[3], xmax = t[4], mul = t[5], logmul = t[6];
@@ -460,17 +491,49 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
 // 3xTF32: x = hi + lo (tf32 each), D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (fp32-class accuracy;
 // a single TF32/BF16 pass would break the rel-1e-5 parity).
 // =============================================================================================
+#ifdef ZF_TRACE   // developer build only (scripts/trace_chain.py): per-phase clock64 stamps of one steady-state tile
+__device__ long long g_zf_trace[4][64];
+#define ZF_TR_DECL int titer_ = -1, tev_ = 0
+#define ZF_TR_TILE do { ++titer_; tev_ = 0; } while (0)
+#define ZF_TRV(slot, v) do { if (blockIdx.x == 0 && titer_ == 8 && lane == 0 && tev_ < 64) g_zf_trace[slot][tev_++] = (v); } while (0)
+#define ZF_TR(slot) do { if (blockIdx.x == 0 && titer_ == 8 && lane == 0 && tev_ < 64) g_zf_trace[slot][tev_++] = clock64(); } while (0)
+#else
+#define ZF_TR_DECL
+#define ZF_TR_TILE
+#define ZF_TR(slot)
+#define ZF_TRV(slot, v)
+#endif
 constexpr int UM = 128;
 constexpr int UTHREADS = 320;
-constexpr int URING = 4;
+#ifndef ZF_URING
+#define ZF_URING 4
+#endif
+constexpr int URING = ZF_URING;   // <= 8 (barrier numbering below)
 constexpr int URING_FLOATS = 8192;  // 32 KB: one K-chunk (32) of a 128-column unit, hi|lo
 constexpr int UFMAX = 32;           // conditioner inputs handled by the SIMT first layer
 constexpr int UDMAX = 32;           // transformed dims
-enum UBar : int { B_FULL = 0, B_EMPTY = 4, B_AREADY = 8, B_DFULL_H = 9, B_DFULL_D = 10, B_DEMPTY_H = 12, B_DEMPTY_D = 13, B_COUNT = 16 };
+// B_AREADY + c: K-chunk c (32 columns) of the current activation version is in tensor memory AND the
+// accumulator columns it was computed from have been read (so they may be overwritten)
+// B_CFULL/B_CEMPTY + b: constant block buffer b;  B_XFULL/B_XEMPTY: the raw rows of the next input tile
+enum UBar : int { B_FULL = 0, B_EMPTY = 8, B_AREADY = 16, B_DFULL_H = 20, B_DFULL_D = 21, B_DEMPTY_D = 23,
+                  B_CFULL = 25, B_CEMPTY = 27, B_XFULL = 29, B_XEMPTY = 30, B_COUNT = 32 };
 
-__host__ __device__ inline size_t umma_smem_floats(int D, int C) {
-    return (size_t)UM * (D + C) + UFMAX * UM + UFMAX * 128 + 128 + 96 + ZF_MAX_LAYERS * 128 + UDMAX * 96 + 128 +
-           (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32;
+// per-coupling constants (BatchNorm affine, first Dense, biases), double-buffered: the next coupling's set is
+// fetched with cp.async while the current one computes
+__host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
+    UCst l;
+    l.bn = 0;
+    l.w0 = ru(3 * ru(Fmax, KC), 32);
+    l.b0 = l.w0 + Fmax * 128;
+    l.bh = l.b0 + 128;
+    l.bl = l.bh + Hmax * 128;
+    l.total = ru(l.bl + BLmax, 32);
+    return l;
+}
+constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer programs read them from global)
+__host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
+    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 128 +
+           (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -492,18 +555,34 @@ __device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_ba
     }
 }
 
-// theta row of this thread's event from a D buffer in tensor memory -> bin parameters
+// the same in two steps, so that a barrier arrival can sit between the arithmetic and the stores
+__device__ __forceinline__ void activation16_compute(const float (&v)[16], float (&hi)[16], float (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) umma::split_tf32(swish_fast(v[i]), hi[i], lo[i]);
+}
+__device__ __forceinline__ void activation16_store(uint32_t tb, uint32_t lane_base, int n0, const float (&hi)[16],
+                                                   const float (&lo)[16]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float th[8], tl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { th[i] = hi[h * 8 + i]; tl[i] = lo[h * 8 + i]; }
+        umma::st8(umma::taddr(tb, lane_base, n0 + h * 8), th);
+        umma::st8(umma::taddr(tb, lane_base, 128 + n0 + h * 8), tl);
+    }
+}
+
 // ---- theta row of this thread's event from a D buffer in tensor memory ---------------------------
 // issue the TMEM loads of one raw K-block (main accumulator, and the separate cross accumulator at
 // +3K when K = 16); tcgen05.wait::ld must follow before the registers are read
 template <int KT>
-__device__ __forceinline__ void theta_block_issue(uint32_t dbase, int col, float (&p)[KT], float (&w)[KT]) {
+__device__ __forceinline__ void theta_block_issue(uint32_t dbase, uint32_t cross_off, int col, float (&p)[KT], float (&w)[KT]) {
     constexpr bool kSplit = (2 * 3 * KT <= 128);
 #pragma unroll
     for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + col + c0, p + c0);
     if (kSplit) {
 #pragma unroll
-        for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + 3 * KT + col + c0, w + c0);
+        for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + cross_off + col + c0, w + c0);
     }
 }
 // main + cross + bias; returns max |theta| of the block (NaN-poisoned to +inf)
@@ -530,22 +609,22 @@ constexpr float kThetaFastBound = 4096.0f;
 // block's TMEM load is in flight while the current one is processed) and the D buffer is handed back to
 // the MMA warp (release()) right after the last load, before the second pass and the spline evaluation.
 template <int KT, bool INVERSE, class Release>
-__device__ __forceinline__ void spline_row_tmem(uint32_t dbase, const float* __restrict__ bias, float v, RqsBin& b,
-                                                Release release) {
+__device__ __forceinline__ void spline_row_tmem(uint32_t dbase, uint32_t cross_off, const float* __restrict__ bias, float v,
+                                                RqsBin& b, Release release) {
     constexpr int cs_ = INVERSE ? KT : 0, co_ = INVERSE ? 0 : KT;
     const KnotNorm kn = make_knot_norm(KT);
     float pa[KT], pb[KT], wa[KT], wb[KT];
     RqsCheck chk;
-    theta_block_issue<KT>(dbase, cs_, pa, wa);
+    theta_block_issue<KT>(dbase, cross_off, cs_, pa, wa);
     umma::wait_ld();
-    theta_block_issue<KT>(dbase, co_, pb, wb);          // in flight during the search pass
+    theta_block_issue<KT>(dbase, cross_off, co_, pb, wb);          // in flight during the search pass
     const float amax_s = theta_block_finish<KT>(cs_, bias, pa, wa);
     if (__any_sync(0xffffffffu, !(amax_s < kThetaFastBound)))
         rqs_block_search<KT, true>(pa, v, kn, b.idx, b.ks, b.bs, chk);
     else
         rqs_block_search<KT, false>(pa, v, kn, b.idx, b.ks, b.bs, chk);
     umma::wait_ld();
-    theta_block_issue<KT>(dbase, 2 * KT, pa, wa);       // slopes reuse the searched block's registers
+    theta_block_issue<KT>(dbase, cross_off, 2 * KT, pa, wa);       // slopes reuse the searched block's registers
     umma::wait_ld();
     release();                                          // every TMEM read of this row is done
     const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
@@ -562,30 +641,38 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = a.D, C = a.C;
-    float* xs = smem;
-    float* cs = xs + D * UM;
-    float* hs = cs + C * UM;
-    float* w0s = hs + UFMAX * UM;
-    float* b0s = w0s + UFMAX * 128;
-    float* bns = b0s + 128;
-    float* bhs = bns + 96;
-    float* bls = bhs + ZF_MAX_LAYERS * 128;
-    float* ldx = bls + UDMAX * 96;
+    const UCst cl = ucst_layout(a.u_fmax, a.u_hmax, a.u_blmax);
+    float* xs = smem;                         // [D][UM]  the tile, feature-major
+    float* cs = xs + D * UM;                  // [C][UM]
+    float* xraw = cs + C * UM;                // [UM][D] | [UM][C]  next tile as it lies in global memory (cp.async)
+    float* hs = xraw + UM * (D + C);          // [Fmax][UM]  BatchNorm output
+    float* cst = hs + a.u_fmax * UM;          // [2][cl.total] per-coupling constants
+    float* ldx = cst + 2 * cl.total;
     float* ring = ldx + 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-    const StepDesc* steps = reinterpret_cast<const StepDesc*>(a.ws);
+    StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
     const float* wsf = a.ws;
+    // the step program is read at every phase boundary by every role: keep it in shared memory
+    const bool steps_fit = a.n_steps <= USTEPS;
+    if (steps_fit) {
+        const int4* src = reinterpret_cast<const int4*>(a.ws);
+        int4* dst = reinterpret_cast<int4*>(steps_s);
+        for (int i = tid; i < a.n_steps * (int)(sizeof(StepDesc) / 16); i += UTHREADS) dst[i] = src[i];
+    }
+    const StepDesc* steps = steps_fit ? steps_s : reinterpret_cast<const StepDesc*>(a.ws);
 
     if (tid == 0) {
         for (int i = 0; i < URING; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-        mbar_init(&bars[B_AREADY], 256);
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[B_AREADY + i], 256);
         mbar_init(&bars[B_DFULL_H], 1);
         mbar_init(&bars[B_DFULL_D + 0], 1);
         mbar_init(&bars[B_DFULL_D + 1], 1);
-        mbar_init(&bars[B_DEMPTY_H], 256);
         mbar_init(&bars[B_DEMPTY_D + 0], 128);
         mbar_init(&bars[B_DEMPTY_D + 1], 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_CFULL + i], 1); mbar_init(&bars[B_CEMPTY + i], 256); }
+        mbar_init(&bars[B_XFULL], 1);
+        mbar_init(&bars[B_XEMPTY], 256);
         mbar_fence_init();
     }
     if (warp == 9) umma::tmem_alloc(tmem_slot, 512);
@@ -594,12 +681,50 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
     umma::fence_after_sync();
     const uint32_t tb = *tmem_slot;
     const long long n_tiles = (a.M + UM - 1) / UM;
+    // Full tiles of 16-byte-aligned inputs are fetched one tile ahead by the producer warp (bulk copies of the raw
+    // rows); the tail tile and unaligned inputs are read by the epilogue warps themselves.
+    const uint32_t in_bytes = (a.sample ? 0u : (uint32_t)(UM * D * 4)) + (uint32_t)(UM * C * 4);
+    const bool in16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
+    auto tile_by_bulk = [&](long long t) { return in16 && in_bytes != 0 && (t + 1) * UM <= a.M; };
+    // the coupling that follows step position `si` in processing order, cyclically (the next tile starts over)
+    auto next_coupling = [&](int si) -> const StepDesc& {
+        for (int k = 1; k <= a.n_steps; ++k) {
+            const int sj = (si + k) % a.n_steps;
+            const StepDesc& t = steps[INVERSE ? (a.n_steps - 1 - sj) : sj];
+            if (t.kind == kStepKindCoupling) return t;
+        }
+        return steps[0];   // not reached: this kernel is only launched for chains with a coupling
+    };
+    int last_coupling_si = 0;
+    for (int si = 0; si < a.n_steps; ++si)
+        if (steps[INVERSE ? (a.n_steps - 1 - si) : si].kind == kStepKindCoupling) last_coupling_si = si;
 
     if (warp == 8) {
-        // ------------------------------------------------------------------ weight producer
+        // ------------------------------------------------------------------ producer: weights, constants, inputs
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, kc = 0, xk = 0;
+            auto issue_consts = [&](const StepDesc& sn) {   // constant block of the kc-th coupling of this CTA
+                const uint32_t b = kc & 1u;
+                mbar_wait(&bars[B_CEMPTY + b], ((kc >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&bars[B_CFULL + b], (uint32_t)cl.total * 4u);
+                bulk_copy_g2s(cst + (size_t)b * cl.total, wsf + sn.off_C, (uint32_t)cl.total * 4u, &bars[B_CFULL + b]);
+                ++kc;
+            };
+            auto issue_inputs = [&](long long t) {
+                if (!tile_by_bulk(t)) return;
+                mbar_wait(&bars[B_XEMPTY], (xk & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&bars[B_XFULL], in_bytes);
+                if (!a.sample) bulk_copy_g2s(xraw, a.x + t * UM * D, (uint32_t)(UM * D * 4), &bars[B_XFULL]);
+                if (C) bulk_copy_g2s(xraw + UM * D, a.c + t * UM * C, (uint32_t)(UM * C * 4), &bars[B_XFULL]);
+                ++xk;
+            };
+            if ((long long)blockIdx.x < n_tiles) {
+                issue_inputs(blockIdx.x);
+                issue_consts(next_coupling(a.n_steps - 1));
+            }
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const bool more_tiles = tile + gridDim.x < n_tiles;
+                bool inputs_pending = more_tiles;
                 for (int si = 0; si < a.n_steps; ++si) {
                     const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
                     if (s.kind != kStepKindCoupling) continue;
@@ -616,6 +741,12 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                                           &bars[B_FULL + stage]);
                             if (++stage == URING) { stage = 0; phase ^= 1u; }
                         }
+                        if (u == 0) {
+                            // behind this coupling's first unit: the next coupling's constants (their buffer is
+                            // released when the previous coupling ends) and, once per tile, the next tile's rows
+                            if (si != last_coupling_si || more_tiles) issue_consts(next_coupling(si));
+                            if (inputs_pending) { issue_inputs(tile + gridDim.x); inputs_pending = false; }
+                        }
                     }
                 }
             }
@@ -626,11 +757,18 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
         // The tensor core's fp32 accumulator truncates at every accumulate step (measured: -2.3e-8 relative
         // per step, tests/test_gpu_umma.py), so the two small cross products (2^-11 of the main one) go to
         // their own accumulator wherever tensor memory has room: hidden layers main -> D0, cross -> D1;
-        // last-layer dims with 2*NL <= 128 (K = 16) main -> [0,NL), cross -> [NL,2NL) of their buffer.
-        uint32_t stage = 0, phase = 0, p_ar = 0, p_eh = 0, p_ed0 = 0, p_ed1 = 0;
-        bool hid_pending = false;      // both buffers hold an undrained hidden-layer result
+        // last-layer dims with NL <= 64 (K = 16) main -> D0[64b, 64b+NL), cross -> D1[64b, 64b+NL) (b = dim & 1);
+        // wider ones (K = 32) have no room for a cross accumulator and use D0 / D1 whole.
+        // The epilogue publishes a new activation version one 32-column K-chunk at a time (B_AREADY + c), and the
+        // MMAs of chunk c are issued as soon as it has arrived, so the layer's GEMM runs underneath the
+        // bias/swish/split of the chunks behind it.  The arrival of chunk c also says that accumulator columns
+        // [32c, 32c+32) of D0 and D1 have been drained, which is what lets the first last-layer unit start
+        // before the hidden epilogue has finished (it only needs the columns it overwrites to be free).
+        uint32_t stage = 0, phase = 0, p_ar = 0, p_ed0 = 0, p_ed1 = 0;
         bool dim_pending0 = false, dim_pending1 = false;
+        ZF_TR_DECL;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ZF_TR_TILE;
             for (int si = 0; si < a.n_steps; ++si) {
                 const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
                 if (s.kind != kStepKindCoupling) continue;
@@ -639,21 +777,46 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                     const bool hid = u < L - 1;
                     const int N = hid ? 128 : NL;
                     const int b = hid ? 0 : ((u - (L - 1)) & 1);
-                    if (hid || u == L - 1) {  // a new version of the activations
-                        mbar_wait(&bars[B_AREADY], p_ar);
-                        p_ar ^= 1u;
-                    }
-                    if (hid_pending) { mbar_wait(&bars[B_DEMPTY_H], p_eh); p_eh ^= 1u; hid_pending = false; }
+                    ZF_TR(2);
+                    const bool newver = hid || u == L - 1;   // this unit reads a new version of the activations
+                    const bool split_acc = hid || NL <= 64;
+                    // chunks that must have arrived before the first MMA: those whose accumulator columns this unit
+                    // overwrites (u == 0 follows the SIMT first layer: nothing to drain)
+                    const int nfree = (u == 0) ? 0 : (hid ? 4 : (split_acc ? 2 : 3));
+                    int waited = 0;
+#ifdef ZF_TRACE
+                    long long w_pend = clock64(), w_full = 0, w_a = 0;
+#endif
                     if ((hid || b == 0) && dim_pending0) { mbar_wait(&bars[B_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; dim_pending0 = false; }
                     if ((hid || b == 1) && dim_pending1) { mbar_wait(&bars[B_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; dim_pending1 = false; }
                     umma::fence_after_sync();
-                    const uint32_t dmain = tb + 256u + (uint32_t)b * 128u;
-                    const bool split_acc = hid || (2 * NL <= 128);
-                    const uint32_t dcross = hid ? (tb + 384u) : (split_acc ? dmain + (uint32_t)NL : dmain);
+#ifdef ZF_TRACE
+                    w_pend = clock64() - w_pend;
+#endif
+                    const uint32_t dmain = hid ? tb + 256u : (split_acc ? tb + 256u + (uint32_t)b * 64u : tb + 256u + (uint32_t)b * 128u);
+                    const uint32_t dcross = split_acc ? dmain + 128u : dmain;
                     const uint32_t idesc = umma::instr_desc_tf32(N);
                     const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+#pragma unroll
                     for (int c = 0; c < 4; ++c) {
+#ifdef ZF_TRACE
+                        long long t_a = clock64();
+#endif
+                        if (newver) {
+                            const int need = max(c + 1, nfree);
+#pragma unroll
+                            for (int w = 0; w < 4; ++w)
+                                if (w >= waited && w < need) mbar_wait(&bars[B_AREADY + w], p_ar);
+                            waited = max(waited, need);
+                        }
+#ifdef ZF_TRACE
+                        long long t_f = clock64();
+                        w_a += t_f - t_a;
+#endif
                         mbar_wait(&bars[B_FULL + stage], phase);
+#ifdef ZF_TRACE
+                        w_full += clock64() - t_f;
+#endif
                         umma::fence_after_sync();
                         if (umma::elect_one()) {
                             const uint32_t bhi = smem_u32(ring + (size_t)stage * URING_FLOATS);
@@ -674,9 +837,10 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                         __syncwarp();
                         if (++stage == URING) { stage = 0; phase ^= 1u; }
                     }
-                    if (hid) hid_pending = true;
-                    else if (b) dim_pending1 = true;
-                    else dim_pending0 = true;
+                    ZF_TR(2);
+                    ZF_TRV(2, -w_pend); ZF_TRV(2, -w_a); ZF_TRV(2, -w_full);
+                    if (newver) p_ar ^= 1u;
+                    if (!hid) { if (b) dim_pending1 = true; else dim_pending0 = true; }
                 }
             }
         }
@@ -685,52 +849,82 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32);
         uint32_t p_fh = 0, p_fd = 0;
+        ZF_TR_DECL;
+#ifdef ZF_TRACE
+        const int trs = (warp == 0) ? 0 : (warp == 4 ? 1 : 3);
+#endif
+        const int rot_in = INVERSE ? a.rot_total : 0;
+        uint32_t ke = 0, xk = 0;   // couplings / bulk-fetched tiles consumed so far (barrier phases)
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ZF_TR_TILE;
+            ZF_TR(trs);
             const long long m0 = tile * UM;
             const int nm = (int)min((long long)UM, a.M - m0);
-            const int rot_in = INVERSE ? a.rot_total : 0;
-            for (int e = tid; e < UM * D; e += 256) {
-                const int mm = e / D, j = e - mm * D;
-                xs[pmod(j - rot_in, D) * UM + mm] =
-                    (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : a.x[m0 * D + e]) : 0.5f;
+            // rows -> feature-major tile; padding events sit at 0.5 / 0 and are never stored
+            const bool bulk = tile_by_bulk(tile);
+            if (bulk) mbar_wait(&bars[B_XFULL], xk & 1u);
+            const float* xsrc = bulk ? xraw : a.x + m0 * D;
+            const float* csrc = bulk ? xraw + UM * D : a.c + m0 * C;
+            {   // element e = mm * D + j, advanced by 256 per round without dividing
+                int mm = tid / D, j = tid - mm * D;
+                const int dm = 256 / D, dj = 256 - dm * D;
+                for (int e = tid; e < UM * D; e += 256) {
+                    int col = j - rot_in;
+                    if (col < 0) col += D;
+                    xs[col * UM + mm] =
+                        (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : xsrc[e]) : 0.5f;
+                    mm += dm; j += dj;
+                    if (j >= D) { j -= D; ++mm; }
+                }
             }
-            for (int e = tid; e < UM * C; e += 256) {
-                const int mm = e / C, j = e - mm * C;
-                cs[j * UM + mm] = (mm < nm) ? a.c[m0 * C + e] : 0.f;
+            if (C) {
+                int mm = tid / C, j = tid - mm * C;
+                const int dm = 256 / C, dj = 256 - dm * C;
+                for (int e = tid; e < UM * C; e += 256) {
+                    cs[j * UM + mm] = (mm < nm) ? csrc[e] : 0.f;
+                    mm += dm; j += dj;
+                    if (j >= C) { j -= C; ++mm; }
+                }
             }
+            if (bulk) { umma::mbar_arrive(&bars[B_XEMPTY]); ++xk; }
             epi_barrier();
+            ZF_TR(trs);   // 1: inputs loaded
 
             float ld_acc = 0.f;
             for (int si = 0; si < a.n_steps; ++si) {
                 const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
                 if (s.kind == kStepKindShiftBounds) {
-                    if (half == 0) shift_bounds_row<INVERSE>(s, wsf, D, xs, UM, m, ld_acc);
+                    // columns split between the two halves; half 1 hands its log-det share over through ldx
+                    float ld_sb = 0.f;
+                    shift_bounds_row<INVERSE>(s, wsf, D, xs, UM, m, ld_sb, half, 2);
+                    if (half == 1) ldx[m] = ld_sb;
                     epi_barrier();
+                    if (half == 0) ld_acc += ld_sb + ldx[m];
+                    epi_barrier();
+                    ZF_TR(trs);   // shift bounds done
                     continue;
                 }
                 const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
-                const int K = s.K, P = 3 * K - 1, NL = ru(P, 16), Pp4 = ru(P, 4);
-                // ---- stage this coupling's small constants
-                for (int i = tid; i < 3 * F_p; i += 256) bns[i] = wsf[s.off_bn + i];
-                for (int i = tid; i < F * 128; i += 256) w0s[i] = wsf[s.off_W[0] + i];
-                if (tid < 128) b0s[tid] = wsf[s.off_b[0] + tid];
-                for (int i = tid; i < (L - 1) * 128; i += 256) bhs[i] = wsf[s.off_b[1 + (i >> 7)] + (i & 127)];
-                for (int i = tid; i < d * NL; i += 256) {
-                    const int jj = i / NL, pp = i - jj * NL;
-                    bls[i] = pp < Pp4 ? wsf[s.off_b[L] + jj * Pp4 + pp] : 0.f;
-                }
-                epi_barrier();
+                const int K = s.K, P = 3 * K - 1, NL = ru(P, 16);
+                // ---- this coupling's constants: fetched by the producer warp into buffer ke & 1
+                const uint32_t cb = ke & 1u;
+                const float* cc = cst + (size_t)cb * cl.total;
+                const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh, *bls = cc + cl.bl;
+                mbar_wait(&bars[B_CFULL + cb], (ke >> 1) & 1u);
+                ZF_TR(trs);   // constants staged
                 // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342); halves share the features
                 for (int f = half; f < F; f += 2) {
                     const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
                     hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
                 }
                 epi_barrier();
+                ZF_TR(trs);   // batch norm done
                 // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
+                // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
 #pragma unroll 1
-                for (int nb = 0; nb < 4; ++nb) {
-                    const int n0 = half * 64 + nb * 16;
-                    float acc[16];
+                for (int c = 0; c < 4; ++c) {
+                    const int n0 = c * 32 + half * 16;
+                    float acc[16], ahi[16], alo[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[i] = b0s[n0 + i];
                     for (int f = 0; f < F; ++f) {
@@ -745,38 +939,43 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                             acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
                         }
                     }
-                    store_activation16(tb, lane_base, n0, acc);
+                    activation16_compute(acc, ahi, alo);
+                    activation16_store(tb, lane_base, n0, ahi, alo);
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_AREADY + c]);
                 }
-                umma::wait_st();
-                umma::fence_before_sync();
-                umma::mbar_arrive(&bars[B_AREADY]);
+                ZF_TR(trs);   // first dense done
                 // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
                 for (int l = 1; l < L; ++l) {
                     mbar_wait(&bars[B_DFULL_H], p_fh);
                     p_fh ^= 1u;
                     umma::fence_after_sync();
+                    ZF_TR(trs);   // hidden accumulator ready
                     const float* bh = bhs + (l - 1) * 128;
+                    // chunk c: accumulator columns [32c + 16 half, +16) -> the same columns of the next activations.
+                    // The TMEM loads of chunk c+1 are in flight during the arithmetic of chunk c.
+                    float vn[16], wn[16];
+                    umma::ld16(umma::taddr(tb, lane_base, 256 + half * 16), vn);        // main products
+                    umma::ld16(umma::taddr(tb, lane_base, 384 + half * 16), wn);        // cross products
 #pragma unroll 1
-                    for (int nb = 0; nb < 2; ++nb) {  // 32 columns per round: four TMEM loads in flight
-                        const int n0 = half * 64 + nb * 32;
-                        float v[32], w[32];
-                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);        // main products
-                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0 + 16), v + 16);
-                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0), w);        // cross products
-                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0 + 16), w + 16);
+                    for (int c = 0; c < 4; ++c) {
+                        const int n0 = c * 32 + half * 16;
+                        float v[16], ahi[16], alo[16];
                         umma::wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = (v[i] + w[i]) + bh[n0 + i];
-                        float lo16[16], hi16[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { lo16[i] = v[i]; hi16[i] = v[16 + i]; }
-                        store_activation16(tb, lane_base, n0, lo16);
-                        store_activation16(tb, lane_base, n0 + 16, hi16);
+                        for (int i = 0; i < 16; ++i) v[i] = (vn[i] + wn[i]) + bh[n0 + i];
+                        if (c < 3) {
+                            umma::ld16(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
+                            umma::ld16(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);
+                        }
+                        activation16_compute(v, ahi, alo);
+                        activation16_store(tb, lane_base, n0, ahi, alo);
+                        umma::wait_st();
+                        umma::fence_before_sync();
+                        umma::mbar_arrive(&bars[B_AREADY + c]);
                     }
-                    umma::wait_st();
-                    umma::fence_before_sync();
-                    umma::mbar_arrive(&bars[B_AREADY]);
-                    umma::mbar_arrive(&bars[B_DEMPTY_H]);
+                    ZF_TR(trs);   // hidden epilogue done
                 }
                 // ---- last layer: theta of one transformed dim at a time, read from tensor memory
                 float ldc = 0.f;
@@ -784,16 +983,18 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                     mbar_wait(&bars[B_DFULL_D + half], p_fd);
                     p_fd ^= 1u;
                     umma::fence_after_sync();
-                    const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * 128);
+                    ZF_TR(trs);   // theta ready
+                    const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * (K == 16 ? 64 : 128));
                     float* px = xs + pmod(jj - rot, D) * UM + m;
                     const float v = *px;
                     RqsBin bin;
                     auto release = [&]() {
                         umma::fence_before_sync();
                         umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                        ZF_TR(trs);   // released
                     };
-                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, bls + jj * NL, v, bin, release);
-                    else spline_row_tmem<32, INVERSE>(dbase, bls + jj * NL, v, bin, release);
+                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls + jj * NL, v, bin, release);
+                    else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
                     if (!INVERSE) {
                         float y, ld;
                         rqs_eval_forward(v, bin, y, ld);
@@ -803,10 +1004,14 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                         *px = rqs_eval_inverse(v, bin);
                     }
                 }
+                ZF_TR(trs);   // spline rows done
+                umma::mbar_arrive(&bars[B_CEMPTY + cb]);   // last read of this coupling's constants
+                ++ke;
                 if (half == 1) ldx[m] = ldc;
                 epi_barrier();
                 if (half == 0) ld_acc += ldc + ldx[m];
                 epi_barrier();
+                ZF_TR(trs);   // coupling done
             }
 
             // ---- store
@@ -828,6 +1033,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                     a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
             }
             epi_barrier();
+            ZF_TR(trs);   // tile stored
         }
     }
 
@@ -1097,8 +1303,8 @@ __global__ void __launch_bounds__(U2THREADS, 1) chain_umma2_kernel(const __grid_
                         umma::fence_before_sync();
                         umma::mbar_arrive(&bars[C_DEMPTY_D + half]);
                     };
-                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, bls + jj * NL, v, bin, release);
-                    else spline_row_tmem<32, INVERSE>(dbase, bls + jj * NL, v, bin, release);
+                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 48u, bls + jj * NL, v, bin, release);
+                    else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
                     if (!INVERSE) {
                         float y, ld;
                         rqs_eval_forward(v, bin, y, ld);
@@ -1261,6 +1467,8 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
                 off = (off + 31) / 32 * 32;  // images are fetched by 16-byte-aligned bulk copies
                 for (int l = 1; l < L; ++l) s.off_U[l] = take((size_t)128 * 256);
                 s.off_U[L] = take((size_t)s.d * NL * 256);
+                job.cst = ucst_layout(plan.Fmax, plan.Hmax, plan.BLmax);
+                s.off_C = take((size_t)job.cst.total);
             }
         }
         if (off > (size_t)0x7fffffff) return fail(ZF_ERR_UNSUPPORTED, "packed parameters exceed 2^31 floats");
@@ -1351,7 +1559,10 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
         }
     }
     if (want_umma) {
-        const size_t usmem = umma_smem_floats(a.D, a.C) * sizeof(float);
+        a.u_fmax = plan.Fmax;
+        a.u_hmax = plan.Hmax;
+        a.u_blmax = plan.BLmax;
+        const size_t usmem = umma_smem_floats(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax) * sizeof(float);
         if (usmem <= (size_t)di.max_smem_optin) {
             const long long tiles = (M + UM - 1) / UM;
             const unsigned ugrid = (unsigned)std::min<long long>(tiles, (long long)di.sm_count);
@@ -1428,3 +1639,9 @@ extern "C" int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t lat
     return zf::run_chain((cudaStream_t)stream, chain, zf::kModeLogProb, latent_kind, peakness, x, c, (long long)M,
                          nullptr, nullptr, log_prob, workspace, workspace_bytes);
 }
+
+#ifdef ZF_TRACE
+extern "C" int zf_debug_trace_read(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, zf::g_zf_trace, sizeof(long long) * 4 * 64);
+}
+#endif

@@ -90,3 +90,94 @@ extern "C" int zf_selftest_umma(void* stream, const float* A, const float* B, in
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;
 }
+
+#ifdef ZF_TRACE
+// Developer microbenchmark (scripts/umma_rate.py, -DZF_TRACE builds only): cycles per tcgen05.mma for the shapes the
+// chain kernel issues.  mode 0: every product into one accumulator; 1: cross products into a second accumulator;
+// bit 2 (mode | 4): four more warps keep reading the accumulator with tcgen05.ld while the MMAs run.
+namespace zf {
+__global__ void __launch_bounds__(192) umma_rate_kernel(int N, int reps, int mode, long long* out) {
+    extern __shared__ __align__(128) float sB[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 4) umma::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
+    for (int e = tid; e < 2 * N * 32; e += blockDim.x) sB[e] = 0.f;
+    fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    if (warp < 4) {
+        float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 512; c += 8) umma::st8(umma::taddr(tb, warp * 32, c), z);
+        umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (warp == 4) {
+        if (umma::elect_one()) {
+            const uint32_t idesc = umma::instr_desc_tf32(N);
+            const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+            const uint32_t bhi = smem_u32(sB), blo = bhi + (uint32_t)N * 128u;
+            const uint32_t dmain = tb + 256u, dcross = (mode & 1) ? tb + 384u : dmain;
+            const long long t0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, 128u);
+                        const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, 128u);
+                        const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                        if (mode & 2) {   // one product only (plain TF32)
+                            umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, true);
+                        } else {
+                            umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, true);
+                            umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);
+                            umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, true);
+                        }
+                    }
+                }
+            }
+            const long long t1 = clock64();
+            umma::commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t2 = clock64();
+            out[0] = t1 - t0;   // issue
+            out[1] = t2 - t0;   // issue + drain
+            stop = 1;
+        }
+        __syncwarp();
+    } else if (warp < 4 && (mode & 4)) {
+        float v[16];
+        float acc = 0.f;
+        while (!stop) {
+            umma::ld16(umma::taddr(tb, warp * 32, 256 + (lane & 1) * 16), v);
+            umma::wait_ld();
+            acc += v[0];
+        }
+        if (acc == 123.f) out[2] = 1;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) umma::tmem_dealloc(tb, 512);
+}
+}  // namespace zf
+
+extern "C" int zf_debug_umma_rate(int32_t N, int32_t reps, int32_t mode, int32_t ctas, long long* host_out) {
+    long long* d = nullptr;
+    if (cudaMalloc(&d, 4 * sizeof(long long)) != cudaSuccess) return 1;
+    cudaMemset(d, 0, 4 * sizeof(long long));
+    const size_t smem = (size_t)2 * N * 32 * sizeof(float);
+    cudaFuncSetAttribute(zf::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    zf::umma_rate_kernel<<<ctas, 192, smem>>>(N, reps, mode, d);
+    const int rc = (int)cudaDeviceSynchronize();
+    cudaMemcpy(host_out, d, 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return rc;
+}
+#endif

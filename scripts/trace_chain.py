@@ -23,7 +23,7 @@ if "--build" in sys.argv:  # same as: python scripts/build_variant.py trace -DZF
     sys.exit(0)
 
 os.environ["ZENFLOW_B200_NO_BUILD"] = "1"
-zb.LIB_PATH = TRACE_LIB
+zb.LIB_PATH = os.path.abspath(os.environ["ZF_LIB"]) if os.environ.get("ZF_LIB") else TRACE_LIB
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from zenflow_b200 import _lib, Flow  # noqa: E402

@@ -37,11 +37,12 @@ CONFIGS = [
 ]
 
 
-@pytest.fixture(params=["auto", "simt", "umma2"])
+@pytest.fixture(params=["auto", "simt", "umma2", "umma16"])
 def chain_impl(request, monkeypatch):
     """auto = tensor-core (tcgen05) kernel when the chain fits it, else the FFMA kernel; simt = force FFMA;
-    umma2 = the opt-in two-pipeline tensor-core variant (falls back like auto when the chain does not fit)."""
-    if request.param in ("simt", "umma2"):
+    umma2 = the opt-in two-pipeline tensor-core variant, umma16 = the opt-in 16-epilogue-warp layout (both fall
+    back like auto when the chain does not fit)."""
+    if request.param in ("simt", "umma2", "umma16"):
         monkeypatch.setenv("ZF_CHAIN_IMPL", request.param)
     else:
         monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)

@@ -504,7 +504,6 @@ __device__ long long g_zf_trace[4][64];
 #define ZF_TRV(slot, v)
 #endif
 constexpr int UM = 128;
-constexpr int UTHREADS = 320;
 #ifndef ZF_URING
 #define ZF_URING 4
 #endif
@@ -532,7 +531,7 @@ __host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
 }
 constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer programs read them from global)
 __host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
-    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 128 +
+    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 3 * UM +
            (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
 
@@ -636,10 +635,281 @@ __device__ __forceinline__ void spline_row_tmem(uint32_t dbase, uint32_t cross_o
     rqs_block_slopes<KT>(pa, b.idx, b.dk, b.dkp1);
 }
 
-template <bool INVERSE>
-__global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_constant__ ChainArgs a) {
+// ---- the epilogue / SIMT role of the tensor-core chain kernel ------------------------------------------------
+// NG column groups of 4 warps each (group g = warp / 4 owns CW = 32 / NG columns of every 32-column K-chunk and
+// every NG-th feature / bounded column); TMEM lane quarter = warp % 4 (hardware rule).  Spline rows are run by
+// groups 0 and 1 (one transformed dim each, alternating accumulator buffers).  HELPER = groups 2.. of the
+// 4-group kernel, compiled without the spline code so that they fit a small register allocation.
+struct UCtx {
+    const ChainArgs& a;
+    float *xs, *cs, *xraw, *hs, *cst, *ldx;
+    uint64_t* bars;
+    const StepDesc* steps;
+    uint32_t tb;
+    long long n_tiles;
+    UCst cl;
+    bool in16;
+    uint32_t in_bytes;
+};
+template <int ET>
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); }
+template <int CW>
+__device__ __forceinline__ void tmem_load(uint32_t addr, float (&v)[CW]) {
+    if constexpr (CW == 16) umma::ld16(addr, v);
+    else umma::ld8(addr, v);
+}
+template <int CW>
+__device__ __forceinline__ void activation_compute(const float (&v)[CW], float (&hi)[CW], float (&lo)[CW]) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) umma::split_tf32(swish_fast(v[i]), hi[i], lo[i]);
+}
+template <int CW>
+__device__ __forceinline__ void activation_store(uint32_t tb, uint32_t lane_base, int n0, const float (&hi)[CW],
+                                                 const float (&lo)[CW]) {
+    if constexpr (CW == 16) {
+        umma::st16(umma::taddr(tb, lane_base, n0), hi);
+        umma::st16(umma::taddr(tb, lane_base, 128 + n0), lo);
+    } else {
+        umma::st8(umma::taddr(tb, lane_base, n0), hi);
+        umma::st8(umma::taddr(tb, lane_base, 128 + n0), lo);
+    }
+}
+
+template <bool INVERSE, int NG, bool HELPER>
+__device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;   // half = column group g in [0, NG)
+    constexpr int ET = NG * 128, CW = 32 / NG;                    // epilogue threads; columns per thread and K-chunk
+    const ChainArgs& a = cx.a;
+    const int D = a.D, C = a.C;
+    const UCst cl = cx.cl;
+    float *xs = cx.xs, *cs = cx.cs, *xraw = cx.xraw, *hs = cx.hs, *cst = cx.cst, *ldx = cx.ldx;
+    uint64_t* bars = cx.bars;
+    const StepDesc* steps = cx.steps;
+    const float* wsf = a.ws;
+    const uint32_t tb = cx.tb;
+    const long long n_tiles = cx.n_tiles;
+    auto tile_by_bulk = [&](long long t) { return cx.in16 && cx.in_bytes != 0 && (t + 1) * UM <= a.M; };
+    const uint32_t lane_base = (uint32_t)(q * 32);
+    uint32_t p_fh = 0, p_fd = 0;
+    ZF_TR_DECL;
+#ifdef ZF_TRACE
+    const int trs = (warp == 0) ? 0 : (warp == 4 ? 1 : 3);
+#endif
+    const int rot_in = INVERSE ? a.rot_total : 0;
+    uint32_t ke = 0, xk = 0;   // couplings / bulk-fetched tiles consumed so far (barrier phases)
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        ZF_TR_TILE;
+        ZF_TR(trs);
+        const long long m0 = tile * UM;
+        const int nm = (int)min((long long)UM, a.M - m0);
+        // rows -> feature-major tile; padding events sit at 0.5 / 0 and are never stored
+        const bool bulk = tile_by_bulk(tile);
+        if (bulk) mbar_wait(&bars[B_XFULL], xk & 1u);
+        const float* xsrc = bulk ? xraw : a.x + m0 * D;
+        const float* csrc = bulk ? xraw + UM * D : a.c + m0 * C;
+        {   // element e = mm * D + j, advanced by 256 per round without dividing
+            int mm = tid / D, j = tid - mm * D;
+            const int dm = ET / D, dj = ET - dm * D;
+            for (int e = tid; e < UM * D; e += ET) {
+                int col = j - rot_in;
+                if (col < 0) col += D;
+                xs[col * UM + mm] =
+                    (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : xsrc[e]) : 0.5f;
+                mm += dm; j += dj;
+                if (j >= D) { j -= D; ++mm; }
+            }
+        }
+        if (C) {
+            int mm = tid / C, j = tid - mm * C;
+            const int dm = ET / C, dj = ET - dm * C;
+            for (int e = tid; e < UM * C; e += ET) {
+                cs[j * UM + mm] = (mm < nm) ? csrc[e] : 0.f;
+                mm += dm; j += dj;
+                if (j >= C) { j -= C; ++mm; }
+            }
+        }
+        if (bulk) { umma::mbar_arrive(&bars[B_XEMPTY]); ++xk; }
+        epi_barrier<ET>();
+        ZF_TR(trs);   // 1: inputs loaded
+
+        float ld_acc = 0.f;
+        for (int si = 0; si < a.n_steps; ++si) {
+            const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
+            if (s.kind == kStepKindShiftBounds) {
+                // columns split between the groups; groups 1.. hand their log-det share over through ldx
+                float ld_sb = 0.f;
+                shift_bounds_row<INVERSE>(s, wsf, D, xs, UM, m, ld_sb, half, NG);
+                if (half > 0) ldx[(half - 1) * UM + m] = ld_sb;
+                epi_barrier<ET>();
+                if (half == 0) {
+#pragma unroll
+                    for (int g = 1; g < NG; ++g) ld_sb += ldx[(g - 1) * UM + m];
+                    ld_acc += ld_sb;
+                }
+                epi_barrier<ET>();
+                ZF_TR(trs);   // shift bounds done
+                continue;
+            }
+            const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
+            const int K = s.K, P = 3 * K - 1, NL = ru(P, 16);
+            // ---- this coupling's constants: fetched by the producer warp into buffer ke & 1
+            const uint32_t cb = ke & 1u;
+            const float* cc = cst + (size_t)cb * cl.total;
+            const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh, *bls = cc + cl.bl;
+            mbar_wait(&bars[B_CFULL + cb], (ke >> 1) & 1u);
+            ZF_TR(trs);   // constants staged
+            // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342); halves share the features
+            for (int f = half; f < F; f += NG) {
+                const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
+                hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+            }
+            epi_barrier<ET>();
+            ZF_TR(trs);   // batch norm done
+            // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
+            // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int n0 = c * 32 + half * CW;
+                float acc[CW], ahi[CW], alo[CW];
+#pragma unroll
+                for (int i = 0; i < CW; ++i) acc[i] = b0s[n0 + i];
+                for (int f = 0; f < F; ++f) {
+                    const float h = hs[f * UM + m];
+                    const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
+#pragma unroll
+                    for (int g4 = 0; g4 < CW / 4; ++g4) {
+                        const float4 wv = w[g4];
+                        acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
+                        acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
+                        acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
+                        acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
+                    }
+                }
+                activation_compute<CW>(acc, ahi, alo);
+#ifdef ZF_TRACE_FINE
+                asm volatile("" :: "f"(ahi[0]), "f"(alo[CW - 1]) : "memory");
+                ZF_TR(trs);
+#endif
+                activation_store<CW>(tb, lane_base, n0, ahi, alo);
+#ifdef ZF_TRACE_FINE
+                ZF_TR(trs);
+#endif
+                umma::wait_st();
+#ifdef ZF_TRACE_FINE
+                ZF_TR(trs);
+#endif
+                umma::fence_before_sync();
+                umma::mbar_arrive(&bars[B_AREADY + c]);
+#ifdef ZF_TRACE_FINE
+                ZF_TR(trs);
+#endif
+            }
+            ZF_TR(trs);   // first dense done
+            // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
+            for (int l = 1; l < L; ++l) {
+                mbar_wait(&bars[B_DFULL_H], p_fh);
+                p_fh ^= 1u;
+                umma::fence_after_sync();
+                ZF_TR(trs);   // hidden accumulator ready
+                const float* bh = bhs + (l - 1) * 128;
+                // chunk c: accumulator columns [32c + CW g, +CW) -> the same columns of the next activations.
+                // The TMEM loads of chunk c+1 are in flight during the arithmetic of chunk c.
+                float vn[CW], wn[CW];
+                tmem_load<CW>(umma::taddr(tb, lane_base, 256 + half * CW), vn);     // main products
+                tmem_load<CW>(umma::taddr(tb, lane_base, 384 + half * CW), wn);     // cross products
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int n0 = c * 32 + half * CW;
+                    float v[CW], ahi[CW], alo[CW];
+                    umma::wait_ld();
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) v[i] = (vn[i] + wn[i]) + bh[n0 + i];
+                    if (c < 3) {
+                        tmem_load<CW>(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);
+                    }
+                    activation_compute<CW>(v, ahi, alo);
+                    activation_store<CW>(tb, lane_base, n0, ahi, alo);
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_AREADY + c]);
+                }
+                ZF_TR(trs);   // hidden epilogue done
+            }
+            // ---- last layer: theta of one transformed dim at a time, read from tensor memory
+            float ldc = 0.f;
+            if (!HELPER)
+            for (int jj = half; jj < d && half < 2; jj += 2) {
+                mbar_wait(&bars[B_DFULL_D + half], p_fd);
+                p_fd ^= 1u;
+                umma::fence_after_sync();
+                ZF_TR(trs);   // theta ready
+                const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * (K == 16 ? 64 : 128));
+                float* px = xs + pmod(jj - rot, D) * UM + m;
+                const float v = *px;
+                RqsBin bin;
+                auto release = [&]() {
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                    ZF_TR(trs);   // released
+                };
+                if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls + jj * NL, v, bin, release);
+                else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
+                if (!INVERSE) {
+                    float y, ld;
+                    rqs_eval_forward(v, bin, y, ld);
+                    *px = y;
+                    ldc += ld;
+                } else {
+                    *px = rqs_eval_inverse(v, bin);
+                }
+            }
+            ZF_TR(trs);   // spline rows done
+            umma::mbar_arrive(&bars[B_CEMPTY + cb]);   // last read of this coupling's constants
+            ++ke;
+            if (half == 1) ldx[m] = ldc;
+            epi_barrier<ET>();
+            if (half == 0) ld_acc += ldc + ldx[m];
+            epi_barrier<ET>();
+            ZF_TR(trs);   // coupling done
+        }
+
+        // ---- store
+        if (a.mode == kModeLogProb) {
+            if (half == 0 && m < nm) {
+                float lat = 0.f;
+                for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * UM + m], a.lc);
+                a.lp[m0 + m] = nan_to_num_lp(lat + ld_acc);
+            }
+        } else {
+            const int rot_out = INVERSE ? 0 : a.rot_total;
+            if (a.y) {
+                for (int e = tid; e < nm * D; e += ET) {
+                    const int mm = e / D, j = e - mm * D;
+                    a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * UM + mm];
+                }
+            }
+            if (!INVERSE && a.log_det && half == 0 && m < nm)
+                a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
+        }
+        epi_barrier<ET>();
+        ZF_TR(trs);   // tile stored
+    }
+}
+
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// NG = 2: 8 epilogue warps + producer + MMA issuer (320 threads).
+// NG = 4: 16 epilogue warps (two spline-capable groups, two helper groups) + a fifth warpgroup holding the
+//         producer and the MMA issuer (640 threads); the register file is re-divided with setmaxnreg: the spline
+//         groups grow, the helpers and the fifth warpgroup shrink.
+template <bool INVERSE, int NG>
+__global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int ET = NG * 128, PW = NG * 4, MW = NG * 4 + 1;   // epilogue threads, producer warp, MMA warp
     const int D = a.D, C = a.C;
     const UCst cl = ucst_layout(a.u_fmax, a.u_hmax, a.u_blmax);
     float* xs = smem;                         // [D][UM]  the tile, feature-major
@@ -648,7 +918,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
     float* hs = xraw + UM * (D + C);          // [Fmax][UM]  BatchNorm output
     float* cst = hs + a.u_fmax * UM;          // [2][cl.total] per-coupling constants
     float* ldx = cst + 2 * cl.total;
-    float* ring = ldx + 128;
+    float* ring = ldx + 3 * UM;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
@@ -658,24 +928,24 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
     if (steps_fit) {
         const int4* src = reinterpret_cast<const int4*>(a.ws);
         int4* dst = reinterpret_cast<int4*>(steps_s);
-        for (int i = tid; i < a.n_steps * (int)(sizeof(StepDesc) / 16); i += UTHREADS) dst[i] = src[i];
+        for (int i = tid; i < a.n_steps * (int)(sizeof(StepDesc) / 16); i += (int)blockDim.x) dst[i] = src[i];
     }
     const StepDesc* steps = steps_fit ? steps_s : reinterpret_cast<const StepDesc*>(a.ws);
 
     if (tid == 0) {
         for (int i = 0; i < URING; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-        for (int i = 0; i < 4; ++i) mbar_init(&bars[B_AREADY + i], 256);
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[B_AREADY + i], ET);
         mbar_init(&bars[B_DFULL_H], 1);
         mbar_init(&bars[B_DFULL_D + 0], 1);
         mbar_init(&bars[B_DFULL_D + 1], 1);
         mbar_init(&bars[B_DEMPTY_D + 0], 128);
         mbar_init(&bars[B_DEMPTY_D + 1], 128);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_CFULL + i], 1); mbar_init(&bars[B_CEMPTY + i], 256); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_CFULL + i], 1); mbar_init(&bars[B_CEMPTY + i], ET); }
         mbar_init(&bars[B_XFULL], 1);
-        mbar_init(&bars[B_XEMPTY], 256);
+        mbar_init(&bars[B_XEMPTY], ET);
         mbar_fence_init();
     }
-    if (warp == 9) umma::tmem_alloc(tmem_slot, 512);
+    if (warp == MW) umma::tmem_alloc(tmem_slot, 512);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -699,7 +969,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
     for (int si = 0; si < a.n_steps; ++si)
         if (steps[INVERSE ? (a.n_steps - 1 - si) : si].kind == kStepKindCoupling) last_coupling_si = si;
 
-    if (warp == 8) {
+    auto producer_role = [&]() {
         // ------------------------------------------------------------------ producer: weights, constants, inputs
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, kc = 0, xk = 0;
@@ -752,7 +1022,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    };
+    auto mma_role = [&]() {
         // ------------------------------------------------------------------ MMA issuer
         // The tensor core's fp32 accumulator truncates at every accumulate step (measured: -2.3e-8 relative
         // per step, tests/test_gpu_umma.py), so the two small cross products (2^-11 of the main one) go to
@@ -844,202 +1115,35 @@ __global__ void __launch_bounds__(UTHREADS, 1) chain_umma_kernel(const __grid_co
                 }
             }
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue / SIMT warps
-        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32);
-        uint32_t p_fh = 0, p_fd = 0;
-        ZF_TR_DECL;
-#ifdef ZF_TRACE
-        const int trs = (warp == 0) ? 0 : (warp == 4 ? 1 : 3);
-#endif
-        const int rot_in = INVERSE ? a.rot_total : 0;
-        uint32_t ke = 0, xk = 0;   // couplings / bulk-fetched tiles consumed so far (barrier phases)
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            ZF_TR_TILE;
-            ZF_TR(trs);
-            const long long m0 = tile * UM;
-            const int nm = (int)min((long long)UM, a.M - m0);
-            // rows -> feature-major tile; padding events sit at 0.5 / 0 and are never stored
-            const bool bulk = tile_by_bulk(tile);
-            if (bulk) mbar_wait(&bars[B_XFULL], xk & 1u);
-            const float* xsrc = bulk ? xraw : a.x + m0 * D;
-            const float* csrc = bulk ? xraw + UM * D : a.c + m0 * C;
-            {   // element e = mm * D + j, advanced by 256 per round without dividing
-                int mm = tid / D, j = tid - mm * D;
-                const int dm = 256 / D, dj = 256 - dm * D;
-                for (int e = tid; e < UM * D; e += 256) {
-                    int col = j - rot_in;
-                    if (col < 0) col += D;
-                    xs[col * UM + mm] =
-                        (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : xsrc[e]) : 0.5f;
-                    mm += dm; j += dj;
-                    if (j >= D) { j -= D; ++mm; }
-                }
-            }
-            if (C) {
-                int mm = tid / C, j = tid - mm * C;
-                const int dm = 256 / C, dj = 256 - dm * C;
-                for (int e = tid; e < UM * C; e += 256) {
-                    cs[j * UM + mm] = (mm < nm) ? csrc[e] : 0.f;
-                    mm += dm; j += dj;
-                    if (j >= C) { j -= C; ++mm; }
-                }
-            }
-            if (bulk) { umma::mbar_arrive(&bars[B_XEMPTY]); ++xk; }
-            epi_barrier();
-            ZF_TR(trs);   // 1: inputs loaded
-
-            float ld_acc = 0.f;
-            for (int si = 0; si < a.n_steps; ++si) {
-                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
-                if (s.kind == kStepKindShiftBounds) {
-                    // columns split between the two halves; half 1 hands its log-det share over through ldx
-                    float ld_sb = 0.f;
-                    shift_bounds_row<INVERSE>(s, wsf, D, xs, UM, m, ld_sb, half, 2);
-                    if (half == 1) ldx[m] = ld_sb;
-                    epi_barrier();
-                    if (half == 0) ld_acc += ld_sb + ldx[m];
-                    epi_barrier();
-                    ZF_TR(trs);   // shift bounds done
-                    continue;
-                }
-                const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
-                const int K = s.K, P = 3 * K - 1, NL = ru(P, 16);
-                // ---- this coupling's constants: fetched by the producer warp into buffer ke & 1
-                const uint32_t cb = ke & 1u;
-                const float* cc = cst + (size_t)cb * cl.total;
-                const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh, *bls = cc + cl.bl;
-                mbar_wait(&bars[B_CFULL + cb], (ke >> 1) & 1u);
-                ZF_TR(trs);   // constants staged
-                // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342); halves share the features
-                for (int f = half; f < F; f += 2) {
-                    const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
-                    hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
-                }
-                epi_barrier();
-                ZF_TR(trs);   // batch norm done
-                // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
-                // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    const int n0 = c * 32 + half * 16;
-                    float acc[16], ahi[16], alo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[i] = b0s[n0 + i];
-                    for (int f = 0; f < F; ++f) {
-                        const float h = hs[f * UM + m];
-                        const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            const float4 wv = w[g4];
-                            acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
-                            acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
-                            acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
-                            acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
-                        }
-                    }
-                    activation16_compute(acc, ahi, alo);
-                    activation16_store(tb, lane_base, n0, ahi, alo);
-                    umma::wait_st();
-                    umma::fence_before_sync();
-                    umma::mbar_arrive(&bars[B_AREADY + c]);
-                }
-                ZF_TR(trs);   // first dense done
-                // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
-                for (int l = 1; l < L; ++l) {
-                    mbar_wait(&bars[B_DFULL_H], p_fh);
-                    p_fh ^= 1u;
-                    umma::fence_after_sync();
-                    ZF_TR(trs);   // hidden accumulator ready
-                    const float* bh = bhs + (l - 1) * 128;
-                    // chunk c: accumulator columns [32c + 16 half, +16) -> the same columns of the next activations.
-                    // The TMEM loads of chunk c+1 are in flight during the arithmetic of chunk c.
-                    float vn[16], wn[16];
-                    umma::ld16(umma::taddr(tb, lane_base, 256 + half * 16), vn);        // main products
-                    umma::ld16(umma::taddr(tb, lane_base, 384 + half * 16), wn);        // cross products
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        const int n0 = c * 32 + half * 16;
-                        float v[16], ahi[16], alo[16];
-                        umma::wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = (vn[i] + wn[i]) + bh[n0 + i];
-                        if (c < 3) {
-                            umma::ld16(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
-                            umma::ld16(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);
-                        }
-                        activation16_compute(v, ahi, alo);
-                        activation16_store(tb, lane_base, n0, ahi, alo);
-                        umma::wait_st();
-                        umma::fence_before_sync();
-                        umma::mbar_arrive(&bars[B_AREADY + c]);
-                    }
-                    ZF_TR(trs);   // hidden epilogue done
-                }
-                // ---- last layer: theta of one transformed dim at a time, read from tensor memory
-                float ldc = 0.f;
-                for (int jj = half; jj < d; jj += 2) {
-                    mbar_wait(&bars[B_DFULL_D + half], p_fd);
-                    p_fd ^= 1u;
-                    umma::fence_after_sync();
-                    ZF_TR(trs);   // theta ready
-                    const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * (K == 16 ? 64 : 128));
-                    float* px = xs + pmod(jj - rot, D) * UM + m;
-                    const float v = *px;
-                    RqsBin bin;
-                    auto release = [&]() {
-                        umma::fence_before_sync();
-                        umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
-                        ZF_TR(trs);   // released
-                    };
-                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls + jj * NL, v, bin, release);
-                    else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
-                    if (!INVERSE) {
-                        float y, ld;
-                        rqs_eval_forward(v, bin, y, ld);
-                        *px = y;
-                        ldc += ld;
-                    } else {
-                        *px = rqs_eval_inverse(v, bin);
-                    }
-                }
-                ZF_TR(trs);   // spline rows done
-                umma::mbar_arrive(&bars[B_CEMPTY + cb]);   // last read of this coupling's constants
-                ++ke;
-                if (half == 1) ldx[m] = ldc;
-                epi_barrier();
-                if (half == 0) ld_acc += ldc + ldx[m];
-                epi_barrier();
-                ZF_TR(trs);   // coupling done
-            }
-
-            // ---- store
-            if (a.mode == kModeLogProb) {
-                if (half == 0 && m < nm) {
-                    float lat = 0.f;
-                    for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * UM + m], a.lc);
-                    a.lp[m0 + m] = nan_to_num_lp(lat + ld_acc);
-                }
-            } else {
-                const int rot_out = INVERSE ? 0 : a.rot_total;
-                if (a.y) {
-                    for (int e = tid; e < nm * D; e += 256) {
-                        const int mm = e / D, j = e - mm * D;
-                        a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * UM + mm];
-                    }
-                }
-                if (!INVERSE && a.log_det && half == 0 && m < nm)
-                    a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
-            }
-            epi_barrier();
-            ZF_TR(trs);   // tile stored
+    };
+    // ------------------------------------------------------------------ role dispatch
+    // Each setmaxnreg dominates exactly the code of its warpgroup (no join before the role ends), which is what lets
+    // ptxas give every role its own register budget: groups 0,1 | groups 2,3 | producer + MMA issuer + two idle warps.
+    // setmaxnreg moves registers inside the pool the CTA was launched with (640 threads x 96 registers; the rest of
+    // the register file is not reachable), so the three allocations must add up to it or the increase never succeeds.
+    static_assert(256 * 144 + 256 * 56 + 128 * 80 == 640 * 96, "setmaxnreg split must equal the launch allocation");
+    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, bars, steps, tb, n_tiles, cl, in16, in_bytes};
+    if constexpr (NG == 4) {
+        if (warp < 8) {
+            reg_inc<144>();
+            umma_epilogue_role<INVERSE, NG, false>(cx);
+        } else if (warp < 16) {
+            reg_dec<56>();
+            umma_epilogue_role<INVERSE, NG, true>(cx);
+        } else {
+            reg_dec<80>();
+            if (warp == PW) producer_role();
+            else if (warp == MW) mma_role();
         }
+    } else {
+        if (warp == PW) producer_role();
+        else if (warp == MW) mma_role();
+        else umma_epilogue_role<INVERSE, NG, false>(cx);
     }
 
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 9) umma::tmem_dealloc(tb, 512);
+    if (warp == MW) umma::tmem_dealloc(tb, 512);
 }
 
 // =============================================================================================
@@ -1566,13 +1670,18 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
         if (usmem <= (size_t)di.max_smem_optin) {
             const long long tiles = (M + UM - 1) / UM;
             const unsigned ugrid = (unsigned)std::min<long long>(tiles, (long long)di.sm_count);
-            if (mode == kModeInverse) {
-                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-                chain_umma_kernel<true><<<ugrid, UTHREADS, usmem, stream>>>(a);
-            } else {
-                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-                chain_umma_kernel<false><<<ugrid, UTHREADS, usmem, stream>>>(a);
-            }
+            // ZF_CHAIN_IMPL=umma16: 16 epilogue warps with a setmaxnreg register split.  Measured no faster than the
+            // default 8 (the activation phases are bound by the SFU / tensor-memory-store port, not by latency).
+            const bool eight = !(impl && strcmp(impl, "umma16") == 0);
+            auto launch = [&](auto kern, unsigned threads) -> int {
+                ZF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+                kern<<<ugrid, threads, usmem, stream>>>(a);
+                return ZF_OK;
+            };
+            int rc;
+            if (mode == kModeInverse) rc = eight ? launch(chain_umma_kernel<true, 2>, 320) : launch(chain_umma_kernel<true, 4>, 640);
+            else rc = eight ? launch(chain_umma_kernel<false, 2>, 320) : launch(chain_umma_kernel<false, 4>, 640);
+            if (rc != ZF_OK) return rc;
             count_launch();
             ZF_CUDA_CHECK(cudaGetLastError());
             return ZF_OK;

@@ -53,6 +53,16 @@ __device__ __forceinline__ void st8(uint32_t a, const float (&v)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void st16(uint32_t a, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
 // ---- 3xTF32 split -------------------------------------------------------------------------------
 // hi = x rounded to tf32 (round to nearest, ties away from zero: exactly cvt.rna.tf32.f32, but as two
 // full-rate integer ops instead of a trip through the conversion unit); lo = x - hi is exact in fp32

@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
         // bias/swish/split of the chunks behind it.  The arrival of chunk c also says that accumulator columns
         // [32c, 32c+32) of D0 and D1 have been drained, which is what lets the first last-layer unit start
         // before the hidden epilogue has finished (it only needs the columns it overwrites to be free).
-        uint32_t stage = 0, phase = 0, p_ar = 0, p_ed0 = 0, p_ed1 = 0;
+        uint32_t phase = 0, p_ar = 0, p_ed0 = 0, p_ed1 = 0;
         bool dim_pending0 = false, dim_pending1 = false;
         ZF_TR_DECL;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1046,7 +1046,6 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
                 const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
                 for (int u = 0; u < (L - 1) + s.d; ++u) {
                     const bool hid = u < L - 1;
-                    const int N = hid ? 128 : NL;
                     const int b = hid ? 0 : ((u - (L - 1)) & 1);
                     ZF_TR(2);
                     const bool newver = hid || u == L - 1;   // this unit reads a new version of the activations
@@ -1066,48 +1065,60 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
 #endif
                     const uint32_t dmain = hid ? tb + 256u : (split_acc ? tb + 256u + (uint32_t)b * 64u : tb + 256u + (uint32_t)b * 128u);
                     const uint32_t dcross = split_acc ? dmain + 128u : dmain;
-                    const uint32_t idesc = umma::instr_desc_tf32(N);
-                    const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+                    // One unit = 4 K-chunks = one lap of the 4-stage ring, so chunk c always sits in stage c and every
+                    // descriptor is (a hoisted ring address) + (a compile-time offset): the issuing thread's
+                    // per-MMA work is what bounds the small-N units, keep it to a couple of instructions.
+                    static_assert(URING == 4, "the MMA issuer maps chunk c to ring stage c");
+                    auto issue_unit = [&](auto ntag) {
+                        constexpr int N = decltype(ntag)::value;
+                        constexpr uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+                        constexpr uint32_t idesc = umma::instr_desc_tf32(N);
+                        constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO, descriptor version
+                        const uint32_t ring16 = (smem_u32(ring) >> 4) | ((lbo >> 4) << 16);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < 4; ++c) {
 #ifdef ZF_TRACE
-                        long long t_a = clock64();
+                            long long t_a = clock64();
 #endif
-                        if (newver) {
-                            const int need = max(c + 1, nfree);
+                            if (newver) {
+                                const int need = max(c + 1, nfree);
 #pragma unroll
-                            for (int w = 0; w < 4; ++w)
-                                if (w >= waited && w < need) mbar_wait(&bars[B_AREADY + w], p_ar);
-                            waited = max(waited, need);
-                        }
-#ifdef ZF_TRACE
-                        long long t_f = clock64();
-                        w_a += t_f - t_a;
-#endif
-                        mbar_wait(&bars[B_FULL + stage], phase);
-#ifdef ZF_TRACE
-                        w_full += clock64() - t_f;
-#endif
-                        umma::fence_after_sync();
-                        if (umma::elect_one()) {
-                            const uint32_t bhi = smem_u32(ring + (size_t)stage * URING_FLOATS);
-                            const uint32_t blo = bhi + (uint32_t)N * 128u;  // lo image follows the N*32-float hi image
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, 128u);
-                                const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, 128u);
-                                const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
-                                const bool first = (c | ks) == 0;
-                                umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, !first);          // A_lo * B_hi
-                                umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);                   // A_hi * B_lo
-                                umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, split_acc ? !first : true);  // A_hi * B_hi
+                                for (int w = 0; w < 4; ++w)
+                                    if (w >= waited && w < need) mbar_wait(&bars[B_AREADY + w], p_ar);
+                                waited = max(waited, need);
                             }
-                            umma::commit(&bars[B_EMPTY + stage]);
-                            if (c == 3) umma::commit(&bars[hid ? B_DFULL_H : (B_DFULL_D + b)]);
+#ifdef ZF_TRACE
+                            long long t_f = clock64();
+                            w_a += t_f - t_a;
+#endif
+                            mbar_wait(&bars[B_FULL + c], phase);
+#ifdef ZF_TRACE
+                            w_full += clock64() - t_f;
+#endif
+                            umma::fence_after_sync();
+                            if (umma::elect_one()) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t off_hi = (uint32_t)(c * URING_FLOATS * 4 + ks * 2 * (int)lbo) >> 4;
+                                    const uint32_t off_lo = off_hi + ((uint32_t)N * 128u >> 4);   // lo image follows the hi image
+                                    const uint64_t dhi = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_hi);
+                                    const uint64_t dlo = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_lo);
+                                    const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                                    const bool first = (c | ks) == 0;
+                                    umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, !first);          // A_lo * B_hi
+                                    umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);                   // A_hi * B_lo
+                                    umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, split_acc ? !first : true);  // A_hi * B_hi
+                                }
+                                umma::commit(&bars[B_EMPTY + c]);
+                                if (c == 3) umma::commit(&bars[hid ? B_DFULL_H : (B_DFULL_D + b)]);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
-                        if (++stage == URING) { stage = 0; phase ^= 1u; }
-                    }
+                    };
+                    if (hid) issue_unit(std::integral_constant<int, 128>{});
+                    else if (NL == 48) issue_unit(std::integral_constant<int, 48>{});
+                    else issue_unit(std::integral_constant<int, 96>{});
+                    phase ^= 1u;
                     ZF_TR(2);
                     ZF_TRV(2, -w_pend); ZF_TRV(2, -w_a); ZF_TRV(2, -w_full);
                     if (newver) p_ar ^= 1u;

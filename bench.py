@@ -272,9 +272,14 @@ def run_gpu(args):
         return flow.apply(variables, xs_d[i % n_sets], cs_d[i % n_sets])
 
     # e2e: every step copies its inputs from pinned host memory and its result back to the host.
-    # Copies run on a side stream so that step i+1's H2D overlaps step i's kernel (double-buffered
-    # device staging buffers); all of it is inside the timed region.
+    # Copies run on side streams so that step i+1's H2D and step i-1's D2H overlap step i's kernel
+    # (double-buffered device staging buffers and host result buffers); all of it is inside the timed
+    # region: the last step's D2H is drained into the compute stream before the closing event.
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
+    d2h_done = [torch.cuda.Event() for _ in range(2)]
+    lp_hosts = [lp_host, torch.empty(M, dtype=torch.float32).pin_memory()]
+    lp_keep = [None, None]   # the device result stays referenced until its copy has been waited for
     stage_x = [torch.empty_like(xs_d[0]) for _ in range(2)]
     stage_c = [None if cs_d[0] is None else torch.empty_like(cs_d[0]) for _ in range(2)]
     h2d_done = [torch.cuda.Event() for _ in range(2)]
@@ -298,17 +303,27 @@ def run_gpu(args):
         e2e_state["primed"] = i + 1
         b = i & 1
         cur.wait_event(h2d_done[b])
+        cur.wait_event(d2h_done[b])     # step i-2's result has left the device: its buffer may be reused
         lp = flow.apply(variables, stage_x[b], stage_c[b])
         compute_done[b].record(cur)
-        lp_host.copy_(lp, non_blocking=True)  # 4 MB result back on the compute stream
+        lp_keep[b] = lp
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(compute_done[b])
+            lp_hosts[b].copy_(lp, non_blocking=True)  # 4 MB result back, overlapping the next step's kernel
+            d2h_done[b].record(d2h_stream)
         return lp
+
+    def drain_e2e():
+        cur = torch.cuda.current_stream()
+        for e in d2h_done:
+            cur.wait_event(e)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step, K, W):
+    def timed(step, K, W, drain=None):
         for i in range(W):
             step(i)
         barrier()
@@ -318,6 +333,8 @@ def run_gpu(args):
         for i in range(K):
             ev[i][0].record()
             step(W + i)
+            if drain is not None and i == K - 1:
+                drain()
             ev[i][1].record()
         barrier()
         t1 = time.perf_counter()
@@ -336,7 +353,7 @@ def run_gpu(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     value = world * M * K / (total_ms * 1e-3)
 
-    e2e_ms, _, _, _ = timed(step_e2e, K, W)
+    e2e_ms, _, _, _ = timed(step_e2e, K, W, drain=drain_e2e)
     e2e_value = world * M * K / (e2e_ms * 1e-3)
 
     # Flow.sample's inverse chain on a given latent draw (same events/s unit), N=1 extra

@@ -768,14 +768,24 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             ZF_TR(trs);   // batch norm done
             // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
             // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
+            // the event's first four inputs stay in registers for all chunks (F is 2 on the 2-D flows): the chunk
+            // loop then has no load -> FMA dependency on hs, and its weight / bias loads are issued up front
+            float hreg[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int n0 = c * 32 + half * CW;
                 float acc[CW], ahi[CW], alo[CW];
+                {
+                    const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
 #pragma unroll
-                for (int i = 0; i < CW; ++i) acc[i] = b0s[n0 + i];
-                for (int f = 0; f < F; ++f) {
-                    const float h = hs[f * UM + m];
+                    for (int g4 = 0; g4 < CW / 4; ++g4) {
+                        const float4 t = bv[g4];
+                        acc[g4 * 4 + 0] = t.x; acc[g4 * 4 + 1] = t.y; acc[g4 * 4 + 2] = t.z; acc[g4 * 4 + 3] = t.w;
+                    }
+                }
+                auto fma_row = [&](float h, int f) {
                     const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
 #pragma unroll
                     for (int g4 = 0; g4 < CW / 4; ++g4) {
@@ -785,7 +795,11 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                         acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
                         acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
                     }
-                }
+                };
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if (f < F) fma_row(hreg[f], f);
+                for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
                 activation_compute<CW>(acc, ahi, alo);
 #ifdef ZF_TRACE_FINE
                 asm volatile("" :: "f"(ahi[0]), "f"(alo[CW - 1]) : "memory");
@@ -823,8 +837,17 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     const int n0 = c * 32 + half * CW;
                     float v[CW], ahi[CW], alo[CW];
                     umma::wait_ld();
+                    {
+                        const float4* bv = reinterpret_cast<const float4*>(bh + n0);
 #pragma unroll
-                    for (int i = 0; i < CW; ++i) v[i] = (vn[i] + wn[i]) + bh[n0 + i];
+                        for (int g4 = 0; g4 < CW / 4; ++g4) {
+                            const float4 t = bv[g4];
+                            v[g4 * 4 + 0] = (vn[g4 * 4 + 0] + wn[g4 * 4 + 0]) + t.x;
+                            v[g4 * 4 + 1] = (vn[g4 * 4 + 1] + wn[g4 * 4 + 1]) + t.y;
+                            v[g4 * 4 + 2] = (vn[g4 * 4 + 2] + wn[g4 * 4 + 2]) + t.z;
+                            v[g4 * 4 + 3] = (vn[g4 * 4 + 3] + wn[g4 * 4 + 3]) + t.w;
+                        }
+                    }
                     if (c < 3) {
                         tmem_load<CW>(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
                         tmem_load<CW>(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);

@@ -76,3 +76,22 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "zenflow_oracle" not in text, f
+
+
+def test_build_digest_is_path_independent(tmp_path):
+    """The in-tree library ships to other machines with the sources: a copy of the tree under another path must see
+    the same digest (it once hashed absolute paths, so every process on the GPU box rebuilt - and 8 ranks raced)."""
+    import importlib.util
+    import shutil
+
+    from zenflow_b200 import build as zb
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = tmp_path / "relocated"
+    shutil.copytree(os.path.join(root, "zenflow_b200", "csrc"), dst / "zenflow_b200" / "csrc")
+    shutil.copytree(os.path.join(root, "include"), dst / "include")
+    shutil.copy(os.path.join(root, "zenflow_b200", "build.py"), dst / "zenflow_b200" / "build.py")
+    spec = importlib.util.spec_from_file_location("relocated_build", dst / "zenflow_b200" / "build.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod._digest() == zb._digest()

@@ -31,12 +31,14 @@ def _sources():
 
 
 def _digest() -> str:
+    """Content digest of the sources and flags.  File NAMES only (no absolute paths): the tree is copied to other
+    machines and must not look stale there."""
     h = hashlib.sha256()
     inc = os.path.join(os.path.dirname(HERE), "include", "zenflow_b200.h")
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [inc]
     for p in files:
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -49,24 +51,44 @@ def nvcc_path() -> str:
     return p
 
 
+def _fresh(dig: str) -> bool:
+    return os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library. Returns its path."""
+    """Compile every .cu under csrc/ into one shared library. Returns its path.
+
+    Safe under concurrent callers (one process per GPU): an exclusive file lock serialises the build, the library
+    is written to a temporary name and renamed into place, and whoever gets the lock second finds it fresh."""
+    import fcntl
+
     os.makedirs(LIB_DIR, exist_ok=True)
     dig = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
-        if open(STAMP).read().strip() == dig:
-            return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB_PATH] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-8000:])
-    if verbose:
-        print(log)
-    with open(STAMP, "w") as f:
-        f.write(dig)
+    if not force and _fresh(dig):
+        return LIB_PATH
+    with open(os.path.join(LIB_DIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _fresh(dig):
+                return LIB_PATH
+            tmp = LIB_PATH + f".tmp{os.getpid()}"
+            cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", tmp] + _sources()
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            log = res.stdout + res.stderr
+            with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
+                f.write(" ".join(cmd).replace(tmp, LIB_PATH) + "\n" + log)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + log[-8000:])
+            if verbose:
+                print(log)
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP + ".tmp", "w") as f:
+                f.write(dig)
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -2,6 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+if os.environ.get("ZF_LIB"):
+    from zenflow_b200 import build as _zb
+    _zb.LIB_PATH = os.path.abspath(os.environ["ZF_LIB"]); os.environ["ZENFLOW_B200_NO_BUILD"] = "1"
 from zenflow_b200 import _lib
 lib = _lib.load()
 M = 262144

@@ -60,6 +60,9 @@ template <bool RCONTIG>
 __device__ __forceinline__ float4 ug_load_unit(const float* __restrict__ X, long long ld, long long row, long long row_max,
                                                long long r, long long r_max, bool vec_ok) {
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef ZF_GEMM_EXP_NOLOAD   // timing experiment only
+    return make_float4((float)row, (float)r, 1.f, 2.f);
+#endif
     if (row < row_max) {
         if (RCONTIG && vec_ok && r + 3 < r_max) {
             o = __ldg(reinterpret_cast<const float4*>(X + row * ld + r));
@@ -73,6 +76,26 @@ __device__ __forceinline__ float4 ug_load_unit(const float* __restrict__ X, long
         }
     }
     return o;
+}
+
+// Which 16-byte unit (image row, k-quad r4) thread `tid` handles in round q of a chunk of ROWS x R4 units.
+//   transposed operands (reduction index strided in memory): lanes vary the row, so the four scalar loads of a
+//     unit are coalesced along the row index and 8 lanes fill one 128-byte core matrix of the image;
+//   reduction-contiguous operands: a quarter-warp takes 8 rows of one k-quad (conflict-free image stores) and the
+//     four quarter-warps take 4 consecutive k-quads, so a warp load reads 64 contiguous bytes from each of 8 rows
+//     (full sectors, 8 cache lines) instead of 16 bytes from each of 32 rows.
+template <bool RCONTIG, int ROWS, int R4>
+__device__ __forceinline__ void ug_unit(int tid, int q, int& row, int& r4) {
+    const int u = tid + q * 256;
+    if (!RCONTIG || R4 < 4) {
+        row = u % ROWS;
+        r4 = u / ROWS;
+    } else {
+        const int lane = u & 31, w = u >> 5;            // w: warp-sized group index in [0, ROWS * R4 / 32)
+        constexpr int GROUPS_PER_ROWBLOCK = R4 / 4;      // groups that share the same 8 rows
+        row = (w / GROUPS_PER_ROWBLOCK) * 8 + (lane & 7);
+        r4 = (w % GROUPS_PER_ROWBLOCK) * 4 + (lane >> 3);
+    }
 }
 
 template <int MODE, int TN>
@@ -124,47 +147,53 @@ __global__ void __launch_bounds__(UG_THREADS, (TN == 256) ? 1 : 2) umma_gemm_ker
             const long long r0 = rbeg + (long long)c * UG_KC;
 #pragma unroll
             for (int q = 0; q < UA; ++q) {
-                const int u = tid + q * 256;
                 int row, r4;
-                row = u & 127; r4 = u >> 7;  // lanes vary the row: 8 lanes fill one 128-byte core matrix
+                ug_unit<A_RCONTIG, 128, R4>(tid, q, row, r4);
                 ra[q] = ug_load_unit<A_RCONTIG>(g.A, g.lda, i0 + row, g.I, r0 + r4 * 4, rend, vecA);
             }
 #pragma unroll
             for (int q = 0; q < UB; ++q) {
-                const int u = tid + q * 256;
                 int row, r4;
-                row = u % TN; r4 = u / TN;
+                ug_unit<B_RCONTIG, TN, R4>(tid, q, row, r4);
                 rb[q] = ug_load_unit<B_RCONTIG>(g.B, g.ldb, j0 + row, g.J, r0 + r4 * 4, rend, vecB);
             }
         };
         auto store = [&](float* st, const float4 (&ra)[UA], const float4 (&rb)[UB]) {
 #pragma unroll
             for (int q = 0; q < UA; ++q) {
-                const int u = tid + q * 256;
                 int row, r4;
-                row = u & 127; r4 = u >> 7;  // lanes vary the row: 8 lanes fill one 128-byte core matrix
+                ug_unit<A_RCONTIG, 128, R4>(tid, q, row, r4);
                 float4 v = ra[q];
                 if (g.a_swish) { v.x = ug_swish(v.x); v.y = ug_swish(v.y); v.z = ug_swish(v.z); v.w = ug_swish(v.w); }
                 float4 hi, lo;
                 umma::split_tf32(v.x, hi.x, lo.x); umma::split_tf32(v.y, hi.y, lo.y);
                 umma::split_tf32(v.z, hi.z, lo.z); umma::split_tf32(v.w, hi.w, lo.w);
                 const int off = (r4 * 16 + (row >> 3)) * 32 + (row & 7) * 4;
+#ifdef ZF_GEMM_EXP_NOSTORE   // timing experiment only
+                if (hi.x == 1234.5f && lo.y == 0.25f)
+#endif
+                {
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + A_FLOATS + off) = lo;
+                }
             }
 #pragma unroll
             for (int q = 0; q < UB; ++q) {
-                const int u = tid + q * 256;
                 int row, r4;
-                row = u % TN; r4 = u / TN;
+                ug_unit<B_RCONTIG, TN, R4>(tid, q, row, r4);
                 const float4 v = rb[q];
                 if (MODE == 2) csum += (v.x + v.y) + (v.z + v.w);
                 float4 hi, lo;
                 umma::split_tf32(v.x, hi.x, lo.x); umma::split_tf32(v.y, hi.y, lo.y);
                 umma::split_tf32(v.z, hi.z, lo.z); umma::split_tf32(v.w, hi.w, lo.w);
                 const int off = (r4 * (TN / 8) + (row >> 3)) * 32 + (row & 7) * 4;
+#ifdef ZF_GEMM_EXP_NOSTORE
+                if (hi.x == 1234.5f && lo.y == 0.25f)
+#endif
+                {
                 *reinterpret_cast<float4*>(st + 2 * A_FLOATS + off) = hi;
                 *reinterpret_cast<float4*>(st + 2 * A_FLOATS + B_FLOATS + off) = lo;
+                }
             }
         };
         float4 ra0[UA], rb0[UB], ra1[UA], rb1[UB];
@@ -207,6 +236,9 @@ __global__ void __launch_bounds__(UG_THREADS, (TN == 256) ? 1 : 2) umma_gemm_ker
             umma::ld16(umma::taddr(tb, q * 32, n0), v);
             umma::ld16(umma::taddr(tb, q * 32, TN + n0), w);
             umma::wait_ld();
+#ifdef ZF_GEMM_EXP_NOEPI
+            if (v[0] == 1234.5f)
+#endif
             if (i < g.I) {
                 float x[16];
 #pragma unroll

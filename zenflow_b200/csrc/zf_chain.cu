@@ -531,7 +531,7 @@ __host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
 }
 constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer programs read them from global)
 __host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
-    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 3 * UM +
+    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 11 * UM +
            (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
 
@@ -635,6 +635,55 @@ __device__ __forceinline__ void spline_row_tmem(uint32_t dbase, uint32_t cross_o
     rqs_block_slopes<KT>(pa, b.idx, b.dk, b.dkp1);
 }
 
+// One spline row shared by two threads (the same event in column groups 0 and 1), for couplings that transform a
+// single dim and would otherwise leave group 1 idle: group 0 normalises the searched axis and finds the bin while
+// group 1 normalises the other axis; the bin goes over through shared memory, group 1 selects the other-axis knot
+// and the slopes and hands them back; then group 0 evaluates y (or x) while group 1 evaluates log|dy/dx|.
+// Operation for operation the same arithmetic as spline_row_tmem + rqs_eval_*.
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+template <int KT, bool INVERSE>
+__device__ __forceinline__ void spline_row_search_half(uint32_t dbase, uint32_t cross_off, const float* __restrict__ bias,
+                                                       float v, RqsBin& b) {
+    constexpr int cs_ = INVERSE ? KT : 0;
+    const KnotNorm kn = make_knot_norm(KT);
+    float pa[KT], wa[KT];
+    RqsCheck chk;
+    theta_block_issue<KT>(dbase, cross_off, cs_, pa, wa);
+    umma::wait_ld();
+    const float amax_s = theta_block_finish<KT>(cs_, bias, pa, wa);
+    if (__any_sync(0xffffffffu, !(amax_s < kThetaFastBound)))
+        rqs_block_search<KT, true>(pa, v, kn, b.idx, b.ks, b.bs, chk);
+    else
+        rqs_block_search<KT, false>(pa, v, kn, b.idx, b.ks, b.bs, chk);
+}
+
+// group 1, before the bin is known: loads of the other-axis and slope blocks, squareplus + sum of the other axis
+template <int KT, bool INVERSE>
+struct OtherHalf {
+    float pb[KT], ps[KT], sum;
+    bool safe;
+    __device__ __forceinline__ void pre(uint32_t dbase, uint32_t cross_off, const float* __restrict__ bias) {
+        constexpr int co_ = INVERSE ? 0 : KT;
+        float wb[KT], ws[KT];
+        RqsCheck chk;
+        theta_block_issue<KT>(dbase, cross_off, co_, pb, wb);
+        theta_block_issue<KT>(dbase, cross_off, 2 * KT, ps, ws);
+        umma::wait_ld();                                    // every TMEM read of this thread is done
+        const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
+        (void)theta_block_finish<KT>(2 * KT, bias, ps, ws);
+        safe = __any_sync(0xffffffffu, !(amax_o < kThetaFastBound));
+        if (safe) rqs_block_other_pre<KT, true>(pb, sum, chk);
+        else rqs_block_other_pre<KT, false>(pb, sum, chk);
+    }
+    __device__ __forceinline__ void post(RqsBin& b) {
+        const KnotNorm kn = make_knot_norm(KT);
+        if (safe) rqs_block_other_post<KT, true>(pb, sum, b.idx, kn, b.ko, b.bo);
+        else rqs_block_other_post<KT, false>(pb, sum, b.idx, kn, b.ko, b.bo);
+        rqs_block_slopes<KT>(ps, b.idx, b.dk, b.dkp1);
+    }
+};
+
 // ---- the epilogue / SIMT role of the tensor-core chain kernel ------------------------------------------------
 // NG column groups of 4 warps each (group g = warp / 4 owns CW = 32 / NG columns of every 32-column K-chunk and
 // every NG-th feature / bounded column); TMEM lane quarter = warp % 4 (hardware rule).  Spline rows are run by
@@ -642,7 +691,7 @@ __device__ __forceinline__ void spline_row_tmem(uint32_t dbase, uint32_t cross_o
 // 4-group kernel, compiled without the spline code so that they fit a small register allocation.
 struct UCtx {
     const ChainArgs& a;
-    float *xs, *cs, *xraw, *hs, *cst, *ldx;
+    float *xs, *cs, *xraw, *hs, *cst, *ldx, *pairx;
     uint64_t* bars;
     const StepDesc* steps;
     uint32_t tb;
@@ -862,7 +911,45 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             }
             // ---- last layer: theta of one transformed dim at a time, read from tensor memory
             float ldc = 0.f;
-            if (!HELPER)
+            if (!HELPER && d == 1 && half < 2) {
+                // one transformed dim: the two spline groups share its row (see spline_row_search_half)
+                mbar_wait(&bars[B_DFULL_D + 0], p_fd);
+                p_fd ^= 1u;
+                umma::fence_after_sync();
+                ZF_TR(trs);   // theta ready
+                const uint32_t dbase = umma::taddr(tb, lane_base, 256);
+                const uint32_t cross = (K == 16) ? 128u : 0u;
+                float* px = xs + pmod(0 - rot, D) * UM + m;
+                const float v = *px;
+                float* ex = cx.pairx;   // [7][UM]: idx, ks, bs | ko, bo, dk, dkp1
+                RqsBin bin;
+                if (half == 0) {
+                    if (K == 16) spline_row_search_half<16, INVERSE>(dbase, cross, bls, v, bin);
+                    else spline_row_search_half<32, INVERSE>(dbase, cross, bls, v, bin);
+                    ex[0 * UM + m] = __int_as_float(bin.idx); ex[1 * UM + m] = bin.ks; ex[2 * UM + m] = bin.bs;
+                    pair_barrier(3);                         // bin published; both threads' TMEM reads are done
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_DEMPTY_D + 0]);
+                    ZF_TR(trs);   // released
+                    pair_barrier(4);                         // other-axis knot and slopes published
+                    bin.ko = ex[3 * UM + m]; bin.bo = ex[4 * UM + m]; bin.dk = ex[5 * UM + m]; bin.dkp1 = ex[6 * UM + m];
+                    *px = INVERSE ? rqs_eval_inverse(v, bin) : rqs_eval_forward_y(v, bin);
+                } else {
+                    auto other = [&](auto ktag) {
+                        constexpr int KT = decltype(ktag)::value;
+                        OtherHalf<KT, INVERSE> oh;
+                        oh.pre(dbase, cross, bls);
+                        pair_barrier(3);
+                        bin.idx = __float_as_int(ex[0 * UM + m]); bin.ks = ex[1 * UM + m]; bin.bs = ex[2 * UM + m];
+                        oh.post(bin);
+                    };
+                    if (K == 16) other(std::integral_constant<int, 16>{});
+                    else other(std::integral_constant<int, 32>{});
+                    ex[3 * UM + m] = bin.ko; ex[4 * UM + m] = bin.bo; ex[5 * UM + m] = bin.dk; ex[6 * UM + m] = bin.dkp1;
+                    pair_barrier(4);
+                    if (!INVERSE) ldc += rqs_eval_forward_ld(v, bin);
+                }
+            } else if (!HELPER)
             for (int jj = half; jj < d && half < 2; jj += 2) {
                 mbar_wait(&bars[B_DFULL_D + half], p_fd);
                 p_fd ^= 1u;
@@ -941,7 +1028,8 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
     float* hs = xraw + UM * (D + C);          // [Fmax][UM]  BatchNorm output
     float* cst = hs + a.u_fmax * UM;          // [2][cl.total] per-coupling constants
     float* ldx = cst + 2 * cl.total;
-    float* ring = ldx + 3 * UM;
+    float* pairx = ldx + 3 * UM;              // [7][UM] exchange between the two threads of a shared spline row
+    float* ring = pairx + 8 * UM;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
@@ -1156,7 +1244,7 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
     // setmaxnreg moves registers inside the pool the CTA was launched with (640 threads x 96 registers; the rest of
     // the register file is not reachable), so the three allocations must add up to it or the increase never succeeds.
     static_assert(256 * 144 + 256 * 56 + 128 * 80 == 640 * 96, "setmaxnreg split must equal the launch allocation");
-    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, bars, steps, tb, n_tiles, cl, in16, in_bytes};
+    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, bars, steps, tb, n_tiles, cl, in16, in_bytes};
     if constexpr (NG == 4) {
         if (warp < 8) {
             reg_inc<144>();

@@ -666,31 +666,30 @@ __device__ __forceinline__ void spline_row_search_half(uint32_t dbase, uint32_t 
         rqs_block_search<KT, false>(pa, v, kn, b.idx, b.ks, b.bs, chk);
 }
 
-// group 1, before the bin is known: loads of the other-axis and slope blocks, squareplus + sum of the other axis
+// group 1: loads of the other-axis and slope blocks, squareplus + sum of the other axis while group 0 searches; then
+// (pair barrier 3) the bin index arrives through ex[0..2], and the other-axis knot and the slopes are selected
 template <int KT, bool INVERSE>
-struct OtherHalf {
-    float pb[KT], ps[KT], sum;
-    bool safe;
-    __device__ __forceinline__ void pre(uint32_t dbase, uint32_t cross_off, const float* __restrict__ bias) {
-        constexpr int co_ = INVERSE ? 0 : KT;
-        float wb[KT], ws[KT];
-        RqsCheck chk;
-        theta_block_issue<KT>(dbase, cross_off, co_, pb, wb);
-        theta_block_issue<KT>(dbase, cross_off, 2 * KT, ps, ws);
-        umma::wait_ld();                                    // every TMEM read of this thread is done
-        const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
-        (void)theta_block_finish<KT>(2 * KT, bias, ps, ws);
-        safe = __any_sync(0xffffffffu, !(amax_o < kThetaFastBound));
-        if (safe) rqs_block_other_pre<KT, true>(pb, sum, chk);
-        else rqs_block_other_pre<KT, false>(pb, sum, chk);
-    }
-    __device__ __forceinline__ void post(RqsBin& b) {
-        const KnotNorm kn = make_knot_norm(KT);
-        if (safe) rqs_block_other_post<KT, true>(pb, sum, b.idx, kn, b.ko, b.bo);
-        else rqs_block_other_post<KT, false>(pb, sum, b.idx, kn, b.ko, b.bo);
-        rqs_block_slopes<KT>(ps, b.idx, b.dk, b.dkp1);
-    }
-};
+__device__ __forceinline__ void spline_row_other_half(uint32_t dbase, uint32_t cross_off, const float* __restrict__ bias,
+                                                      const float* ex, int m, RqsBin& b) {
+    constexpr int co_ = INVERSE ? 0 : KT;
+    const KnotNorm kn = make_knot_norm(KT);
+    float pb[KT], ps[KT], wb[KT], ws[KT];
+    RqsCheck chk;
+    theta_block_issue<KT>(dbase, cross_off, co_, pb, wb);
+    theta_block_issue<KT>(dbase, cross_off, 2 * KT, ps, ws);
+    umma::wait_ld();                                    // every TMEM read of this thread is done
+    const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
+    (void)theta_block_finish<KT>(2 * KT, bias, ps, ws);
+    float sum;
+    const bool safe = __any_sync(0xffffffffu, !(amax_o < kThetaFastBound));
+    if (safe) rqs_block_other_pre<KT, true>(pb, sum, chk);
+    else rqs_block_other_pre<KT, false>(pb, sum, chk);
+    pair_barrier(3);
+    b.idx = __float_as_int(ex[0 * UM + m]); b.ks = ex[1 * UM + m]; b.bs = ex[2 * UM + m];
+    if (safe) rqs_block_other_post<KT, true>(pb, sum, b.idx, kn, b.ko, b.bo);
+    else rqs_block_other_post<KT, false>(pb, sum, b.idx, kn, b.ko, b.bo);
+    rqs_block_slopes<KT>(ps, b.idx, b.dk, b.dkp1);
+}
 
 // ---- the epilogue / SIMT role of the tensor-core chain kernel ------------------------------------------------
 // NG column groups of 4 warps each (group g = warp / 4 owns CW = 32 / NG columns of every 32-column K-chunk and
@@ -943,16 +942,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     bin.ko = ex[3 * UM + m]; bin.bo = ex[4 * UM + m]; bin.dk = ex[5 * UM + m]; bin.dkp1 = ex[6 * UM + m];
                     *px = INVERSE ? rqs_eval_inverse(v, bin) : rqs_eval_forward_y(v, bin);
                 } else {
-                    auto other = [&](auto ktag) {
-                        constexpr int KT = decltype(ktag)::value;
-                        OtherHalf<KT, INVERSE> oh;
-                        oh.pre(dbase, cross, bls);
-                        pair_barrier(3);
-                        bin.idx = __float_as_int(ex[0 * UM + m]); bin.ks = ex[1 * UM + m]; bin.bs = ex[2 * UM + m];
-                        oh.post(bin);
-                    };
-                    if (K == 16) other(std::integral_constant<int, 16>{});
-                    else other(std::integral_constant<int, 32>{});
+                    if (K == 16) spline_row_other_half<16, INVERSE>(dbase, cross, bls, ex, m, bin);
+                    else spline_row_other_half<32, INVERSE>(dbase, cross, bls, ex, m, bin);
                     ex[3 * UM + m] = bin.ko; ex[4 * UM + m] = bin.bo; ex[5 * UM + m] = bin.dk; ex[6 * UM + m] = bin.dkp1;
                     pair_barrier(4);
                     if (!INVERSE) ldc += rqs_eval_forward_ld(v, bin);

@@ -355,6 +355,13 @@ def run_gpu(args):
 
     e2e_ms, _, _, _ = timed(step_e2e, K, W, drain=drain_e2e)
     e2e_value = world * M * K / (e2e_ms * 1e-3)
+    # the host buffer of the last timed step must hold that step's result (bit-exact against a device-resident rerun)
+    last = W + K - 1
+    torch.cuda.synchronize()
+    ref = flow.apply(variables, xs_d[last % n_sets], cs_d[last % n_sets])
+    e2e_checked = bool(torch.equal(lp_hosts[last & 1], ref.cpu()))
+    if not e2e_checked:
+        raise RuntimeError("e2e pipeline returned a result that differs from the device-resident path")
 
     # Flow.sample's inverse chain on a given latent draw (same events/s unit), N=1 extra
     extras = {}
@@ -428,7 +435,7 @@ def run_gpu(args):
                    "latent": "Beta(12)", "l2": f"rotating {n_sets} input sets ({n_sets * (bytes_in + bytes_out) / 1e6:.0f} MB > 126 MB L2)",
                    "seed": 0},
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
-                "ms_per_step": e2e_ms / K},
+                "ms_per_step": e2e_ms / K, "result_checked": e2e_checked},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -1268,6 +1268,503 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
 }
 
 // =============================================================================================
+// Two tiles in flight for flows whose couplings transform ONE dim (every 2-D / 3-D flow: the headline config).
+//
+// The single-tile kernel above is a serial chain per tile: activation phases (SFU / issue bound), GEMM tails, the
+// spline row, the tile's load / ShiftBounds / store, each waiting for the previous one, because tensor memory is full
+// and a second tile cannot simply be added.  But the chain only needs the activations (A) and the hidden
+// accumulators (D0, D1) during the conditioner, and only the theta columns during the spline - so two tiles can
+// share the same tensor memory if they are half a coupling apart.  Warps are specialised by PHASE instead of by
+// column group:
+//   warps 0-7   "activation" warps (S1): BatchNorm, first Dense, hidden epilogues, for slot 0 and slot 1 in turn
+//   warps 8-11  "row" warps (S2): tile load, ShiftBounds, the spline row (theta from tensor memory), latent + store
+//   warp 12     producer (weights ring, per-(coupling, slot) constants, next tile's raw rows)
+//   warp 13     MMA issuer (same unit logic as above, in the interleaved order)
+// Every role walks the same static schedule: for each pair of tiles, for each step, slot 0 then slot 1.  While S2 runs
+// the spline of slot X, S1 is already in the next activation phase of slot Y, and the MMA tails of one slot hide under
+// the other slot's work.  setmaxnreg gives S2 the registers of the spline code and S1 a small budget.
+// =============================================================================================
+enum PpBar : int { PP_FULL = 0, PP_EMPTY = 4, PP_AREADY = 8, PP_DFULL_H = 12, PP_DFULL_D = 13, PP_DEMPTY_D = 14,
+                   PP_CFULL = 15, PP_CEMPTY = 19, PP_XFULL = 23, PP_XEMPTY = 25, PP_XSREADY = 27, PP_COUNT = 32 };
+constexpr int PP_TBUF = 4;   // tile-state buffers: the row warps prepare the next pair's tiles while the current pair runs
+constexpr int PP_THREADS = 512;
+constexpr int PP_CBUF = 4;   // constant-block buffers: one (coupling, slot) occurrence each, fetched one occurrence ahead
+
+__host__ __device__ inline size_t umma_pp_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
+    return (PP_TBUF + 2) * (size_t)UM * (D + C) + (size_t)Fmax * UM + PP_CBUF * (size_t)ucst_layout(Fmax, Hmax, BLmax).total +
+           PP_TBUF * UM +
+           (size_t)URING * URING_FLOATS + 2 * PP_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float) + USTEPS;
+}
+
+__device__ __forceinline__ void s1_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void s2_barrier() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int PW = 12, MW = 13;
+    const int D = a.D, C = a.C;
+    const UCst cl = ucst_layout(a.u_fmax, a.u_hmax, a.u_blmax);
+    float* xsb = smem;                          // [PP_TBUF][D][UM]  tile state (tile k in buffer k % PP_TBUF), feature-major
+    float* csb = xsb + PP_TBUF * D * UM;        // [PP_TBUF][C][UM]
+    float* xraw = csb + PP_TBUF * C * UM;       // [2]{[UM][D] | [UM][C]}  raw rows of upcoming tiles (bulk copy)
+    float* hs = xraw + 2 * UM * (D + C);        // [Fmax][UM]  BatchNorm output (S1 only)
+    float* cst = hs + a.u_fmax * UM;            // [PP_CBUF][cl.total]
+    float* ldacc = cst + PP_CBUF * cl.total;    // [PP_TBUF][UM]  log-det accumulator per tile (S2 only)
+    float* ring = ldacc + PP_TBUF * UM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + PP_COUNT);
+    StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
+    int* coup_si = reinterpret_cast<int*>(steps_s + USTEPS);   // processing positions of the coupling steps
+    const float* wsf = a.ws;
+
+    {   // step program -> shared memory (the host only launches this kernel when it fits)
+        const int4* src = reinterpret_cast<const int4*>(a.ws);
+        int4* dst = reinterpret_cast<int4*>(steps_s);
+        for (int i = tid; i < a.n_steps * (int)(sizeof(StepDesc) / 16); i += PP_THREADS) dst[i] = src[i];
+    }
+    const StepDesc* steps = steps_s;
+    if (tid == 0) {
+        for (int i = 0; i < URING; ++i) { mbar_init(&bars[PP_FULL + i], 1); mbar_init(&bars[PP_EMPTY + i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[PP_AREADY + i], 256);
+        mbar_init(&bars[PP_DFULL_H], 1);
+        mbar_init(&bars[PP_DFULL_D], 1);
+        mbar_init(&bars[PP_DEMPTY_D], 128);
+        for (int i = 0; i < PP_CBUF; ++i) { mbar_init(&bars[PP_CFULL + i], 1); mbar_init(&bars[PP_CEMPTY + i], 256 + 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[PP_XFULL + i], 1); mbar_init(&bars[PP_XEMPTY + i], 128); }
+        for (int i = 0; i < PP_TBUF; ++i) mbar_init(&bars[PP_XSREADY + i], 128);
+        mbar_fence_init();
+    }
+    if (warp == MW) umma::tmem_alloc(tmem_slot, 512);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+    if (tid == 0) {
+        int n = 0;
+        for (int si = 0; si < a.n_steps; ++si)
+            if (steps[INVERSE ? (a.n_steps - 1 - si) : si].kind == kStepKindCoupling) coup_si[n++] = si;
+    }
+    __syncthreads();
+    int ncoup = 0;
+    for (int si = 0; si < a.n_steps; ++si)
+        if (steps[si].kind == kStepKindCoupling) ++ncoup;
+    auto step_at = [&](int si) -> const StepDesc& { return steps[INVERSE ? (a.n_steps - 1 - si) : si]; };
+
+    const long long n_tiles = (a.M + UM - 1) / UM;
+    const long long n_my = ((long long)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_occ = n_my * ncoup;       // (coupling, tile) occurrences of this CTA, in schedule order
+    auto tile_of = [&](long long k) { return (long long)blockIdx.x + k * gridDim.x; };
+    const uint32_t in_bytes = (a.sample ? 0u : (uint32_t)(UM * D * 4)) + (uint32_t)(UM * C * 4);
+    const bool in16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
+    auto tile_by_bulk = [&](long long t) { return in16 && in_bytes != 0 && (t + 1) * UM <= a.M; };
+    // the coupling step of occurrence n: pairs of tiles, coupling-major, slot-minor
+    auto occ_step = [&](long long n) -> const StepDesc& {
+        const long long per_pair = 2LL * ncoup;
+        const long long p = n / per_pair;
+        const long long r = n - p * per_pair;
+        const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
+        return step_at(coup_si[(int)(r / nslots)]);
+    };
+
+    // ------------------------------------------------------------------------------------------------ roles
+    auto producer_role = [&]() {
+        if (lane != 0) return;
+        uint32_t stage = 0, phase = 0;
+        long long kc = 0;   // constant blocks issued
+        auto issue_consts = [&]() {
+            if (kc >= n_occ) return;
+            const uint32_t b = (uint32_t)(kc % PP_CBUF);
+            mbar_wait(&bars[PP_CEMPTY + b], (uint32_t)((kc / PP_CBUF) & 1) ^ 1u);
+            mbar_arrive_expect_tx(&bars[PP_CFULL + b], (uint32_t)cl.total * 4u);
+            bulk_copy_g2s(cst + (size_t)b * cl.total, wsf + occ_step(kc).off_C, (uint32_t)cl.total * 4u, &bars[PP_CFULL + b]);
+            ++kc;
+        };
+        // tile k (slot k & 1, pair k >> 1) is staged in raw buffer k & 1; its previous user was tile k - 2.  Only full
+        // tiles of aligned inputs come this way, and only the globally last tile can be ragged, so the use count of a
+        // buffer is the pair index on both sides.
+        auto issue_inputs = [&](long long k) {
+            if (k >= n_my) return;
+            const long long t = tile_of(k);
+            if (!tile_by_bulk(t)) return;
+            const int b = (int)(k & 1);
+            const uint32_t use = (uint32_t)(k >> 1);
+            float* dst = xraw + (size_t)b * UM * (D + C);
+            mbar_wait(&bars[PP_XEMPTY + b], (use & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&bars[PP_XFULL + b], in_bytes);
+            if (!a.sample) bulk_copy_g2s(dst, a.x + t * UM * D, (uint32_t)(UM * D * 4), &bars[PP_XFULL + b]);
+            if (C) bulk_copy_g2s(dst + UM * D, a.c + t * UM * C, (uint32_t)(UM * C * 4), &bars[PP_XFULL + b]);
+        };
+        issue_inputs(0);
+        issue_inputs(1);
+        issue_consts();
+        for (long long p = 0; 2 * p < n_my; ++p) {
+            const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = step_at(si);
+                if (s.kind != kStepKindCoupling) continue;
+                const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                for (int slot = 0; slot < nslots; ++slot) {
+                    for (int u = 0; u < L; ++u) {   // L - 1 hidden units + one last-layer unit (d == 1)
+                        const bool hid = u < L - 1;
+                        const int N = hid ? 128 : NL;
+                        const float* base = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L];
+                        const uint32_t bytes = (uint32_t)N * 256u;
+                        for (int c = 0; c < 4; ++c) {
+                            mbar_wait(&bars[PP_EMPTY + stage], phase ^ 1u);
+                            mbar_arrive_expect_tx(&bars[PP_FULL + stage], bytes);
+                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, base + (size_t)c * N * 64, bytes, &bars[PP_FULL + stage]);
+                            if (++stage == URING) { stage = 0; phase ^= 1u; }
+                        }
+                        if (u == 0) {
+                            issue_consts();                       // the next occurrence's constants
+                            // once per tile: the rows of the tile that takes this slot in the next pair
+                            if (si == coup_si[0]) issue_inputs(2 * (p + 1) + slot);
+                        }
+                    }
+                }
+            }
+        }
+    };
+
+    auto mma_role = [&]() {
+        uint32_t phase = 0, p_ar = 0, p_ed = 0;
+        bool theta_pending = false;   // D0/D1 hold a theta row that the row warps may still be reading
+        for (long long p = 0; 2 * p < n_my; ++p) {
+            const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = step_at(si);
+                if (s.kind != kStepKindCoupling) continue;
+                const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                for (int slot = 0; slot < nslots; ++slot) {
+                    for (int u = 0; u < L; ++u) {
+                        const bool hid = u < L - 1;
+                        const bool split_acc = hid || NL <= 64;
+                        const int nfree = (u == 0) ? 0 : (hid ? 4 : (split_acc ? 2 : 3));
+                        int waited = 0;
+                        if (theta_pending) { mbar_wait(&bars[PP_DEMPTY_D], p_ed); p_ed ^= 1u; theta_pending = false; }
+                        umma::fence_after_sync();
+                        const uint32_t dmain = tb + 256u;
+                        const uint32_t dcross = split_acc ? dmain + 128u : dmain;
+                        static_assert(URING == 4, "the MMA issuer maps chunk c to ring stage c");
+                        auto issue_unit = [&](auto ntag) {
+                            constexpr int N = decltype(ntag)::value;
+                            constexpr uint32_t lbo = (uint32_t)(N >> 3) * 128u;
+                            constexpr uint32_t idesc = umma::instr_desc_tf32(N);
+                            constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+                            const uint32_t ring16 = (smem_u32(ring) >> 4) | ((lbo >> 4) << 16);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int need = max(c + 1, nfree);
+#pragma unroll
+                                for (int w = 0; w < 4; ++w)
+                                    if (w >= waited && w < need) mbar_wait(&bars[PP_AREADY + w], p_ar);
+                                waited = max(waited, need);
+                                mbar_wait(&bars[PP_FULL + c], phase);
+                                umma::fence_after_sync();
+                                if (umma::elect_one()) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) {
+                                        const uint32_t off_hi = (uint32_t)(c * URING_FLOATS * 4 + ks * 2 * (int)lbo) >> 4;
+                                        const uint32_t off_lo = off_hi + ((uint32_t)N * 128u >> 4);
+                                        const uint64_t dhi = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_hi);
+                                        const uint64_t dlo = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_lo);
+                                        const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                                        const bool first = (c | ks) == 0;
+                                        umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, !first);
+                                        umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);
+                                        umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, split_acc ? !first : true);
+                                    }
+                                    umma::commit(&bars[PP_EMPTY + c]);
+                                    if (c == 3) umma::commit(&bars[hid ? PP_DFULL_H : PP_DFULL_D]);
+                                }
+                                __syncwarp();
+                            }
+                        };
+                        if (hid) issue_unit(std::integral_constant<int, 128>{});
+                        else if (NL == 48) issue_unit(std::integral_constant<int, 48>{});
+                        else issue_unit(std::integral_constant<int, 96>{});
+                        phase ^= 1u;
+                        p_ar ^= 1u;              // every unit reads a new version of the activations (d == 1)
+                        if (!hid) theta_pending = true;
+                    }
+                }
+            }
+        }
+    };
+
+    // S1: BatchNorm + first Dense + hidden epilogues of one (coupling, slot) occurrence after the other
+    auto activation_role = [&]() {
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32);
+        constexpr int CW = 16;
+        uint32_t p_fh = 0;
+        long long n1 = 0;
+        for (long long p = 0; 2 * p < n_my; ++p) {
+            const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
+            int cj = -1;   // ordinal of the coupling inside the step program
+            for (int si = 0; si < a.n_steps; ++si) {
+                const StepDesc& s = step_at(si);
+                if (s.kind != kStepKindCoupling) continue;
+                ++cj;
+                const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
+#pragma unroll 1
+                for (int slot = 0; slot < nslots; ++slot, ++n1) {
+                    const long long k = 2 * p + slot;
+                    const int tbuf = (int)(k % PP_TBUF);
+                    const float* xs = xsb + tbuf * D * UM;
+                    const float* cs = csb + tbuf * C * UM;
+                    const uint32_t cb = (uint32_t)(n1 % PP_CBUF);
+                    const float* cc = cst + (size_t)cb * cl.total;
+                    const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh;
+                    mbar_wait(&bars[PP_CFULL + cb], (uint32_t)((n1 / PP_CBUF) & 1));
+                    // the cj-th signal of the (k / PP_TBUF)-th tile that uses this state buffer
+                    mbar_wait(&bars[PP_XSREADY + tbuf], (uint32_t)(((k / PP_TBUF) * ncoup + cj) & 1));
+                    // hstack(xc, c) + eval BatchNorm (bijectors.py:341-342)
+                    for (int f = half; f < F; f += 2) {
+                        const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
+                        hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+                    }
+                    s1_barrier();
+                    // the activations of the previous occurrence are still the A operand of its last-layer MMAs: wait
+                    // for their completion (the accumulator-full barrier the row warps also wait on) before rewriting
+                    if (n1 > 0) {
+                        mbar_wait(&bars[PP_DFULL_D], (uint32_t)((n1 - 1) & 1));
+                        umma::fence_after_sync();
+                    }
+                    float hreg[4];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const int n0 = c * 32 + half * CW;
+                        float acc[CW], ahi[CW], alo[CW];
+                        {
+                            const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
+#pragma unroll
+                            for (int g4 = 0; g4 < CW / 4; ++g4) {
+                                const float4 t = bv[g4];
+                                acc[g4 * 4 + 0] = t.x; acc[g4 * 4 + 1] = t.y; acc[g4 * 4 + 2] = t.z; acc[g4 * 4 + 3] = t.w;
+                            }
+                        }
+                        auto fma_row = [&](float h, int f) {
+                            const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
+#pragma unroll
+                            for (int g4 = 0; g4 < CW / 4; ++g4) {
+                                const float4 wv = w[g4];
+                                acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
+                                acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
+                                acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
+                                acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
+                            }
+                        };
+#pragma unroll
+                        for (int f = 0; f < 4; ++f)
+                            if (f < F) fma_row(hreg[f], f);
+                        for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
+                        activation_compute<CW>(acc, ahi, alo);
+                        activation_store<CW>(tb, lane_base, n0, ahi, alo);
+                        umma::wait_st();
+                        umma::fence_before_sync();
+                        umma::mbar_arrive(&bars[PP_AREADY + c]);
+                    }
+                    for (int l = 1; l < L; ++l) {
+                        mbar_wait(&bars[PP_DFULL_H], p_fh);
+                        p_fh ^= 1u;
+                        umma::fence_after_sync();
+                        const float* bh = bhs + (l - 1) * 128;
+                        float vn[CW], wn[CW];
+                        tmem_load<CW>(umma::taddr(tb, lane_base, 256 + half * CW), vn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, 384 + half * CW), wn);
+#pragma unroll 1
+                        for (int c = 0; c < 4; ++c) {
+                            const int n0 = c * 32 + half * CW;
+                            float v[CW], ahi[CW], alo[CW];
+                            umma::wait_ld();
+                            {
+                                const float4* bv = reinterpret_cast<const float4*>(bh + n0);
+#pragma unroll
+                                for (int g4 = 0; g4 < CW / 4; ++g4) {
+                                    const float4 t = bv[g4];
+                                    v[g4 * 4 + 0] = (vn[g4 * 4 + 0] + wn[g4 * 4 + 0]) + t.x;
+                                    v[g4 * 4 + 1] = (vn[g4 * 4 + 1] + wn[g4 * 4 + 1]) + t.y;
+                                    v[g4 * 4 + 2] = (vn[g4 * 4 + 2] + wn[g4 * 4 + 2]) + t.z;
+                                    v[g4 * 4 + 3] = (vn[g4 * 4 + 3] + wn[g4 * 4 + 3]) + t.w;
+                                }
+                            }
+                            if (c < 3) {
+                                tmem_load<CW>(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
+                                tmem_load<CW>(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);
+                            }
+                            activation_compute<CW>(v, ahi, alo);
+                            activation_store<CW>(tb, lane_base, n0, ahi, alo);
+                            umma::wait_st();
+                            umma::fence_before_sync();
+                            umma::mbar_arrive(&bars[PP_AREADY + c]);
+                        }
+                    }
+                    umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // S1 is done with this occurrence's constants
+                    s1_barrier();                                 // hs is rewritten by the next occurrence
+                }
+            }
+        }
+    };
+
+    // S2: one thread per event: tile load, ShiftBounds, spline row, latent + store.  The load and the leading
+    // non-coupling steps of the NEXT pair's tiles are done in the middle of the current pair (right after its first
+    // coupling), so the activation warps never wait for a tile at a pair boundary.
+    auto row_role = [&]() {
+        const int q = warp & 3, m = q * 32 + lane, t2 = tid - 256;   // t2: index inside S2
+        const uint32_t lane_base = (uint32_t)(q * 32);
+        const int rot_in = INVERSE ? a.rot_total : 0;
+        const int fc = coup_si[0];                                   // position of the first coupling
+        uint32_t p_fd = 0;
+        long long n2 = 0;
+        auto tile_ptrs = [&](long long k, float*& xs, float*& cs, float*& lda) {
+            const int tbuf = (int)(k % PP_TBUF);
+            xs = xsb + tbuf * D * UM; cs = csb + tbuf * C * UM; lda = ldacc + tbuf * UM;
+        };
+        auto signal_ready = [&](long long k) { umma::mbar_arrive(&bars[PP_XSREADY + (int)(k % PP_TBUF)]); };
+        auto preamble = [&](long long k) {
+            if (k >= n_my) return;
+            float *xs, *cs, *lda;
+            tile_ptrs(k, xs, cs, lda);
+            const long long tile = tile_of(k), m0 = tile * UM;
+            const int nm = (int)min((long long)UM, a.M - m0);
+            const int rb = (int)(k & 1);
+            // rows -> feature-major tile; padding events sit at 0.5 / 0 and are never stored
+            const bool bulk = tile_by_bulk(tile);
+            const float* raw = xraw + (size_t)rb * UM * (D + C);
+            if (bulk) mbar_wait(&bars[PP_XFULL + rb], (uint32_t)((k >> 1) & 1));
+            const float* xsrc = bulk ? raw : a.x + m0 * D;
+            const float* csrc = bulk ? raw + UM * D : a.c + m0 * C;
+            {
+                int mm = t2 / D, j = t2 - mm * D;
+                const int dm = 128 / D, dj = 128 - dm * D;
+                for (int e = t2; e < UM * D; e += 128) {
+                    int col = j - rot_in;
+                    if (col < 0) col += D;
+                    xs[col * UM + mm] =
+                        (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : xsrc[e]) : 0.5f;
+                    mm += dm; j += dj;
+                    if (j >= D) { j -= D; ++mm; }
+                }
+            }
+            if (C) {
+                int mm = t2 / C, j = t2 - mm * C;
+                const int dm = 128 / C, dj = 128 - dm * C;
+                for (int e = t2; e < UM * C; e += 128) {
+                    cs[j * UM + mm] = (mm < nm) ? csrc[e] : 0.f;
+                    mm += dm; j += dj;
+                    if (j >= C) { j -= C; ++mm; }
+                }
+            }
+            if (bulk) umma::mbar_arrive(&bars[PP_XEMPTY + rb]);
+            s2_barrier();
+            float ld0 = 0.f;
+            for (int si = 0; si < fc; ++si) shift_bounds_row<INVERSE>(step_at(si), wsf, D, xs, UM, m, ld0);   // only non-coupling kind
+            lda[m] = ld0;
+            signal_ready(k);   // the tile state is complete for the first coupling
+        };
+        preamble(0);
+        preamble(1);
+        for (long long p = 0; 2 * p < n_my; ++p) {
+            const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
+            for (int si = fc; si < a.n_steps; ++si) {
+                const StepDesc& s = step_at(si);
+#pragma unroll 1
+                for (int slot = 0; slot < nslots; ++slot) {
+                    const long long k = 2 * p + slot;
+                    float *xs, *cs, *lda;
+                    tile_ptrs(k, xs, cs, lda);
+                    const long long m0 = tile_of(k) * UM;
+                    const int nm = (int)min((long long)UM, a.M - m0);
+                    if (s.kind == kStepKindShiftBounds) {
+                        float ld_sb = 0.f;
+                        shift_bounds_row<INVERSE>(s, wsf, D, xs, UM, m, ld_sb);
+                        lda[m] += ld_sb;
+                    } else {
+                        const int K = s.K, rot = s.rot;
+                        const uint32_t cb = (uint32_t)(n2 % PP_CBUF);
+                        const float* bls = cst + (size_t)cb * cl.total + cl.bl;
+                        mbar_wait(&bars[PP_CFULL + cb], (uint32_t)((n2 / PP_CBUF) & 1));
+                        mbar_wait(&bars[PP_DFULL_D], p_fd);
+                        p_fd ^= 1u;
+                        umma::fence_after_sync();
+                        const uint32_t dbase = umma::taddr(tb, lane_base, 256);
+                        float* px = xs + pmod(0 - rot, D) * UM + m;
+                        const float v = *px;
+                        RqsBin bin;
+                        auto release = [&]() {
+                            umma::fence_before_sync();
+                            umma::mbar_arrive(&bars[PP_DEMPTY_D]);
+                        };
+                        if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls, v, bin, release);
+                        else spline_row_tmem<32, INVERSE>(dbase, 0u, bls, v, bin, release);
+                        umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // last read of this occurrence's constants by S2
+                        if (!INVERSE) {
+                            float y, ld;
+                            rqs_eval_forward(v, bin, y, ld);
+                            *px = y;
+                            lda[m] += ld;
+                        } else {
+                            *px = rqs_eval_inverse(v, bin);
+                        }
+                        ++n2;
+                    }
+                    // as soon as this tile's state is complete for its next coupling, tell the activation warps
+                    if (si + 1 < a.n_steps && step_at(si + 1).kind == kStepKindCoupling) signal_ready(k);
+                    if (si == a.n_steps - 1) {
+                        // ---- store this tile
+                        if (a.mode == kModeLogProb) {
+                            if (m < nm) {
+                                float lat = 0.f;
+                                for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * UM + m], a.lc);
+                                a.lp[m0 + m] = nan_to_num_lp(lat + lda[m]);
+                            }
+                        } else {
+                            const int rot_out = INVERSE ? 0 : a.rot_total;
+                            s2_barrier();
+                            if (a.y) {
+                                for (int e = t2; e < nm * D; e += 128) {
+                                    const int mm = e / D, j = e - mm * D;
+                                    a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * UM + mm];
+                                }
+                            }
+                            if (!INVERSE && a.log_det && m < nm)
+                                a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + lda[m] : lda[m];
+                            s2_barrier();
+                        }
+                    }
+                }
+                if (si == fc) {   // the next pair's tiles: their buffers were released two pairs ago
+                    preamble(2 * (p + 1));
+                    preamble(2 * (p + 1) + 1);
+                }
+            }
+        }
+    };
+
+    // Each setmaxnreg dominates exactly its warpgroup's role: 2 x 96 (S1) + 184 (S2) + 104 (producer, MMA issuer, idle)
+    static_assert(256 * 96 + 128 * 184 + 128 * 104 <= 512 * 128, "register split exceeds the launch allocation");
+    if (warp < 8) {
+        reg_dec<96>();
+        activation_role();
+    } else if (warp < 12) {
+        reg_inc<184>();
+        row_role();
+    } else {
+        reg_dec<104>();
+        if (warp == PW) producer_role();
+        else if (warp == MW) mma_role();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == MW) umma::tmem_dealloc(tb, 512);
+}
+
+// =============================================================================================
 // Two-pipeline variant: tensor memory is full with one tile's operands and accumulators, so a second
 // 128-event tile cannot be in flight and the MMA and epilogue phases of a tile serialise.  Here a CTA
 // runs TWO independent pipelines ("contexts") over 64-event half-tiles that share the same TMEM columns
@@ -1581,6 +2078,7 @@ struct Plan {
     bool umma_ok = true;   // every coupling fits the tensor-core kernel
     int n_couplings = 0;
     int Fmax = 1, Hmax = 1, BLmax = 32;   // shared-memory sizing of the two-pipeline kernel
+    bool all_d1 = true;                   // every coupling transforms a single dim
 };
 
 static int build_plan(const zf_chain* chain, Plan& plan) {
@@ -1636,6 +2134,7 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
                 plan.Fmax = std::max(plan.Fmax, D - d + C);
                 plan.Hmax = std::max(plan.Hmax, std::max(1, cp.n_hidden - 1));
                 plan.BLmax = std::max(plan.BLmax, d * ru(3 * cp.knots - 1, 16));
+                plan.all_d1 = plan.all_d1 && d == 1;
             }
             job.desc.K = cp.knots;
             job.desc.n_hidden = cp.n_hidden;
@@ -1791,6 +2290,24 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
         if (usmem <= (size_t)di.max_smem_optin) {
             const long long tiles = (M + UM - 1) / UM;
             const unsigned ugrid = (unsigned)std::min<long long>(tiles, (long long)di.sm_count);
+            // flows whose couplings transform one dim: two tiles in flight (chain_umma_pp_kernel); ZF_CHAIN_IMPL=umma8
+            // keeps the single-tile kernel for them
+            if (plan.all_d1 && a.n_steps <= USTEPS && !(impl && (strcmp(impl, "umma8") == 0 || strcmp(impl, "umma16") == 0))) {
+                const size_t psmem = umma_pp_smem_floats(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax) * sizeof(float);
+                if (psmem <= (size_t)di.max_smem_optin) {
+                    const unsigned pgrid = (unsigned)std::min<long long>((tiles + 1) / 2, (long long)di.sm_count);
+                    if (mode == kModeInverse) {
+                        ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                        chain_umma_pp_kernel<true><<<pgrid, PP_THREADS, psmem, stream>>>(a);
+                    } else {
+                        ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                        chain_umma_pp_kernel<false><<<pgrid, PP_THREADS, psmem, stream>>>(a);
+                    }
+                    count_launch();
+                    ZF_CUDA_CHECK(cudaGetLastError());
+                    return ZF_OK;
+                }
+            }
             // ZF_CHAIN_IMPL=umma16: 16 epilogue warps with a setmaxnreg register split.  Measured no faster than the
             // default 8 (the activation phases are bound by the SFU / tensor-memory-store port, not by latency).
             const bool eight = !(impl && strcmp(impl, "umma16") == 0);

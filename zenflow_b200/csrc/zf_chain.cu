@@ -1527,12 +1527,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
                     }
                     s1_barrier();
-                    // the activations of the previous occurrence are still the A operand of its last-layer MMAs: wait
-                    // for their completion (the accumulator-full barrier the row warps also wait on) before rewriting
-                    if (n1 > 0) {
-                        mbar_wait(&bars[PP_DFULL_D], (uint32_t)((n1 - 1) & 1));
-                        umma::fence_after_sync();
-                    }
                     float hreg[4];
 #pragma unroll
                     for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
@@ -1564,6 +1558,13 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                             if (f < F) fma_row(hreg[f], f);
                         for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
                         activation_compute<CW>(acc, ahi, alo);
+                        // the activations of the previous occurrence are still the A operand of its last-layer MMAs:
+                        // wait for their completion (the accumulator-full barrier the row warps also wait on) before
+                        // the first store; the first chunk's arithmetic has already run underneath that tail
+                        if (c == 0 && n1 > 0) {
+                            mbar_wait(&bars[PP_DFULL_D], (uint32_t)((n1 - 1) & 1));
+                            umma::fence_after_sync();
+                        }
                         activation_store<CW>(tb, lane_base, n0, ahi, alo);
                         umma::wait_st();
                         umma::fence_before_sync();

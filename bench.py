@@ -411,15 +411,21 @@ def run_gpu(args):
     step_ms = total_ms / K
     tflops = flops * M / (step_ms * 1e-3) / 1e12
     simt = os.environ.get("ZF_CHAIN_IMPL", "").startswith("s")
+    pp = (w["D"] // 2 == 1) and not simt   # single-dim couplings run the two-tiles-in-flight kernel
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this exact workload
+    # (profiles/r01_chain_umma_pp_kernel_ncu.md: 12.51 MB read + 0 written for 1M events of 12 B + parameters)
+    traffic = 12510464 if (pp and args.workload == "two_moons_conditional" and M == 1_000_000) else None
     roofline = {
         "kernel": ("chain_kernel<false>: fused conditioner MLPs (fp32 FFMA) + splines + latent" if simt else
-                   "chain_umma_kernel<false> (zf_flow_log_prob): conditioner GEMMs on tcgen05 (3xTF32, A in TMEM), "
-                   "spline rows read theta from TMEM, latent fused"),
+                   ("chain_umma_pp_kernel<false>" if pp else "chain_umma_kernel<false>") +
+                   " (zf_flow_log_prob): conditioner GEMMs on tcgen05 (3xTF32, A in TMEM), "
+                   "spline rows read theta from TMEM, latent fused" + ("; two tiles in flight" if pp else "")),
         "bound": "tensor", "achieved": tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tflops / pk["bf16"],
-        "traffic": None, "flops_per_event": flops,
+        "traffic": traffic, "flops_per_event": flops,
         "note": "algorithmic fp32 flops (not x3 for the 3xTF32 split; kind::tf32 runs at half the bf16 rate, so the "
                 "tensor pipe executes 6 bf16-equivalents per algorithmic flop); achieved uses the whole step time "
-                "(pack kernels included, <2%); the kernel is bound by the SIMT spline/activation epilogue, see DESIGN.md",
+                "(the three pack launches included, ~5%); the kernel is bound by the SIMT activation / spline phases "
+                "(SFU, tensor-memory store port, issue), see DESIGN.md",
         "tensor_pipe_bf16_equivalent_frac": 6 * tflops / pk["bf16"],
         "frac_of_fp32_simt_peak": tflops / 74.4, "peak_source": pk["source"]}
 

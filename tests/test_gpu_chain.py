@@ -37,12 +37,13 @@ CONFIGS = [
 ]
 
 
-@pytest.fixture(params=["auto", "simt", "umma2", "umma16"])
+@pytest.fixture(params=["auto", "simt", "umma2", "umma8", "umma16"])
 def chain_impl(request, monkeypatch):
     """auto = tensor-core (tcgen05) kernel when the chain fits it, else the FFMA kernel; simt = force FFMA;
-    umma2 = the opt-in two-pipeline tensor-core variant, umma16 = the opt-in 16-epilogue-warp layout (both fall
-    back like auto when the chain does not fit)."""
-    if request.param in ("simt", "umma2", "umma16"):
+    umma2 = the opt-in two-pipeline tensor-core variant, umma8 / umma16 = the single-tile kernel with 8 / 16 epilogue
+    warps (auto picks the two-tiles-in-flight kernel for single-dim couplings, umma8 otherwise); all fall back like auto
+    when the chain does not fit."""
+    if request.param in ("simt", "umma2", "umma8", "umma16"):
         monkeypatch.setenv("ZF_CHAIN_IMPL", request.param)
     else:
         monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
@@ -360,3 +361,38 @@ def test_unaligned_device_inputs_and_tail_tiles(offset_rows):
     lp64, _ = zo.flow_log_prob(ops, to64(v), x[offset_rows:offset_rows + M].astype(np.float64),
                                c[offset_rows:offset_rows + M].astype(np.float64))
     assert_fp32_parity(lp, lp64, lpo, "log_prob", atol=5e-5, slack=4.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,C,K,ncoup", [(2, 1, 16, 2), (3, 0, 32, 3)])
+def test_two_tile_kernel_is_bit_equal_to_single_tile(D, C, K, ncoup, monkeypatch):
+    """Flows with single-dim couplings run two tiles in flight (phase-specialised warps, shared tensor memory); the
+    arithmetic per event is the same as in the single-tile kernel, so the outputs must agree bit for bit - a race
+    or a missed barrier between the roles would show up as a difference at this size.  Also run to run."""
+    import torch
+
+    from zenflow_b200 import Flow
+
+    M = 300_077
+    ops = zo.make_chain(D, K, (128, 128), n_couplings=ncoup, roll_shift=1)
+    x, c = _data(M, D, C, seed=9)
+    v = trained_variables(ops, x[:4096], None if c is None else c[:4096], seed=3)
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    fv = torch.utils._pytree.tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda(), fv)
+    xd = torch.from_numpy(x).cuda()
+    cd = None if c is None else torch.from_numpy(c).cuda()
+    u = torch.rand(M, D, device="cuda") * 0.9 + 0.05
+    out = {}
+    for impl in ("default", "umma8"):
+        if impl == "default":
+            monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
+        else:
+            monkeypatch.setenv("ZF_CHAIN_IMPL", impl)
+        lps = [flow.apply(fv, xd, cd) for _ in range(3)]
+        inv = flow.bijector.apply({"params": fv["params"]["bijector"], "batch_stats": fv["batch_stats"]["bijector"]}, u, cd,
+                                  method="inverse")
+        assert all(torch.equal(lps[0], t) for t in lps[1:])
+        out[impl] = (lps[0], inv)
+    assert torch.equal(out["default"][0], out["umma8"][0])
+    assert torch.equal(out["default"][1], out["umma8"][1])

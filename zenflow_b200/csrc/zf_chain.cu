@@ -1530,15 +1530,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                     float hreg[4];
 #pragma unroll
                     for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
-                    // pre-activations of chunk c: bias + F rank-1 updates.  Chunk c + 1 is computed between the
-                    // arithmetic and the stores of chunk c, so its shared-memory loads hide under the SFU work
-                    auto pre_activations = [&](int c, float (&acc)[CW]) {
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
                         const int n0 = c * 32 + half * CW;
-                        const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
+                        float acc[CW], ahi[CW], alo[CW];
+                        {
+                            const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
 #pragma unroll
-                        for (int g4 = 0; g4 < CW / 4; ++g4) {
-                            const float4 t = bv[g4];
-                            acc[g4 * 4 + 0] = t.x; acc[g4 * 4 + 1] = t.y; acc[g4 * 4 + 2] = t.z; acc[g4 * 4 + 3] = t.w;
+                            for (int g4 = 0; g4 < CW / 4; ++g4) {
+                                const float4 t = bv[g4];
+                                acc[g4 * 4 + 0] = t.x; acc[g4 * 4 + 1] = t.y; acc[g4 * 4 + 2] = t.z; acc[g4 * 4 + 3] = t.w;
+                            }
                         }
                         auto fma_row = [&](float h, int f) {
                             const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
@@ -1555,15 +1557,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         for (int f = 0; f < 4; ++f)
                             if (f < F) fma_row(hreg[f], f);
                         for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
-                    };
-                    float acc[CW];
-                    pre_activations(0, acc);
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        const int n0 = c * 32 + half * CW;
-                        float ahi[CW], alo[CW];
                         activation_compute<CW>(acc, ahi, alo);
-                        if (c < 3) pre_activations(c + 1, acc);
                         // the activations of the previous occurrence are still the A operand of its last-layer MMAs:
                         // wait for their completion (the accumulator-full barrier the row warps also wait on) before
                         // the first store; the first chunk's arithmetic has already run underneath that tail

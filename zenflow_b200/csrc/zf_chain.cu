@@ -1291,7 +1291,7 @@ constexpr int PP_THREADS = 512;
 constexpr int PP_CBUF = 4;   // constant-block buffers: one (coupling, slot) occurrence each, fetched one occurrence ahead
 
 __host__ __device__ inline size_t umma_pp_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
-    return (PP_TBUF + 2) * (size_t)UM * (D + C) + (size_t)Fmax * UM + PP_CBUF * (size_t)ucst_layout(Fmax, Hmax, BLmax).total +
+    return (PP_TBUF + 2) * (size_t)UM * (D + C) + 2 * (size_t)Fmax * UM + PP_CBUF * (size_t)ucst_layout(Fmax, Hmax, BLmax).total +
            PP_TBUF * UM +
            (size_t)URING * URING_FLOATS + 2 * PP_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float) + USTEPS;
 }
@@ -1309,8 +1309,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
     float* xsb = smem;                          // [PP_TBUF][D][UM]  tile state (tile k in buffer k % PP_TBUF), feature-major
     float* csb = xsb + PP_TBUF * D * UM;        // [PP_TBUF][C][UM]
     float* xraw = csb + PP_TBUF * C * UM;       // [2]{[UM][D] | [UM][C]}  raw rows of upcoming tiles (bulk copy)
-    float* hs = xraw + 2 * UM * (D + C);        // [Fmax][UM]  BatchNorm output (S1 only)
-    float* cst = hs + a.u_fmax * UM;            // [PP_CBUF][cl.total]
+    float* hs2 = xraw + 2 * UM * (D + C);       // [2][Fmax][UM]  BatchNorm output by occurrence parity (S1 only)
+    float* cst = hs2 + 2 * a.u_fmax * UM;       // [PP_CBUF][cl.total]
     float* ldacc = cst + PP_CBUF * cl.total;    // [PP_TBUF][UM]  log-det accumulator per tile (S2 only)
     float* ring = ldacc + PP_TBUF * UM;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
@@ -1501,6 +1501,27 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
         constexpr int CW = 16;
         uint32_t p_fh = 0;
         long long n1 = 0;
+        long long bn_done = -1;   // occurrence whose BatchNorm output is already in hs2[n & 1]
+        // waits + hstack(xc, c) + eval BatchNorm (bijectors.py:341-342) of occurrence n = (pair p, coupling cj, slot)
+        auto batch_norm = [&](long long n, long long p, int cj, int slot) {
+            const StepDesc& s = step_at(coup_si[cj]);
+            const int d = s.d, F = s.F, F_p = ru(F, KC), rot = s.rot;
+            const long long k = 2 * p + slot;
+            const int tbuf = (int)(k % PP_TBUF);
+            const float* xs = xsb + tbuf * D * UM;
+            const float* cs = csb + tbuf * C * UM;
+            const uint32_t cb = (uint32_t)(n % PP_CBUF);
+            const float* bns = cst + (size_t)cb * cl.total + cl.bn;
+            float* hs = hs2 + (size_t)(n & 1) * a.u_fmax * UM;
+            mbar_wait(&bars[PP_CFULL + cb], (uint32_t)((n / PP_CBUF) & 1));
+            // the cj-th signal of the (k / PP_TBUF)-th tile that uses this state buffer
+            mbar_wait(&bars[PP_XSREADY + tbuf], (uint32_t)(((k / PP_TBUF) * ncoup + cj) & 1));
+            for (int f = half; f < F; f += 2) {
+                const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
+                hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+            }
+            bn_done = n;
+        };
         for (long long p = 0; 2 * p < n_my; ++p) {
             const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
             int cj = -1;   // ordinal of the coupling inside the step program
@@ -1508,25 +1529,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                 const StepDesc& s = step_at(si);
                 if (s.kind != kStepKindCoupling) continue;
                 ++cj;
-                const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
+                const int F = s.F, L = s.n_hidden;
 #pragma unroll 1
                 for (int slot = 0; slot < nslots; ++slot, ++n1) {
-                    const long long k = 2 * p + slot;
-                    const int tbuf = (int)(k % PP_TBUF);
-                    const float* xs = xsb + tbuf * D * UM;
-                    const float* cs = csb + tbuf * C * UM;
                     const uint32_t cb = (uint32_t)(n1 % PP_CBUF);
                     const float* cc = cst + (size_t)cb * cl.total;
-                    const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh;
-                    mbar_wait(&bars[PP_CFULL + cb], (uint32_t)((n1 / PP_CBUF) & 1));
-                    // the cj-th signal of the (k / PP_TBUF)-th tile that uses this state buffer
-                    mbar_wait(&bars[PP_XSREADY + tbuf], (uint32_t)(((k / PP_TBUF) * ncoup + cj) & 1));
-                    // hstack(xc, c) + eval BatchNorm (bijectors.py:341-342)
-                    for (int f = half; f < F; f += 2) {
-                        const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
-                        hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
-                    }
-                    s1_barrier();
+                    const float *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh;
+                    const float* hs = hs2 + (size_t)(n1 & 1) * a.u_fmax * UM;
+                    if (bn_done != n1) batch_norm(n1, p, cj, slot);
+                    s1_barrier();   // hs of this occurrence complete; every read of the other parity's hs is over
                     float hreg[4];
 #pragma unroll
                     for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
@@ -1571,6 +1582,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         umma::mbar_arrive(&bars[PP_AREADY + c]);
                     }
                     for (int l = 1; l < L; ++l) {
+                        if (l == 1 && nslots == 2) {
+                            // While the first hidden GEMM finishes: the BatchNorm of the next occurrence.  It belongs
+                            // to the other tile of the pair (or to the next pair), whose state does not depend on
+                            // anything this occurrence still has to produce, so waiting for it here cannot deadlock.
+                            long long pn = p;
+                            int cjn = cj, sn = 1;
+                            if (slot == 1) { sn = 0; if (++cjn == ncoup) { cjn = 0; ++pn; } }
+                            if (2 * pn < n_my) batch_norm(n1 + 1, pn, cjn, sn);
+                        }
                         mbar_wait(&bars[PP_DFULL_H], p_fh);
                         p_fh ^= 1u;
                         umma::fence_after_sync();
@@ -1606,7 +1626,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         }
                     }
                     umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // S1 is done with this occurrence's constants
-                    s1_barrier();                                 // hs is rewritten by the next occurrence
                 }
             }
         }

@@ -32,6 +32,8 @@ CONFIGS = [
     ("deep_set_flow", 2, 8, 16, (128,) * 6, None, 1, 1000),
     ("bounded16", 16, 0, 32, (128, 128), 8, 2, 3001),
     ("cond16", 16, 4, 32, (128, 128), 8, 2, 1500),
+    ("one_hidden_k32", 3, 2, 32, (128,), 4, 1, 4099),      # tensor-core kernels with no hidden-layer GEMM
+    ("three_hidden", 2, 0, 16, (128, 128, 128), 3, 1, 2500),
     ("odd", 5, 3, 7, (64, 48), None, 1, 2000),
     ("wide", 3, 0, 4, (200,), None, 1, 333),
 ]

@@ -76,7 +76,14 @@ struct PackJob {
 
 constexpr int kSbStride = 8;  // floats per column: kind, a, b, xmin, xmax, mul, log(mul), -
 
-__global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ PackJob job, float* ws) {
+// Up to kPackBatch steps per launch (blockIdx.y = step of the batch): kernel parameters may be 32 KB since CUDA 12.1,
+// so a whole chain's jobs travel in one launch instead of one launch per step.
+constexpr int kPackBatch = 16;
+struct PackBatch { PackJob jobs[kPackBatch]; };
+static_assert(sizeof(PackBatch) <= 32000, "PackBatch must fit the kernel parameter space");
+
+__global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ PackBatch batch, float* ws) {
+    const PackJob& job = batch.jobs[blockIdx.y];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsz = gridDim.x * blockDim.x;
     const StepDesc& s = job.desc;
@@ -2258,9 +2265,14 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     if (int rc = get_device_info(&di)) return rc;
 
     float* ws = static_cast<float*>(workspace);
-    for (const PackJob& job : plan.jobs) {
-        // latency-bound re-layout of ~50k parameters: one thin wave over all SMs (a ShiftBounds step has <= 64 columns)
-        pack_step_kernel<<<job.desc.kind == kStepKindShiftBounds ? 1 : di.sm_count, 256, 0, stream>>>(job, ws);
+    // latency-bound re-layout of ~50k parameters per coupling: one thin wave over all SMs per step, all steps of the
+    // chain (up to kPackBatch) in one launch
+    for (size_t j0 = 0; j0 < plan.jobs.size(); j0 += kPackBatch) {
+        const size_t nb = std::min<size_t>(kPackBatch, plan.jobs.size() - j0);
+        PackBatch* batch = new PackBatch;   // 25 KB: keep it off the stack
+        for (size_t j = 0; j < nb; ++j) batch->jobs[j] = plan.jobs[j0 + j];
+        pack_step_kernel<<<dim3((unsigned)di.sm_count, (unsigned)nb), 256, 0, stream>>>(*batch, ws);
+        delete batch;
         count_launch();
     }
     ZF_CUDA_CHECK(cudaGetLastError());

@@ -424,7 +424,7 @@ def run_gpu(args):
         "traffic": traffic, "flops_per_event": flops,
         "note": "algorithmic fp32 flops (not x3 for the 3xTF32 split; kind::tf32 runs at half the bf16 rate, so the "
                 "tensor pipe executes 6 bf16-equivalents per algorithmic flop); achieved uses the whole step time "
-                "(the three pack launches included, ~5%); the kernel is bound by the SIMT activation / spline phases "
+                "(the pack launch included, ~1%); the kernel is bound by the SIMT activation / spline phases "
                 "(SFU, tensor-memory store port, issue), see DESIGN.md",
         "tensor_pipe_bf16_equivalent_frac": 6 * tflops / pk["bf16"],
         "frac_of_fp32_simt_peak": tflops / 74.4, "peak_source": pk["source"]}

@@ -23,6 +23,8 @@ if "--build" in sys.argv:  # same as: python scripts/build_variant.py trace -DZF
     sys.exit(0)
 
 os.environ["ZENFLOW_B200_NO_BUILD"] = "1"
+# the clock64 stamps live in the single-tile kernel (2-D flows default to the two-tiles-in-flight kernel)
+os.environ.setdefault("ZF_CHAIN_IMPL", "umma8")
 zb.LIB_PATH = os.path.abspath(os.environ["ZF_LIB"]) if os.environ.get("ZF_LIB") else TRACE_LIB
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

@@ -95,3 +95,65 @@ def test_build_digest_is_path_independent(tmp_path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod._digest() == zb._digest()
+
+
+def _fake_chain(D, C, K, hidden, n_couplings, bound_kind=0):
+    """A zf_chain with well-formed descriptors and fake (non-null, aligned) device pointers: enough for the host-only
+    planning entry zf_chain_workspace_bytes, which never dereferences them."""
+    from zenflow_b200 import _lib
+
+    keep = []
+    ops = []
+    sb = _lib.ZfShiftBounds()
+    for i in range(D):
+        sb.kind[i] = bound_kind
+        sb.lo[i], sb.hi[i] = 0.0, 1.0
+    sb.margin = 0.1
+    sb.xmin = sb.xmax = 0x10000
+    op = _lib.ZfOp(); op.kind = _lib.OP_SHIFT_BOUNDS; op.shift_bounds = ctypes.pointer(sb)
+    ops.append(op); keep.append(sb)
+    for j in range(n_couplings):
+        cp = _lib.ZfCoupling()
+        cp.knots = K
+        cp.n_hidden = len(hidden)
+        for i, w in enumerate(hidden):
+            cp.hidden[i] = w
+        cp.bn_scale = cp.bn_bias = cp.bn_mean = cp.bn_var = 0x10000
+        for i in range(len(hidden) + 1):
+            cp.kernel[i] = 0x20000
+            cp.bias[i] = 0x30000
+        op = _lib.ZfOp(); op.kind = _lib.OP_COUPLING; op.coupling = ctypes.pointer(cp)
+        ops.append(op); keep.append(cp)
+        if j + 1 < n_couplings:
+            r = _lib.ZfOp(); r.kind = _lib.OP_ROLL; r.shift = 1
+            ops.append(r)
+    arr = (_lib.ZfOp * len(ops))(*ops)
+    ch = _lib.ZfChain()
+    ch.dim, ch.cdim, ch.n_ops = D, C, len(ops)
+    ch.ops = ctypes.cast(arr, ctypes.POINTER(_lib.ZfOp))
+    keep += [arr, ops]
+    return ch, keep
+
+
+def test_workspace_planning_is_host_only_and_validates():
+    """zf_chain_workspace_bytes plans the packed layout on the host (no device needed): sizes are 16-byte multiples,
+    grow with the chain, are independent of M, and malformed chains are refused with a message."""
+    from zenflow_b200 import _lib
+
+    lib = _lib.load()
+    ch2, k2 = _fake_chain(2, 1, 16, (128, 128), 2)
+    n2 = lib.zf_chain_workspace_bytes(ctypes.byref(ch2), 1000)
+    assert n2 > 0 and n2 % 16 == 0
+    assert lib.zf_chain_workspace_bytes(ctypes.byref(ch2), 10_000_000) == n2
+    ch8, k8 = _fake_chain(16, 4, 32, (128, 128), 8)
+    n8 = lib.zf_chain_workspace_bytes(ctypes.byref(ch8), 1000)
+    assert n8 > 4 * n2
+    # parameters + tf32 images + constant blocks of the tensor-core path: a few MB at most for the 16-D flow
+    assert n8 < 64 << 20
+    bad, kb = _fake_chain(2, 0, 16, (128,), 1)
+    kb[1].knots = 0
+    assert lib.zf_chain_workspace_bytes(ctypes.byref(bad), 10) == 0
+    assert b"knots" in lib.zf_last_error()
+    one, k1 = _fake_chain(1, 0, 16, (128,), 1)       # NeuralSplineCoupling needs dim >= 2 (bijectors.py:326)
+    assert lib.zf_chain_workspace_bytes(ctypes.byref(one), 10) == 0
+    assert b"dim" in lib.zf_last_error()

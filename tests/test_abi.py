@@ -157,3 +157,38 @@ def test_workspace_planning_is_host_only_and_validates():
     one, k1 = _fake_chain(1, 0, 16, (128,), 1)       # NeuralSplineCoupling needs dim >= 2 (bijectors.py:326)
     assert lib.zf_chain_workspace_bytes(ctypes.byref(one), 10) == 0
     assert b"dim" in lib.zf_last_error()
+
+
+def test_concurrent_builds_compile_once(tmp_path):
+    """One process per GPU imports the package at the same time; with a missing or stale library exactly one of them
+    must compile (file lock), the others wait and find it fresh, and nobody sees a half-written file (atomic rename).
+    A fake nvcc on PATH counts its invocations."""
+    import shutil
+    import stat
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = tmp_path / "tree"
+    shutil.copytree(os.path.join(root, "zenflow_b200", "csrc"), dst / "zenflow_b200" / "csrc")
+    shutil.copytree(os.path.join(root, "include"), dst / "include")
+    shutil.copy(os.path.join(root, "zenflow_b200", "build.py"), dst / "zenflow_b200" / "build.py")
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    counter = tmp_path / "count.txt"
+    fake = bindir / "nvcc"
+    fake.write_text(
+        "#!/bin/sh\n"
+        f"echo run >> {counter}\n"
+        "out=''\nwhile [ $# -gt 0 ]; do if [ \"$1\" = '-o' ]; then out=\"$2\"; fi; shift; done\n"
+        "sleep 1\nprintf 'not-a-real-library' > \"$out\"\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    code = ("import importlib.util, sys\n"
+            f"spec = importlib.util.spec_from_file_location('b', r'{dst / 'zenflow_b200' / 'build.py'}')\n"
+            "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
+            "p = m.build()\n"
+            "assert open(p).read() == 'not-a-real-library'\n")
+    env = dict(os.environ, PATH=f"{bindir}:{os.environ['PATH']}")
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=env) for _ in range(4)]
+    assert all(p.wait(timeout=120) == 0 for p in procs)
+    assert counter.read_text().count("run") == 1

@@ -5,10 +5,13 @@
   python bench.py --impl reference ...        # the reference's CPU implementation of the path
 
 One step = one ``Flow.__call__`` (log-prob) pass over one batch of synthetic events.  At N=1
-the workload is BASELINE.json configs[1] (two_moons_conditional: 2-D flow, 1-D condition,
-default rolling_spline_coupling chain, batch 1M).  With N>1 (torchrun, one rank per GPU) every
-rank evaluates its own batch - the eval path shards over events with no data-path collective,
-so scaling is "weak" - and the time is the max over ranks.
+the workload is the largest single-GPU configuration of BASELINE.json: configs[3] (bounded16:
+16-D flow, ShiftBounds + 8 spline couplings, K=32, 16*2^20 events per step per GPU); configs[1]
+(two_moons_conditional, 1M events) is reported beside it as ``extras.two_moons_conditional``.
+With N>1 (torchrun, one rank per GPU) every rank evaluates its own batch - the eval path shards
+over events with no data-path collective, so scaling is "weak" - and the time is the max over
+ranks.  ``train_step`` is the data-parallel train step of configs[4] (64M events per optimiser
+step, one fixed global batch sliced by rank, NCCL all-reduces), reported at every N.
 
 Printed JSON (one line, rank 0): value = events/s with inputs resident in HBM; e2e = the same
 metric through the public API from pinned HOST buffers (H2D of x and c, D2H of log_prob inside
@@ -123,7 +126,7 @@ def cpu_events_per_s(w, sample, steps=1, warmup=0, cores=None):
     ops, v = make_variables(w)
     x, c = synth(w, sample, 123)
     _G.update(ops=ops, v=v, x=x, c=c)
-    chunk = 16384
+    chunk = int(min(16384, max(256, -(-sample // (4 * cores)))))   # every worker gets several shards per step
     shards = [(i, min(sample, i + chunk)) for i in range(0, sample, chunk)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
@@ -152,18 +155,19 @@ def run_reference(args):
         kind = "reference"
     except Exception:
         pass
-    # bounded: the whole --steps K run stays within ~3x the default sample (a few minutes at most)
-    sample = args.cpu_sample or max(20_000, 3 * default_cpu_sample(w) // max(1, args.steps))
-    value, sec, cores = cpu_events_per_s(w, sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    # bounded: the whole (--warmup W + --steps K) run stays within ~3x the default sample (a few minutes at most)
+    K, W = max(1, args.steps), max(0, args.warmup)
+    sample = args.cpu_sample or max(10_000, 3 * default_cpu_sample(w) // (K + W))
+    value, sec, cores = cpu_events_per_s(w, sample, steps=K, warmup=W)
     line = {
         "impl": "reference", "metric": "flow_log_prob_events_per_s", "value": value, "unit": "events/s",
-        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "events_per_step": sample, **{k: w[k] for k in ("D", "C", "K")},
-                   "layers": list(w["layers"]), "note": "bounded sample of the same workload per step"},
+        "config": bench_config(args.workload, w, args.batch or w["M"]),
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} events/step, numpy fp32 restatement of the reference path "
-                                   f"(JAX not installable here), {cores} forked workers x 1 BLAS thread"},
+                         "sample": f"{sample} events/step (bounded sample of the workload in config), numpy fp32 "
+                                   f"restatement of the reference path (JAX not installable here), {cores} forked "
+                                   f"workers x 1 BLAS thread"},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -221,12 +225,66 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def build_flow(w, dev):
+    """(flow, variables on `dev`) of a workload, from the fixed-seed variables both arms share."""
+    import torch
+
+    from zenflow_b200 import Flow
+    from zenflow_b200 import bijectors as bi
+
+    ops, v = make_variables(w)
+    mods = []
+    for op in ops:
+        if op["kind"] == "shift_bounds":
+            mods.append(bi.ShiftBounds(margin=op["margin"], bounds=op["bounds"]))
+        elif op["kind"] == "roll":
+            mods.append(bi.Roll(op["shift"]))
+        else:
+            mods.append(bi.NeuralSplineCoupling(knots=op["knots"], layers=op["layers"]))
+    flow = Flow(bi.Chain(mods))
+    tree = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    variables = torch.utils._pytree.tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev), tree)
+    flow.latent._latch_dim(w["D"])
+    return flow, variables
+
+
+def ncu_traffic(workload, M):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture of this exact
+    (workload, events) pair (profiles/r02_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(f"{workload}:{M}")
+
+
+def loop_events_per_s(fn, n_events, min_seconds=0.5, warm=3):
+    """Device-timed events/s of fn(i) repeated until at least `min_seconds` have been timed (extras)."""
+    import torch
+
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps, done, ms = 3, 0, 0.0
+    while True:
+        a.record()
+        for i in range(reps):
+            fn(warm + done + i)
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+        done += reps
+        if ms >= min_seconds * 1e3 or done >= 4000:
+            break
+        reps = int(min(2000, max(3, reps * 1.5 * (min_seconds * 1e3 - ms) / max(ms / done, 1e-3) / max(reps, 1) + 1)))
+    return n_events * done / (ms * 1e-3), ms / done, done
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from zenflow_b200 import Flow, _lib
-    from zenflow_b200 import bijectors as bi
+    from zenflow_b200 import _lib
     from zenflow_b200.utils import rqs_forward_raw
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,24 +299,12 @@ def run_gpu(args):
     if args.batch:
         w["M"] = args.batch
     M = w["M"]
-    ops, v = make_variables(w)
-    mods = []
-    for op in ops:
-        if op["kind"] == "shift_bounds":
-            mods.append(bi.ShiftBounds(margin=op["margin"], bounds=op["bounds"]))
-        elif op["kind"] == "roll":
-            mods.append(bi.Roll(op["shift"]))
-        else:
-            mods.append(bi.NeuralSplineCoupling(knots=op["knots"], layers=op["layers"]))
-    flow = Flow(bi.Chain(mods))
-    tree = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
-    variables = torch.utils._pytree.tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev), tree)
+    flow, variables = build_flow(w, dev)
 
-    # rotating input sets: their total exceeds L2 (126 MB), so every step reads cold inputs
+    # Inputs beyond L2 (126 MB): either one set is already larger, or enough rotating sets to exceed it twice
     bytes_in = 4 * M * (w["D"] + w["C"])
     bytes_out = 4 * M
-    n_sets = max(2, int(np.ceil(2 * 126e6 / (bytes_in + bytes_out))))
-    n_sets = min(n_sets, 24)
+    n_sets = min(24, max(2, int(np.ceil(2 * 126e6 / (bytes_in + bytes_out)))))
     xs_h, cs_h = [], []
     for i in range(n_sets):
         x, c = synth(w, M, 1000 + 97 * rank + i)
@@ -309,7 +355,7 @@ def run_gpu(args):
         lp_keep[b] = lp
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(compute_done[b])
-            lp_hosts[b].copy_(lp, non_blocking=True)  # 4 MB result back, overlapping the next step's kernel
+            lp_hosts[b].copy_(lp, non_blocking=True)  # the result back, overlapping the next step's kernel
             d2h_done[b].record(d2h_stream)
         return lp
 
@@ -362,19 +408,56 @@ def run_gpu(args):
     e2e_checked = bool(torch.equal(lp_hosts[last & 1], ref.cpu()))
     if not e2e_checked:
         raise RuntimeError("e2e pipeline returned a result that differs from the device-resident path")
+    del ref
 
-    # Flow.sample's inverse chain on a given latent draw (same events/s unit), N=1 extra
     extras = {}
     pk = peaks()
-    if rank == 0:
-        u = torch.rand(M, w["D"], device=dev) * 0.8 + 0.1
+    if rank == 0 and world == 1:
+        # Flow.sample of the same workload: (i) in-kernel Philox latent draw + inverse chain (the public
+        # ``method="sample"``), (ii) the inverse chain on a given latent draw u (the parity mode)
+        cond = cs_d[0]
+        n_ev = M
+
+        def step_sample(i):
+            return flow.apply(variables, cond if cond is not None else n_ev, method="sample", seed=i)
 
         def step_inv(i):
             return flow.apply(variables, u, cs_d[i % n_sets], method="inverse")
 
-        inv_ms, _, _, _ = timed(step_inv, max(3, K // 4), 3) if world == 1 else (None, None, None, None)
-        if inv_ms:
-            extras["inverse_events_per_s"] = M * max(3, K // 4) / (inv_ms * 1e-3)
+        v_s, ms_s, n_s = loop_events_per_s(step_sample, n_ev, 0.6)
+        extras["sample_events_per_s"] = v_s
+        extras["sample"] = {"value": v_s, "unit": "events/s", "ms_per_step": ms_s, "steps": n_s,
+                            "what": "Flow.sample: Philox latent draw fused into the inverse chain kernel"}
+        u = torch.rand(M, w["D"], device=dev) * 0.8 + 0.1
+        v_i, ms_i, n_i = loop_events_per_s(step_inv, n_ev, 0.6)
+        extras["inverse_events_per_s"] = v_i
+        extras["inverse"] = {"value": v_i, "unit": "events/s", "ms_per_step": ms_i, "steps": n_i,
+                             "what": "Chain.inverse on a given latent draw (parity mode of Flow.sample)"}
+        del u
+
+        # the other single-GPU eval config of BASELINE.json (configs[1] when the headline is configs[3] and vice versa)
+        other = "two_moons_conditional" if args.workload != "two_moons_conditional" else "bounded16"
+        if not args.no_extras:
+            w2 = dict(WORKLOADS[other])
+            if other == "bounded16":
+                w2["M"] = 4 * 2 ** 20
+            flow2, vars2 = build_flow(w2, dev)
+            ns2 = min(24, max(2, int(np.ceil(2 * 126e6 / (4 * w2["M"] * (w2["D"] + w2["C"] + 1))))))
+            sets2 = [synth(w2, w2["M"], 5000 + i) for i in range(ns2)]
+            x2 = [torch.from_numpy(a).to(dev) for a, _ in sets2]
+            c2 = [None if b is None else torch.from_numpy(b).to(dev) for _, b in sets2]
+            v_lp, ms_lp, n_lp = loop_events_per_s(lambda i: flow2.apply(vars2, x2[i % ns2], c2[i % ns2]), w2["M"], 1.0)
+            v_sm, ms_sm, _ = loop_events_per_s(
+                lambda i: flow2.apply(vars2, c2[i % ns2] if c2[0] is not None else w2["M"], method="sample", seed=i),
+                w2["M"], 0.5)
+            fl2 = chain_flops_per_event(w2)
+            extras[other] = {
+                "config": {"workload": other, "events_per_step": w2["M"], "D": w2["D"], "C": w2["C"], "K": w2["K"],
+                           "l2": f"rotating {ns2} input sets"},
+                "log_prob_events_per_s": v_lp, "ms_per_step": ms_lp, "steps": n_lp, "sample_events_per_s": v_sm,
+                "sample_ms_per_step": ms_sm, "tflops_algorithmic": fl2 * v_lp / 1e12,
+                "roofline_frac_tensor": fl2 * v_lp / 1e12 / pk["bf16"], "traffic": ncu_traffic(other, w2["M"])}
+            del x2, c2, flow2, vars2
 
         # the standalone spline stage of this workload's shape against the HBM roof
         d = w["D"] // 2
@@ -386,7 +469,7 @@ def run_gpu(args):
             rqs_forward_raw(xin, theta, w["K"])
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
+        reps = 20
         a.record()
         for _ in range(reps):
             rqs_forward_raw(xin, theta, w["K"])
@@ -396,11 +479,17 @@ def run_gpu(args):
         alg = 4.0 * (d * P + 2 * d + 1) * Ms
         extras["roofline_spline_stage"] = {
             "kernel": "rqs_stage_kernel (zf_rqs_forward)", "bound": "hbm", "achieved": alg / st_ms / 1e6,
-            "peak": pk["hbm"], "unit": "GB/s", "frac": alg / st_ms / 1e6 / pk["hbm"], "traffic": None,
-            "events": Ms, "bytes_per_event": 4 * (d * P + 2 * d + 1), "peak_source": pk["source"]}
+            "peak": pk["hbm"], "unit": "GB/s", "frac": alg / st_ms / 1e6 / pk["hbm"],
+            "traffic": ncu_traffic("rqs_stage", Ms), "events": Ms, "bytes_per_event": 4 * (d * P + 2 * d + 1),
+            "peak_source": pk["source"]}
         del theta, xin
 
+    # free the eval buffers before the train step takes its share of HBM
+    del xs_d, cs_d, stage_x, stage_c, lp_keep
+    torch.cuda.empty_cache()
     train_info = bench_train(args, world, rank, dev) if args.train_batch else None
+    if rank == 0 and world == 1 and args.deep_set and not args.no_extras:
+        extras["deep_set_train_step"] = bench_deep_set(dev)
 
     if rank != 0:
         if world > 1:
@@ -412,20 +501,18 @@ def run_gpu(args):
     tflops = flops * M / (step_ms * 1e-3) / 1e12
     simt = os.environ.get("ZF_CHAIN_IMPL", "").startswith("s")
     pp = (w["D"] // 2 == 1) and not simt   # single-dim couplings run the two-tiles-in-flight kernel
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this exact workload
-    # (profiles/r01_chain_umma_pp_kernel_ncu.md: 12.51 MB read + 0 written for 1M events of 12 B + parameters)
-    traffic = 12510464 if (pp and args.workload == "two_moons_conditional" and M == 1_000_000) else None
     roofline = {
         "kernel": ("chain_kernel<false>: fused conditioner MLPs (fp32 FFMA) + splines + latent" if simt else
                    ("chain_umma_pp_kernel<false>" if pp else "chain_umma_kernel<false>") +
                    " (zf_flow_log_prob): conditioner GEMMs on tcgen05 (3xTF32, A in TMEM), "
                    "spline rows read theta from TMEM, latent fused" + ("; two tiles in flight" if pp else "")),
         "bound": "tensor", "achieved": tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tflops / pk["bf16"],
-        "traffic": traffic, "flops_per_event": flops,
+        "traffic": ncu_traffic(args.workload, M), "flops_per_event": flops,
         "note": "algorithmic fp32 flops (not x3 for the 3xTF32 split; kind::tf32 runs at half the bf16 rate, so the "
                 "tensor pipe executes 6 bf16-equivalents per algorithmic flop); achieved uses the whole step time "
-                "(the pack launch included, ~1%); the kernel is bound by the SIMT activation / spline phases "
-                "(SFU, tensor-memory store port, issue), see DESIGN.md",
+                "(the pack launch included); peak = burst bf16 figure of MEASURED_PEAKS.json, the sustained one "
+                "gives frac_sustained; see DESIGN.md for what bounds the kernel",
+        "frac_sustained": (tflops / pk["bf16_sustained"]) if pk.get("bf16_sustained") else None,
         "tensor_pipe_bf16_equivalent_frac": 6 * tflops / pk["bf16"],
         "frac_of_fp32_simt_peak": tflops / 74.4, "peak_source": pk["source"]}
 
@@ -436,10 +523,8 @@ def run_gpu(args):
         "metric": "flow_log_prob_events_per_s", "value": value, "unit": "events/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "events_per_step_per_gpu": M, "D": w["D"], "C": w["C"], "K": w["K"],
-                   "layers": list(w["layers"]), "couplings": w["D"] if w["n_couplings"] is None else w["n_couplings"],
-                   "latent": "Beta(12)", "l2": f"rotating {n_sets} input sets ({n_sets * (bytes_in + bytes_out) / 1e6:.0f} MB > 126 MB L2)",
-                   "seed": 0},
+        "config": bench_config(args.workload, w, M),
+        "timed_region_s": total_ms * 1e-3,
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
                 "ms_per_step": e2e_ms / K, "result_checked": e2e_checked},
         "gpu_launches": int(launches),
@@ -460,17 +545,20 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def bench_train(args, world, rank, dev):
-    """Extra measurement (not the headline value): the data-parallel train step of train.py:80-86
-    on BASELINE.json configs[4]'s shape (16-D conditional flow, C=4, K=32, 8 couplings, Roll(2)),
-    global batch --train-batch split evenly over the ranks (strong scaling), BatchNorm/ShiftBounds
-    statistics and the flat gradient all-reduced with NCCL.  Samples/s = global batch / step time."""
-    import torch
-    import torch.distributed as dist
+def bench_config(workload, w, M):
+    """The `config` object both arms print (the CPU arm's bounded sample is described in cpu_baseline.sample)."""
+    bytes_io = 4 * M * (w["D"] + w["C"] + 1)
+    n_sets = min(24, max(2, int(np.ceil(2 * 126e6 / bytes_io))))
+    return {"workload": workload, "events_per_step_per_gpu": M, "D": w["D"], "C": w["C"], "K": w["K"],
+            "layers": list(w["layers"]), "couplings": w["D"] if w["n_couplings"] is None else w["n_couplings"],
+            "latent": "Beta(12)", "l2": f"rotating {n_sets} input sets ({n_sets * bytes_io / 1e6:.0f} MB > 126 MB L2)",
+            "seed": 0}
 
+
+def cond16_flow():
+    """BASELINE.json configs[4]: 16-D conditional flow, C=4, K=32, ShiftBounds + 8 couplings with Roll(2)."""
     from zenflow_b200 import Flow
     from zenflow_b200 import bijectors as bi
-    from zenflow_b200._train import TrainEngine
 
     D, C, K, n_c = 16, 4, 32, 8
     mods = [bi.ShiftBounds()]
@@ -479,57 +567,102 @@ def bench_train(args, world, rank, dev):
     mods.append(bi.NeuralSplineCoupling(knots=K, layers=(128, 128)))
     flow = Flow(bi.Chain(mods))
     variables = flow.init(0, np.zeros((1, D), np.float32), np.zeros((1, C), np.float32))
-    local = args.train_batch // world
+    return flow, variables, D, C, K, n_c
+
+
+def global_batch_slice(global_batch, width, seed, lo, hi, dev):
+    """Rows [lo, hi) of ONE fixed synthetic global batch (uniform in (0,1)), identical for every world size:
+    the batch is generated in fixed 1M-row blocks from a counter-free per-block seed, so a rank only materialises
+    the blocks that overlap its slice."""
+    import torch
+
+    blk = 1 << 20
+    out = torch.empty(hi - lo, width, dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    x = torch.rand(local, D, device=dev, generator=g)
-    c = torch.rand(local, C, device=dev, generator=g)
-    eng = TrainEngine(flow, variables, D, C, group=None)
-    steps, warm = args.train_steps, 2
+    for b0 in range(lo // blk * blk, hi, blk):
+        g.manual_seed(seed * 1_000_003 + b0 // blk)
+        rows = min(blk, global_batch - b0)
+        t = torch.rand(rows, width, device=dev, generator=g)
+        s0, s1 = max(lo, b0), min(hi, b0 + rows)
+        out[s0 - lo:s1 - lo] = t[s0 - b0:s1 - b0]
+    return out
+
+
+def bench_train(args, world, rank, dev):
+    """The data-parallel train step of train.py:80-86 on BASELINE.json configs[4] (16-D conditional flow, C=4,
+    K=32, 8 couplings, Roll(2)): ONE fixed global batch of --train-batch events (default 64*2^20) sliced evenly by
+    rank (strong scaling: the loss is the same at every N), BatchNorm / ShiftBounds statistics and the flat
+    gradient all-reduced with NCCL.  Samples/s = global batch / step time (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from zenflow_b200._train import TrainEngine
+
+    flow, variables, D, C, K, n_c = cond16_flow()
+    gb = args.train_batch // world * world
+    local = gb // world
+    x = global_batch_slice(gb, D, 1234, rank * local, (rank + 1) * local, dev)
+    c = global_batch_slice(gb, C, 4321, rank * local, (rank + 1) * local, dev)
+    kw = {}
+    if args.train_micro_batch:
+        kw["micro_batch"] = args.train_micro_batch
+    eng = TrainEngine(flow, variables, D, C, group=None, **kw)
+    steps, warm = args.train_steps, args.train_warmup
+    losses = []
     for _ in range(warm):
-        eng.step(x, c, global_count=local * world)
+        losses.append(eng.step(x, c, global_count=gb).clone())
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    from zenflow_b200 import _lib
+    l0 = _lib.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
-        lp_sum = eng.step(x, c, global_count=local * world)
+        losses.append(eng.step(x, c, global_count=gb).clone())
     b.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
     ms = a.elapsed_time(b)
-    t = torch.tensor([ms, float(lp_sum.item())], device=dev, dtype=torch.float64)
+    ls = torch.cat(losses)          # per-step sums of log-probs over this rank's slice
+    tm = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
-        tm = t[:1].clone()
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ls = t[1:].clone()
         dist.all_reduce(ls, op=dist.ReduceOp.SUM)
-        ms, lpsum = float(tm.item()), float(ls.item())
-    else:
-        lpsum = float(t[1].item())
-    flops_fwd = 2 * (12 * 128 + 128 * 128 + 128 * 760) * n_c
-    return {"samples_per_s": local * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "global_batch": local * world,
-            "steps": steps, "warmup": warm, "n_gpus": world, "scaling": "strong", "loss": -lpsum / (local * world),
+    ms = float(tm.item())
+    loss_per_step = [-float(v) / gb for v in ls.tolist()]
+    flops_fwd = 2 * ((D - D // 2 + C) * 128 + 128 * 128 + 128 * (D // 2) * (3 * K - 1)) * n_c
+    return {"samples_per_s": gb * steps / (ms * 1e-3), "ms_per_step": ms / steps, "global_batch": gb,
+            "steps": steps, "warmup": warm, "n_gpus": world, "scaling": "strong",
+            "loss": loss_per_step[0], "loss_per_step": [float(f"{v:.9g}") for v in loss_per_step],
+            "gpu_launches": int(launches), "micro_batch": eng.micro_batch,
             "config": {"workload": "cond16_train", "D": D, "C": C, "K": K, "couplings": n_c, "layers": [128, 128],
-                       "optimizer": "nadamw(1e-3)", "collectives": "NCCL all-reduce: ShiftBounds min/max, BatchNorm moments fwd+bwd, flat gradient"},
-            "tflops_algorithmic": 3 * flops_fwd * local * world / (ms / steps * 1e-3) / 1e12,
-            "note": "BASELINE configs[4] names 64M/step; this extra uses --train-batch events/step; conditioner GEMMs of "
-                    "forward, recompute and VJP on tcgen05 (3xTF32), micro-batches of 262144 events"}
+                       "optimizer": "nadamw(1e-3)", "data": "one fixed global batch (seed 1234/4321) sliced by rank",
+                       "collectives": eng.collectives_note()},
+            "tflops_algorithmic": 3 * flops_fwd * gb / (ms / steps * 1e-3) / 1e12,
+            "roofline_frac_tensor": 3 * flops_fwd * gb / (ms / steps * 1e-3) / 1e12 / peaks()["bf16"],
+            "note": "loss_per_step[0] is the loss of the initial parameters on the fixed global batch: identical at "
+                    "every N up to the summation order of the all-reduced double sums"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="two_moons_conditional", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="bounded16", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override events per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0)
-    ap.add_argument("--train-batch", type=int, default=1 << 20, help="global batch of the extra train-step measurement (0: skip)")
-    ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--train-batch", type=int, default=64 << 20,
+                    help="global batch of the data-parallel train step (BASELINE configs[4]: 64M; 0: skip)")
+    ap.add_argument("--train-steps", type=int, default=2)
+    ap.add_argument("--train-warmup", type=int, default=1)
+    ap.add_argument("--train-micro-batch", type=int, default=0, help="override TrainEngine's micro-batch (0: default)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (other eval config, deep_set)")
+    ap.add_argument("--deep-set", type=int, default=0, help="run the deep_set (configs[2]) train-step leg at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ZF_ABI_VERSION 1
+#define ZF_ABI_VERSION 2
 #define ZF_MAX_LAYERS 8   /* hidden layers per conditioner */
 #define ZF_MAX_DIM 64     /* columns of x */
 
@@ -116,6 +116,11 @@ int zf_rqs_forward(void* stream, const float* theta, const float* x, int64_t M, 
 int zf_rqs_inverse(void* stream, const float* theta, const float* y, int64_t M, int32_t d,
                    int32_t K, float* x, int32_t* idx);
 
+/* Developer switch (parity tests): force a chain kernel ("simt", "umma", "umma8"; NULL / "" = automatic) and a train
+ * GEMM ("simt"; NULL = tcgen05).  The ZF_CHAIN_IMPL / ZF_GEMM_IMPL environment variables give the initial values
+ * and are read once per process. */
+int zf_debug_set_impl(const char* chain_impl, const char* gemm_impl);
+
 /* Exhaustive device self-test of the exact-arithmetic fast paths the bin search relies on
  * (zf_math.cuh): mismatches[0] = sqrt fast path vs sqrt.rn over every float in [2^-100, 2^100],
  * [1] = squareplus fast vs IEEE over |x| < 2^40, [2] = reciprocal-form division vs div.rn.
@@ -143,6 +148,11 @@ size_t zf_chain_workspace_bytes(const zf_chain* chain, int64_t M);
  * may be NULL.  c is (M,C) or NULL when cdim == 0. */
 int zf_chain_forward(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
                      float* y, float* log_det, void* workspace, size_t workspace_bytes);
+/* Parity evidence: the bin index (utils.py:244-250 _index, in [0, K]) of every spline evaluation of
+ * Chain.__call__(x, c): idx (M, n_couplings, D/2) int32, coupling-major in op order.  Same kernels, same
+ * arithmetic as zf_chain_forward; nothing else is written. */
+int zf_chain_bin_indices(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                         int32_t* idx, void* workspace, size_t workspace_bytes);
 /* Chain.inverse(z, c), bijectors.py:113-116. */
 int zf_chain_inverse(void* stream, const zf_chain* chain, const float* z, const float* c, int64_t M,
                      float* x, void* workspace, size_t workspace_bytes);
@@ -157,6 +167,20 @@ int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t latent_kind, f
  * inverse chain kernel's tile load, then bijector.inverse.  x (M,D) out; c (M,C) or NULL. */
 int zf_flow_sample(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness, uint64_t seed,
                    const float* c, int64_t M, float* x, void* workspace, size_t workspace_bytes);
+
+/* The same passes with the per-call parameter re-layout hoisted out: zf_chain_pack writes the packed parameter
+ * blocks of `chain` into `workspace` once (after every parameter / statistics update); the *_packed calls then
+ * only launch the fused kernel.  `chain` must describe the same ops and the same workspace must be passed. */
+int zf_chain_pack(void* stream, const zf_chain* chain, void* workspace, size_t workspace_bytes);
+int zf_chain_forward_packed(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                            float* y, float* log_det, void* workspace, size_t workspace_bytes);
+int zf_chain_inverse_packed(void* stream, const zf_chain* chain, const float* z, const float* c, int64_t M,
+                            float* x, void* workspace, size_t workspace_bytes);
+int zf_flow_log_prob_packed(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness,
+                            const float* x, const float* c, int64_t M, float* log_prob, void* workspace,
+                            size_t workspace_bytes);
+int zf_flow_sample_packed(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness, uint64_t seed,
+                          const float* c, int64_t M, float* x, void* workspace, size_t workspace_bytes);
 
 /* Same as zf_chain_forward but log_det[m] += (this chain's log-det): Chain's running sum
  * (bijectors.py:107-110) when the train step applies the bijectors one phase at a time. */
@@ -196,6 +220,11 @@ int zf_bn_finalize(void* stream, const double* sums, double count, int32_t F, fl
  * gz (M,D) = glp * d latent/dz.  lp (M,) may be NULL. */
 int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
                       int64_t M, int32_t D, double global_count, float* lp, float* gz, float* glp, double* lp_sum);
+/* The same with a caller-supplied cotangent of lp (M,), e.g. from a jax.custom_vjp backward rule; NULL = the
+ * -1/global_count of loss = -mean(lp). */
+int zf_flow_loss_grad_ct(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
+                         int64_t M, int32_t D, double global_count, const float* lp_cotangent, float* lp, float* gz,
+                         float* glp, double* lp_sum);
 
 /* VJP of NeuralSplineCoupling.__call__(train=True) (bijectors.py:329-365) except the BatchNorm
  * input path: recomputes the conditioner in micro-batches, then
@@ -230,6 +259,48 @@ int zf_nadamw_update(void* stream, int64_t n, float* params, const float* grads,
 int zf_permute_rows(void* stream, const float* x, int64_t N, int32_t D, uint64_t seed, float* out);
 /* *out = -sum(lp[0..M)) in double (metric_fn / loss: divide by M, train.py:73,78). */
 int zf_neg_sum(void* stream, const float* lp, int64_t M, double* out);
+
+/* ---- data-parallel helpers (the reference has no distributed code) ------------------------
+ * The collectives between the train-step phases, issued with NCCL on the caller's stream.  `comm` is an
+ * ncclComm_t (as void*); NULL means single device and every call is a no-op.  libnccl.so.2 is resolved at run
+ * time (the copy already loaded into the process wins; ZF_NCCL_LIBRARY overrides). */
+#define ZF_DP_UNIQUE_ID_BYTES 128
+/* ncclGetUniqueId: id_out = ZF_DP_UNIQUE_ID_BYTES host bytes, to be broadcast to the other ranks by the host. */
+int zf_dp_unique_id(void* id_out);
+/* ncclCommInitRank on the calling thread's current device; *comm_out is the ncclComm_t. */
+int zf_dp_comm_create(const void* id, int32_t rank, int32_t world, void** comm_out);
+int zf_dp_comm_destroy(void* comm);
+int zf_dp_comm_size(void* comm, int32_t* world_out);
+/* In-place all-reduce(sum) of DEVICE buffers: BatchNorm moment sums (double) and gradients (float). */
+int zf_dp_allreduce_sum_f32(void* stream, void* comm, float* buf, int64_t n);
+int zf_dp_allreduce_sum_f64(void* stream, void* comm, double* buf, int64_t n);
+/* ShiftBounds batch statistics (bijectors.py:250-252): minmax = min[D] | max[D]; ONE all-reduce(min) over
+ * [min | -max]. */
+int zf_dp_allreduce_minmax_f32(void* stream, void* comm, float* minmax, int32_t D);
+
+/* ---- value and gradient of the train loss in one call (train.py:64-86: loss_fn + jax.grad) ---------------
+ * loss = -sum(lp) / global_count over Flow.__call__(x, c, train=True) (or, with lp_cotangent, the VJP of lp for
+ * a caller-supplied cotangent: the backward rule of a jax.custom_vjp around the flow).  Runs every phase of
+ * the step on `stream`: per bijector the batch statistics (all-reduced over dp_comm when given), the fused
+ * forward, then the loss cotangents and the backward of every coupling.
+ *   chain        ops as for zf_chain_forward; the coupling's bn_mean / bn_var and the ShiftBounds' xmin / xmax are
+ *                the RUNNING statistics ("batch_stats" collection) and are UPDATED IN PLACE (mutable=["batch_stats"],
+ *                train.py:66-72).  Layout accepted: [ShiftBounds]? (NeuralSplineCoupling Roll*)+ (bijectors.py:418-423).
+ *   grads        one zf_coupling_grads per coupling op, in op order; accumulated into (+=)
+ *   lp (M,)      optional output; lp_sum: DEVICE double, += sum of lp over this rank's rows
+ *   gc (M,C)     optional output: d loss / d c (the cotangent a Deep-Set conditioner upstream needs,
+ *                examples/deep_set.ipynb:320-323); overwritten
+ *   dp_comm      ncclComm_t or NULL.  With it the statistics are global and, when grad_flat is given, the
+ *                gradient buckets grad_flat[bucket_off[k] .. bucket_off[k+1]) (coupling k in op order) are
+ *                all-reduced as soon as coupling k's backward is queued: on aux_stream through dp_grad_comm when
+ *                both are given (overlapping the next coupling's backward; `stream` waits for them before
+ *                returning), else on `stream` through dp_comm. */
+size_t zf_flow_value_and_grad_workspace_bytes(const zf_chain* chain, int64_t M, int64_t micro_batch);
+int zf_flow_value_and_grad(void* stream, void* aux_stream, const zf_chain* chain, const zf_coupling_grads* grads,
+                           int32_t latent_kind, float peakness, const float* x, const float* c, int64_t M,
+                           double global_count, const float* lp_cotangent, float* lp, double* lp_sum, float* gc,
+                           void* dp_comm, void* dp_grad_comm, float* grad_flat, const int64_t* bucket_off,
+                           void* workspace, size_t workspace_bytes, int64_t micro_batch);
 
 #ifdef __cplusplus
 }

@@ -68,3 +68,40 @@ def test_single_process_is_world_one():
     t = torch.ones(3)
     _allreduce(t, None, "sum")  # no-op
     assert t.tolist() == [1, 1, 1]
+
+
+def _steps_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from zenflow_b200.train import _global_step_counts
+
+    res = {}
+    # equal step counts, ragged last batch of different sizes: per-step global row counts
+    n_rows = 1000 if rank == 0 else 900
+    res["counts"] = _global_step_counts(n_rows, 256, torch.device("cpu"), None, world)
+    # shards that disagree on the number of steps: ValueError on EVERY rank (no rank is left in a collective)
+    try:
+        _global_step_counts(700 if rank == 0 else 300, 256, torch.device("cpu"), None, world)
+        res["raised"] = False
+    except ValueError as e:
+        res["raised"] = "disagree" in str(e)
+    out.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_train_loop_step_counts_are_global_and_validated():
+    """data-parallel train() must not let ranks run different numbers of collective steps."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_steps_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert got[r]["counts"] == [512, 512, 512, 232 + 132]
+        assert got[r]["raised"] is True

@@ -39,17 +39,16 @@ CONFIGS = [
 ]
 
 
-@pytest.fixture(params=["auto", "simt", "umma2", "umma8", "umma16"])
-def chain_impl(request, monkeypatch):
+@pytest.fixture(params=["auto", "simt", "umma8"])
+def chain_impl(request):
     """auto = tensor-core (tcgen05) kernel when the chain fits it, else the FFMA kernel; simt = force FFMA;
-    umma2 = the opt-in two-pipeline tensor-core variant, umma8 / umma16 = the single-tile kernel with 8 / 16 epilogue
-    warps (auto picks the two-tiles-in-flight kernel for single-dim couplings, umma8 otherwise); all fall back like auto
-    when the chain does not fit."""
-    if request.param in ("simt", "umma2", "umma8", "umma16"):
-        monkeypatch.setenv("ZF_CHAIN_IMPL", request.param)
-    else:
-        monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
-    return request.param
+    umma8 = the single-tile tensor-core kernel (auto picks the two-tiles-in-flight kernel for single-dim couplings,
+    the single-tile one otherwise); all fall back like auto when the chain does not fit."""
+    from zenflow_b200 import _lib
+
+    _lib.set_impl(None if request.param == "auto" else request.param)
+    yield request.param
+    _lib.set_impl(None)
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
@@ -338,6 +337,43 @@ def test_flow_sample_and_steps():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("D,C,K,layers", [(2, 1, 16, (128, 128)), (5, 2, 8, (32, 16)), (16, 0, 32, (128, 128))])
+def test_steps_match_oracle_steps(D, C, K, layers):
+    """Flow._steps (flow.py:80-95): every per-bijector intermediate, forward and inverse, against the oracle's
+    chain_forward / chain_inverse(return_steps=True) - not only shapes and the round trip."""
+    from zenflow_b200 import Flow
+
+    M = 777
+    ncoup = 3 if D == 16 else None
+    ops = zo.make_chain(D, K, layers, n_couplings=ncoup, roll_shift=2 if D == 16 else 1)
+    x, c = _data(M, D, C, seed=21)
+    v = trained_variables(ops, x, c, seed=4)
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    v64 = to64(v)
+    x64, c64 = x.astype(np.float64), None if c is None else c.astype(np.float64)
+    steps = flow.apply(fv, x, c, method="_steps")
+    _, _, _, ref = zo.chain_forward(ops, v64, x64, c64, return_steps=True)
+    _, _, _, ref32 = zo.chain_forward(ops, v, x, c, return_steps=True)
+    assert len(steps) == len(ref) == len(ops)
+    for i, (got, want, want32) in enumerate(zip(steps, ref, ref32)):
+        assert got.shape == (M, D)
+        if ops[i]["kind"] == "roll":   # a permutation of the previous step: bit-exact (tests/test_bijectors.py:168-188)
+            np.testing.assert_array_equal(got, np.roll(steps[i - 1], ops[i]["shift"], axis=-1))
+        e, e32 = np.abs(got - want).max(), np.abs(want32 - want).max()
+        assert e <= 4 * e32 + Y_ATOL, f"forward step {i} ({ops[i]['kind']}): err {e:.2e} vs fp32 oracle {e32:.2e}"
+    z = steps[-1]
+    back = flow.apply(fv, z, c, method="_steps", inverse=True)
+    _, refb = zo.chain_inverse(ops, v64, z.astype(np.float64), c64, return_steps=True)
+    _, refb32 = zo.chain_inverse(ops, v, z, c, return_steps=True)
+    assert len(back) == len(refb) == len(ops)
+    scale = np.abs(x).max()
+    for i, (got, want, want32) in enumerate(zip(back, refb, refb32)):
+        e, e32 = np.abs(got - want).max(), np.abs(want32 - want).max()
+        assert e <= 4 * e32 + 2e-5 * scale, f"inverse step {i}: err {e:.2e} vs fp32 oracle {e32:.2e}"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("offset_rows", [0, 1, 3])
 def test_unaligned_device_inputs_and_tail_tiles(offset_rows):
     """The tensor-core kernel fetches full tiles of 16-byte-aligned inputs with bulk copies one tile ahead and reads
@@ -367,13 +403,13 @@ def test_unaligned_device_inputs_and_tail_tiles(offset_rows):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("D,C,K,ncoup", [(2, 1, 16, 2), (3, 0, 32, 3)])
-def test_two_tile_kernel_is_bit_equal_to_single_tile(D, C, K, ncoup, monkeypatch):
+def test_two_tile_kernel_is_bit_equal_to_single_tile(D, C, K, ncoup):
     """Flows with single-dim couplings run two tiles in flight (phase-specialised warps, shared tensor memory); the
     arithmetic per event is the same as in the single-tile kernel, so the outputs must agree bit for bit - a race
     or a missed barrier between the roles would show up as a difference at this size.  Also run to run."""
     import torch
 
-    from zenflow_b200 import Flow
+    from zenflow_b200 import Flow, _lib
 
     M = 300_077
     ops = zo.make_chain(D, K, (128, 128), n_couplings=ncoup, roll_shift=1)
@@ -387,14 +423,12 @@ def test_two_tile_kernel_is_bit_equal_to_single_tile(D, C, K, ncoup, monkeypatch
     u = torch.rand(M, D, device="cuda") * 0.9 + 0.05
     out = {}
     for impl in ("default", "umma8"):
-        if impl == "default":
-            monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
-        else:
-            monkeypatch.setenv("ZF_CHAIN_IMPL", impl)
+        _lib.set_impl(None if impl == "default" else impl)
         lps = [flow.apply(fv, xd, cd) for _ in range(3)]
         inv = flow.bijector.apply({"params": fv["params"]["bijector"], "batch_stats": fv["batch_stats"]["bijector"]}, u, cd,
                                   method="inverse")
         assert all(torch.equal(lps[0], t) for t in lps[1:])
         out[impl] = (lps[0], inv)
+    _lib.set_impl(None)
     assert torch.equal(out["default"][0], out["umma8"][0])
     assert torch.equal(out["default"][1], out["umma8"][1])

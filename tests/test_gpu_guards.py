@@ -51,17 +51,15 @@ def test_stage_kernels_stay_in_bounds(M, d, K):
     ar.check()
 
 
-@pytest.mark.parametrize("impl", ["", "simt", "umma2"])
+@pytest.mark.parametrize("impl", ["", "simt", "umma8"])
 @pytest.mark.parametrize("cfg", [(2, 1, 16, (128, 128), None, 1, 777), (16, 4, 32, (128, 128), 2, 2, 193),
                                  (5, 3, 7, (64, 48), None, 1, 65)])
-def test_chain_kernels_stay_in_bounds(cfg, impl, monkeypatch):
+def test_chain_kernels_stay_in_bounds(cfg, impl, request):
     from zenflow_b200 import _lib
     from zenflow_b200._chain import ChainSpec
 
-    if impl:
-        monkeypatch.setenv("ZF_CHAIN_IMPL", impl)
-    else:
-        monkeypatch.delenv("ZF_CHAIN_IMPL", raising=False)
+    _lib.set_impl(impl or None)
+    request.addfinalizer(lambda: _lib.set_impl(None))
     D, Cd, K, layers, nc, roll, M = cfg
     rng = np.random.default_rng(M)
     ops = zo.make_chain(D, K, layers, n_couplings=nc, roll_shift=roll)
@@ -94,13 +92,13 @@ def test_chain_kernels_stay_in_bounds(cfg, impl, monkeypatch):
 
 
 @pytest.mark.parametrize("gemm", ["", "simt"])
-def test_train_step_stays_in_bounds(gemm, monkeypatch):
+def test_train_step_stays_in_bounds(gemm, request):
     """The whole train step with its buffers carved out of guarded arenas (TrainEngine allocates through
     torch; here the C-ABI GEMM family is called directly on ragged shapes)."""
     from zenflow_b200 import _lib
 
-    if gemm:
-        monkeypatch.setenv("ZF_GEMM_IMPL", gemm)
+    _lib.set_impl(None, gemm or None)
+    request.addfinalizer(lambda: _lib.set_impl(None))
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
     for mode, I, J, R in [(0, 333, 760, 128), (0, 129, 47, 12), (1, 257, 128, 760), (1, 64, 12, 128), (2, 128, 760, 1000),

@@ -12,6 +12,8 @@ import threading
 
 from . import build as _build
 
+ABI_VERSION = 2
+DP_UNIQUE_ID_BYTES = 128
 ZF_MAX_LAYERS = 8
 ZF_MAX_DIM = 64
 
@@ -98,6 +100,18 @@ SIGNATURES = {
     "zf_chain_workspace_bytes": (C.c_size_t, [C.POINTER(ZfChain), C.c_int64]),
     "zf_chain_forward": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_debug_set_impl": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "zf_chain_pack": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_size_t]),
+    "zf_chain_forward_packed": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_chain_inverse_packed": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_flow_log_prob_packed": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_int32, C.c_float, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_flow_sample_packed": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_int32, C.c_float, C.c_uint64, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zf_chain_bin_indices": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_size_t]),
     "zf_flow_sample": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_int32, C.c_float, C.c_uint64, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_size_t]),
     "zf_chain_forward_acc": (C.c_int, [C.c_void_p, C.POINTER(ZfChain), C.c_void_p, C.c_void_p, C.c_int64,
@@ -110,6 +124,20 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p]),
     "zf_flow_loss_grad": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                     C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zf_flow_loss_grad_ct": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                       C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zf_dp_unique_id": (C.c_int, [C.c_void_p]),
+    "zf_dp_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "zf_dp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "zf_dp_comm_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "zf_dp_allreduce_sum_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "zf_dp_allreduce_sum_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "zf_dp_allreduce_minmax_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "zf_flow_value_and_grad_workspace_bytes": (C.c_size_t, [C.POINTER(ZfChain), C.c_int64, C.c_int64]),
+    "zf_flow_value_and_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ZfChain), C.POINTER(ZfCouplingGrads),
+                                         C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
     "zf_coupling_backward_workspace_bytes": (C.c_size_t, [C.POINTER(ZfCoupling), C.c_int32, C.c_int32, C.c_int64]),
     "zf_coupling_backward": (C.c_int, [C.c_void_p, C.POINTER(ZfCoupling), C.POINTER(ZfCouplingGrads), C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
@@ -141,12 +169,19 @@ def load():
         path = _build.LIB_PATH
         if os.environ.get("ZENFLOW_B200_NO_BUILD") != "1":
             try:
-                path = _build.build()
-            except Exception as e:  # no nvcc on the box: use the prebuilt library if present
-                if not os.path.exists(path):
-                    raise ImportError(
-                        f"zenflow_b200: native library {path} is missing and could not be built: {e}"
-                    ) from e
+                _build.nvcc_path()
+                have_nvcc = True
+            except RuntimeError:
+                have_nvcc = False
+            if have_nvcc:
+                path = _build.build()   # a compile error on edited sources must surface, never a stale library
+            elif not os.path.exists(path):
+                raise ImportError(f"zenflow_b200: native library {path} is missing and there is no nvcc to build it")
+            elif not _build.is_fresh():
+                import warnings
+
+                warnings.warn(f"zenflow_b200: {path} was not built from the sources in this tree (build.stamp differs) "
+                              "and there is no nvcc to rebuild it", RuntimeWarning)
         if not os.path.exists(path):
             raise ImportError(f"zenflow_b200: native library {path} is missing (run python -m zenflow_b200.build)")
         lib = C.CDLL(path)
@@ -155,8 +190,8 @@ def load():
             fn.restype = res
             fn.argtypes = args
         ver = lib.zf_abi_version()
-        if ver != 1:
-            raise ImportError(f"zenflow_b200: ABI version {ver} != 1")
+        if ver != ABI_VERSION:
+            raise ImportError(f"zenflow_b200: ABI version {ver} != {ABI_VERSION} (stale {path}? run python -m zenflow_b200.build)")
         _lib = lib
         return lib
 
@@ -165,6 +200,12 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().zf_last_error().decode(errors="replace")
         raise ZenflowNativeError(f"{what or 'zenflow_b200'} failed (status {rc}): {msg}")
+
+
+def set_impl(chain_impl=None, gemm_impl=None) -> None:
+    """Developer switch: force a chain kernel / train GEMM implementation (None = automatic)."""
+    enc = lambda v: None if not v else v.encode()
+    check(load().zf_debug_set_impl(enc(chain_impl), enc(gemm_impl)), "zf_debug_set_impl")
 
 
 def launch_count() -> int:

@@ -44,6 +44,46 @@ def _allreduce(t: torch.Tensor, group, op: str = "sum"):
     dist.all_reduce(t, op=opmap[op], group=group)
 
 
+class DpComm:
+    """The NCCL communicators of the data-parallel train step, created through the C ABI (zf_dp_*).
+
+    Two communicators over the same ranks: one for the small batch statistics on the compute stream and one for
+    the gradient buckets on a side stream (so a bucket's all-reduce overlaps the next coupling's backward).
+    torch.distributed is only the rendezvous: it broadcasts the two ncclUniqueIds (any backend)."""
+
+    def __init__(self, group=None):
+        dist, world = _dist_world(group)
+        self.world = world
+        self.rank = dist.get_rank(group) if world > 1 else 0
+        self.stats = None
+        self.grads = None
+        self.aux_stream = None
+        if world == 1:
+            return
+        lib = _lib.load()
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        handles = []
+        for _ in range(2):
+            buf = (C.c_ubyte * _lib.DP_UNIQUE_ID_BYTES)()
+            if self.rank == 0:
+                _lib.check(lib.zf_dp_unique_id(buf), "zf_dp_unique_id")
+            obj = [bytes(buf)]
+            dist.broadcast_object_list(obj, src=src, group=group)
+            h = C.c_void_p()
+            idbuf = (C.c_ubyte * _lib.DP_UNIQUE_ID_BYTES).from_buffer_copy(obj[0])
+            _lib.check(lib.zf_dp_comm_create(idbuf, self.rank, world, C.byref(h)), "zf_dp_comm_create")
+            handles.append(h)
+        self.stats, self.grads = handles
+        self.aux_stream = torch.cuda.Stream()
+
+    def close(self):
+        lib = _lib.load()
+        for h in (self.stats, self.grads):
+            if h is not None:
+                lib.zf_dp_comm_destroy(h)
+        self.stats = self.grads = None
+
+
 def _sb_struct(kinds, lo, hi, margin, xmin: torch.Tensor, xmax: torch.Tensor) -> _lib.ZfShiftBounds:
     sb = _lib.ZfShiftBounds()
     for i, k in enumerate(kinds):
@@ -113,8 +153,11 @@ def _minmax_update(sb, x, D, group=None):
     scratch = torch.empty(2 * D, dtype=torch.int32, device=x.device)
     _lib.check(lib.zf_shift_bounds_minmax(stream_ptr(), C.byref(sb), ptr(x), x.shape[0], D, ptr(mm), ptr(scratch)),
                "zf_shift_bounds_minmax")
-    _allreduce(mm[:D], group, "min")
-    _allreduce(mm[D:], group, "max")
+    dist, world = _dist_world(group)
+    if world > 1:   # one all-reduce(min) over [min | -max]
+        mm[D:].neg_()
+        _allreduce(mm, group, "min")
+        mm[D:].neg_()
     _lib.check(lib.zf_shift_bounds_update(stream_ptr(), C.byref(sb), D, ptr(mm)), "zf_shift_bounds_update")
 
 
@@ -239,6 +282,8 @@ class TrainEngine:
         # D comes from the data: the default latent instance is shared between Flow objects and
         # latches its dim only once (flow.py:20, distributions.py:31-32)
         self.D = D = int(dim)
+        if D > _lib.ZF_MAX_DIM:
+            raise ValueError(f"at most {_lib.ZF_MAX_DIM} columns are supported (got {D})")
         flow.latent._latch_dim(D)
         self.C = int(cdim)
         d = D // 2
@@ -336,6 +381,36 @@ class TrainEngine:
         self._bufs: Dict[int, dict] = {}
         self.lp_sum = torch.zeros(1, dtype=torch.float64, device=self.dev)
 
+        # ---- the whole flow as ONE native chain for zf_flow_value_and_grad: couplings point at the flat parameter
+        # buffer and at the RUNNING statistics (updated in place by the call)
+        ops, self._keep_run = [], []
+        cgr = []
+        offs = [0]
+        for g in self.groups:
+            if g["kind"] == "sb":
+                ops.append(_op_sb(g["sb"]))
+            else:
+                nl = len(g["mod"].layers) + 1
+                run = _coupling_struct(g["mod"].knots, g["mod"].layers, g["pv"][("BatchNorm_0", "scale")],
+                                       g["pv"][("BatchNorm_0", "bias")], g["ra_mean"], g["ra_var"],
+                                       [g["pv"][(f"Dense_{j}", "kernel")] for j in range(nl)],
+                                       [g["pv"][(f"Dense_{j}", "bias")] for j in range(nl)])
+                self._keep_run.append(run)
+                ops.append(_op_cp(run))
+                cgr.append(g["gr"])
+                offs.append(offs[-1] + sum(int(v.numel()) for v in g["gv"].values()))
+            ops += [_op_roll(sft) for sft in g["rolls"]]
+        self.chain, self._keep_chain = _chain_struct(D, self.C, ops)
+        self.n_couplings = len(cgr)
+        self._grads_arr = (_lib.ZfCouplingGrads * max(1, len(cgr)))(*cgr)
+        self._bucket_off = (C.c_int64 * len(offs))(*offs)
+        assert offs[-1] == self.n_params
+        self._ws: Dict[int, torch.Tensor] = {}
+        dist, world = _dist_world(group)
+        self.world = world
+        self.use_nccl = world > 1 and dist.get_backend(group) == "nccl"
+        self.comm = DpComm(group) if self.use_nccl else None
+
     # -- buffers sized for a local batch ------------------------------------------------------
     def _buffers(self, M: int) -> dict:
         b = self._bufs.get(M)
@@ -358,9 +433,33 @@ class TrainEngine:
         return b
 
     # -- one optimiser step -------------------------------------------------------------------
-    def step(self, x, c=None, *, global_count: Optional[int] = None, update: bool = True, want_gc: bool = False):
+    def collectives_note(self) -> str:
+        if self.world == 1:
+            return "none (single device)"
+        if self.use_nccl:
+            return ("NCCL through the C ABI (zf_dp_*): ShiftBounds min/max as one all-reduce(min), BatchNorm moments fwd+bwd, "
+                    "per-coupling gradient buckets on a side stream overlapping the next coupling's backward")
+        return "torch.distributed all-reduces between the C-ABI phases (non-NCCL group)"
+
+    def _workspace(self, M: int) -> torch.Tensor:
+        ws = self._ws.get(M)
+        if ws is None:
+            lib = _lib.load()
+            need = int(lib.zf_flow_value_and_grad_workspace_bytes(C.byref(self.chain), M, self.micro_batch))
+            if need == 0:
+                _lib.check(1, "zf_flow_value_and_grad_workspace_bytes")
+            if len(self._ws) >= 2:  # full and ragged minibatch shapes
+                self._ws.pop(next(iter(self._ws)))
+            ws = self._ws[M] = torch.empty(need + 256, dtype=torch.uint8, device=self.dev)
+        return ws
+
+    def step(self, x, c=None, *, global_count: Optional[int] = None, update: bool = True, want_gc: bool = False,
+             lp_cotangent=None):
         """Loss, gradients and (if ``update``) the optimiser update for the local shard (x, c).
-        Returns the device scalar sum of log-probs over the local shard (loss = -sum/global_count)."""
+
+        Returns the device scalar sum of log-probs over the local shard (loss = -sum/global_count);
+        with ``want_gc`` also d loss / d c (M, C), the cotangent a conditioner upstream of the flow needs
+        (examples/deep_set.ipynb:320-323).  ``lp_cotangent`` (M,) replaces the -1/global_count of the mean loss."""
         lib = _lib.load()
         st = stream_ptr()
         x = to_device_f32(x, self.dev)
@@ -368,19 +467,57 @@ class TrainEngine:
         if c is not None and c.ndim == 1:
             c = c.reshape(-1, 1)
         M = x.shape[0]
-        D, Cd, F = self.D, self.C, self.F
+        if x.shape[1] != self.D or (0 if c is None else c.shape[1]) != self.C:
+            raise ValueError(f"expected x (M, {self.D}) and c (M, {self.C})")
         if global_count is None:
-            dist, world = _dist_world(self.group)
-            if world > 1:
+            if self.world > 1:
                 cnt = torch.tensor([M], dtype=torch.int64, device=self.dev)
                 _allreduce(cnt, self.group, "sum")
                 global_count = int(cnt.item())
             else:
                 global_count = M
-        b = self._buffers(M)
-        b["ld"].zero_()
         self.G.zero_()
         self.lp_sum.zero_()
+        if self.world > 1 and not self.use_nccl:
+            gc = self._step_phased(x, c, global_count, lp_cotangent)
+        else:
+            ws = self._workspace(M)
+            base = (ws.data_ptr() + 255) & ~255
+            gc = torch.empty(M, self.C, dtype=torch.float32, device=self.dev) if (want_gc and self.C) else None
+            comm = self.comm
+            aux = comm.aux_stream.cuda_stream if comm is not None else None
+            ct = None if lp_cotangent is None else to_device_f32(lp_cotangent, self.dev)
+            kind, peak = self.flow.latent._native()
+            _lib.check(lib.zf_flow_value_and_grad(
+                st, aux, C.byref(self.chain), self._grads_arr, kind, peak, ptr(x), ptr(c), M, float(global_count),
+                ptr(ct), None, ptr(self.lp_sum), ptr(gc), None if comm is None else comm.stats,
+                None if comm is None else comm.grads, ptr(self.G) if comm is not None else None, self._bucket_off,
+                base, ws.numel() - (base - ws.data_ptr()), self.micro_batch), "zf_flow_value_and_grad")
+        self._last_gc = gc
+        if update:
+            h = self.hp
+            _lib.check(lib.zf_nadamw_update(st, self.n_params, ptr(self.P), ptr(self.G), ptr(self.mu), ptr(self.nu),
+                                            self.count, h["lr"], h["b1"], h["b2"], h["eps"], h["weight_decay"],
+                                            h["nesterov"]), "zf_nadamw_update")
+            self.count += 1
+        return (self.lp_sum, gc) if want_gc else self.lp_sum
+
+    def value_and_grad(self, x, c=None, *, global_count: Optional[int] = None):
+        """(loss, gradient pytree, d loss / d c) without touching the parameters: what ``jax.value_and_grad`` of
+        train.py's ``loss_fn`` returns, plus the cotangent of the conditions."""
+        lp_sum, gc = self.step(x, c, global_count=global_count, update=False, want_gc=True)
+        n = global_count if global_count is not None else x.shape[0]
+        return -float(lp_sum.item()) / n, self.gradients(), gc
+
+    def _step_phased(self, x, c, global_count, lp_cotangent=None):
+        """The same step with the phases sequenced from the host and torch.distributed all-reduces in between:
+        for process groups that are not NCCL (e.g. gloo in the single-GPU data-parallel parity test)."""
+        lib = _lib.load()
+        st = stream_ptr()
+        M = x.shape[0]
+        D, Cd, F = self.D, self.C, self.F
+        b = self._buffers(M)
+        b["ld"].zero_()
         if b["gc"] is not None:
             b["gc"].zero_()
 
@@ -399,8 +536,9 @@ class TrainEngine:
         # ---- loss and the cotangents of z and of the log-dets
         kind, peak = self.flow.latent._native()
         gy, gx = b["ga"], b["gb"]
-        _lib.check(lib.zf_flow_loss_grad(st, kind, peak, ptr(cur), ptr(b["ld"]), M, D, float(global_count), None, ptr(gy),
-                                         ptr(b["glp"]), ptr(self.lp_sum)), "zf_flow_loss_grad")
+        ct = None if lp_cotangent is None else to_device_f32(lp_cotangent, self.dev)
+        _lib.check(lib.zf_flow_loss_grad_ct(st, kind, peak, ptr(cur), ptr(b["ld"]), M, D, float(global_count), ptr(ct), None,
+                                            ptr(gy), ptr(b["glp"]), ptr(self.lp_sum)), "zf_flow_loss_grad")
 
         # ---- backward
         for g in reversed(self.groups):
@@ -416,16 +554,8 @@ class TrainEngine:
                                                 ptr(g["bn_sums"]), float(global_count), M, ptr(gx), ptr(b["gc"])),
                        "zf_bn_backward_apply")
             gy, gx = gx, gy
-        self._last_gc = b["gc"]
-
         _allreduce(self.G, self.group, "sum")
-        if update:
-            h = self.hp
-            _lib.check(lib.zf_nadamw_update(st, self.n_params, ptr(self.P), ptr(self.G), ptr(self.mu), ptr(self.nu),
-                                            self.count, h["lr"], h["b1"], h["b2"], h["eps"], h["weight_decay"],
-                                            h["nesterov"]), "zf_nadamw_update")
-            self.count += 1
-        return self.lp_sum
+        return b["gc"]
 
     # -- FLAX-shaped views of the current state -------------------------------------------------
     def variables(self, as_numpy: bool = False) -> Dict[str, dict]:

@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+# developer builds: ZF_NVCC_EXTRA="-DZF_EXPERIMENTAL" compiles the measured-slower kernel variants back in
+EXTRA_FLAGS = [f for f in os.environ.get("ZF_NVCC_EXTRA", "").split() if f]
+
+
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -40,7 +44,7 @@ def _digest() -> str:
         with open(p, "rb") as f:
             h.update(os.path.basename(p).encode())
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -53,6 +57,11 @@ def nvcc_path() -> str:
 
 def _fresh(dig: str) -> bool:
     return os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig
+
+
+def is_fresh() -> bool:
+    """True when the in-tree library was built from exactly the sources (and flags) in this tree."""
+    return _fresh(_digest())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -72,12 +81,45 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if not force and _fresh(dig):
                 return LIB_PATH
             tmp = LIB_PATH + f".tmp{os.getpid()}"
-            cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", tmp] + _sources()
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            log = res.stdout + res.stderr
+            # one nvcc per translation unit, in parallel; objects are reused when neither the source nor any
+            # header nor the flags changed
+            from concurrent.futures import ThreadPoolExecutor
+
+            obj_dir = os.path.join(LIB_DIR, "obj")
+            os.makedirs(obj_dir, exist_ok=True)
+            hdr = hashlib.sha256()
+            inc = os.path.join(os.path.dirname(HERE), "include", "zenflow_b200.h")
+            for p in sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [inc]:
+                hdr.update(open(p, "rb").read())
+            hdr.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
+            compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + EXTRA_FLAGS
+
+            def compile_one(src):
+                key = hashlib.sha256(hdr.digest() + open(src, "rb").read()).hexdigest()[:24]
+                obj = os.path.join(obj_dir, os.path.basename(src) + "." + key + ".o")
+                if os.path.exists(obj):
+                    return obj, "", 0
+                for old in os.listdir(obj_dir):
+                    if old.startswith(os.path.basename(src) + "."):
+                        os.remove(os.path.join(obj_dir, old))
+                otmp = obj + f".tmp{os.getpid()}"
+                r = subprocess.run([nvcc_path()] + compile_flags + ["-c", "-o", otmp, src], capture_output=True, text=True)
+                if r.returncode == 0:
+                    os.replace(otmp, obj)
+                return obj, "# " + os.path.basename(src) + "\n" + r.stdout + r.stderr, r.returncode
+
+            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+                results = list(pool.map(compile_one, _sources()))
+            log = "".join(r[1] for r in results)
+            rc = max(r[2] for r in results)
+            cmd = [nvcc_path()] + NVCC_FLAGS + EXTRA_FLAGS + ["-o", tmp] + [r[0] for r in results] + ["-ldl"]
+            if rc == 0:
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                log += res.stdout + res.stderr
+                rc = res.returncode
             with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
                 f.write(" ".join(cmd).replace(tmp, LIB_PATH) + "\n" + log)
-            if res.returncode != 0:
+            if rc != 0:
                 if os.path.exists(tmp):
                     os.remove(tmp)
                 raise RuntimeError("nvcc failed:\n" + log[-8000:])

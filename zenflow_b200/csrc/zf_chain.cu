@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace zf {
@@ -51,7 +53,8 @@ struct StepDesc {
     int off_U[ZF_MAX_LAYERS + 1];   // tensor-core weight images (3xTF32 hi|lo, K-major core matrices), layers 1..L
     int umma_ok;                    // this coupling fits the tensor-core kernel
     int off_C;                      // tensor-core kernel: this coupling's small constants as one contiguous block
-    int pad[3];
+    int cidx;                       // ordinal of this coupling among the chain's couplings (bin-index output)
+    int pad[2];
 };
 static_assert(sizeof(StepDesc) % 16 == 0, "StepDesc must keep the packed blocks 16-byte aligned");
 
@@ -222,7 +225,14 @@ struct ChainArgs {
     float peakness;
     LatentConst lc;
     int u_fmax, u_hmax, u_blmax;   // tensor-core kernel: max conditioner inputs / hidden biases / last-layer bias floats
+    int* idx_out;       // (M, n_couplings, d) bin indices of every spline evaluation, or null (parity evidence)
+    int n_couplings;
 };
+
+// bin index of event m, coupling s.cidx, transformed dim jj (zf_chain_bin_indices)
+__device__ __forceinline__ void put_idx(const ChainArgs& a, const StepDesc& s, long long m, int jj, int idx) {
+    if (a.idx_out) a.idx_out[(m * a.n_couplings + s.cidx) * s.d + jj] = idx;
+}
 
 __device__ __forceinline__ int pmod(int a, int D) {
     int r = a % D;
@@ -279,8 +289,8 @@ __device__ __forceinline__ void gemm_pass(const float* __restrict__ act_in, int 
 }
 
 template <bool INVERSE>
-__device__ __forceinline__ void spline_rows(float* th, int Pst, int K, const KnotNorm& kn, float* xcol,
-                                            float& ldc, int tid) {
+__device__ __forceinline__ int spline_rows(float* th, int Pst, int K, const KnotNorm& kn, float* xcol,
+                                           float& ldc, int tid) {
     // one thread per sample of the tile (tid < TM): theta row -> bin -> transform
     float* row = th + tid * Pst;
     const float v = xcol[tid];
@@ -298,10 +308,12 @@ __device__ __forceinline__ void spline_rows(float* th, int Pst, int K, const Kno
     } else {
         xcol[tid] = rqs_eval_inverse(v, b);
     }
+    return b.idx;
 }
 
 template <bool INVERSE>
-__device__ __forceinline__ void run_coupling(const StepDesc& s, const float* __restrict__ wsf, int D, int C,
+__device__ __forceinline__ void run_coupling(const ChainArgs& a, long long m0, int nm, const StepDesc& s,
+                                             const float* __restrict__ wsf, int D, int C,
                                              float* xs, const float* cs, float* act0, float* act1,
                                              float* wst, float& ld_acc, int tid) {
     const int d = s.d, F = s.F, F_p = ru(F, KC), rot = s.rot;
@@ -370,7 +382,10 @@ __device__ __forceinline__ void run_coupling(const StepDesc& s, const float* __r
             }
         }
         __syncthreads();
-        if (tid < TM) spline_rows<INVERSE>(nxt, Pst, K, kn, xs + pmod(jj - rot, D) * TM, ldc, tid);
+        if (tid < TM) {
+            const int idx = spline_rows<INVERSE>(nxt, Pst, K, kn, xs + pmod(jj - rot, D) * TM, ldc, tid);
+            if (tid < nm) put_idx(a, s, m0 + tid, jj, idx);
+        }
         __syncthreads();
     }
     ld_acc += ldc;  // Chain: log_det += ld   (bijectors.py:110)
@@ -458,7 +473,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
         for (int si = 0; si < a.n_steps; ++si) {
             const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
             if (s.kind == kStepKindShiftBounds) run_shift_bounds<INVERSE>(s, wsf, D, xs, ld_acc, tid);
-            else run_coupling<INVERSE>(s, wsf, D, C, xs, cs, act0, act1, wst, ld_acc, tid);
+            else run_coupling<INVERSE>(a, m0, nm, s, wsf, D, C, xs, cs, act0, act1, wst, ld_acc, tid);
         }
 
         // ---- store
@@ -941,6 +956,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     if (K == 16) spline_row_search_half<16, INVERSE>(dbase, cross, bls, v, bin);
                     else spline_row_search_half<32, INVERSE>(dbase, cross, bls, v, bin);
                     ex[0 * UM + m] = __int_as_float(bin.idx); ex[1 * UM + m] = bin.ks; ex[2 * UM + m] = bin.bs;
+                    if (m < nm) put_idx(a, s, m0 + m, 0, bin.idx);
                     pair_barrier(3);                         // bin published; both threads' TMEM reads are done
                     umma::fence_before_sync();
                     umma::mbar_arrive(&bars[B_DEMPTY_D + 0]);
@@ -972,6 +988,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 };
                 if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls + jj * NL, v, bin, release);
                 else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
+                if (m < nm) put_idx(a, s, m0 + m, jj, bin.idx);
                 if (!INVERSE) {
                     float y, ld;
                     rqs_eval_forward(v, bin, y, ld);
@@ -1729,6 +1746,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         };
                         if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls, v, bin, release);
                         else spline_row_tmem<32, INVERSE>(dbase, 0u, bls, v, bin, release);
+                        if (m < nm) put_idx(a, s, m0 + m, 0, bin.idx);
                         umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // last read of this occurrence's constants by S2
                         if (!INVERSE) {
                             float y, ld;
@@ -1791,6 +1809,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
     if (warp == MW) umma::tmem_dealloc(tb, 512);
 }
 
+#ifdef ZF_EXPERIMENTAL   // measured-slower negative results: kept out of the product library
 // =============================================================================================
 // Two-pipeline variant: tensor memory is full with one tile's operands and accumulators, so a second
 // 128-event tile cannot be in flight and the MMA and epilogue phases of a tile serialise.  Here a CTA
@@ -2095,6 +2114,8 @@ __global__ void __launch_bounds__(U2THREADS, 1) chain_umma2_kernel(const __grid_
     if (warp == 10) umma::tmem_dealloc(tb, 512);
 }
 
+#endif  // ZF_EXPERIMENTAL
+
 // ---- host side ------------------------------------------------------------------------
 
 struct Plan {
@@ -2152,6 +2173,7 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
                 return fail(ZF_ERR_UNSUPPORTED, "op %d: knots=%d needs %d columns per dim; the fused kernel holds %d",
                             i, cp.knots, P, NCOL);
             job.desc.kind = kStepKindCoupling;
+            job.desc.cidx = plan.n_couplings;
             plan.n_couplings++;
             {   // tensor-core kernel: hidden width 128 throughout, K in {16, 32}, small first layer
                 bool ok = cp.n_hidden >= 1 && (cp.knots == 16 || cp.knots == 32) && (D - d + C) <= UFMAX && d <= UDMAX;
@@ -2238,24 +2260,51 @@ static LatentConst make_latent(int kind, float peakness) {
     return lc;
 }
 
+enum PackMode : int { kPackAndRun = 0, kPackOnly = 1, kRunPacked = 2 };
+
+// Developer switches: which chain kernel (simt | umma | umma8 [| umma2 | umma16 in ZF_EXPERIMENTAL builds]) and which
+// train GEMM (simt | umma) run.  The environment (ZF_CHAIN_IMPL, ZF_GEMM_IMPL) is read ONCE per process;
+// zf_debug_set_impl overrides it afterwards (the parity tests compare the implementations inside one process).
+struct ImplSwitch {
+    char chain[16];
+    char gemm[16];
+};
+ImplSwitch& impl_switch() {
+    static ImplSwitch sw = [] {
+        ImplSwitch v{};
+        const char* e = getenv("ZF_CHAIN_IMPL");
+        if (e) strncpy(v.chain, e, sizeof(v.chain) - 1);
+        e = getenv("ZF_GEMM_IMPL");
+        if (e) strncpy(v.gemm, e, sizeof(v.gemm) - 1);
+        return v;
+    }();
+    return sw;
+}
+static const char* chain_impl_env() {
+    const char* v = impl_switch().chain;
+    return v[0] ? v : nullptr;
+}
+
 static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int latent_kind, float peakness,
                      const float* x, const float* c, long long M, float* y, float* log_det, float* lp,
                      void* workspace, size_t workspace_bytes, int acc_log_det = 0, int sample = 0,
-                     unsigned long long seed = 0) {
+                     unsigned long long seed = 0, int* idx_out = nullptr, int pack_mode = kPackAndRun) {
     Plan plan;
     if (int rc = build_plan(chain, plan)) return rc;
     ZF_REQUIRE(M >= 0, "M must be >= 0");
-    if (M == 0) return ZF_OK;
-    ZF_REQUIRE(x != nullptr || sample, "input tensor is NULL");
-    ZF_REQUIRE(chain->cdim == 0 || c != nullptr, "chain has cdim=%d but c is NULL", chain->cdim);
-    if (sample) {
-        ZF_REQUIRE(latent_kind >= 0 && latent_kind <= 3, "unknown latent kind %d", latent_kind);
-        ZF_REQUIRE(latent_kind != ZF_LATENT_BETA || peakness >= 1.f, "peakness must be at least 1 (distributions.py:96-97)");
-    }
-    if (mode == kModeLogProb) {
-        ZF_REQUIRE(lp != nullptr, "log_prob output is NULL");
-        ZF_REQUIRE(latent_kind >= 0 && latent_kind <= 3, "unknown latent kind %d", latent_kind);
-        ZF_REQUIRE(latent_kind != ZF_LATENT_BETA || peakness >= 1.f, "peakness must be at least 1 (distributions.py:96-97)");
+    if (M == 0 && pack_mode != kPackOnly) return ZF_OK;
+    if (pack_mode != kPackOnly) {
+        ZF_REQUIRE(x != nullptr || sample, "input tensor is NULL");
+        ZF_REQUIRE(chain->cdim == 0 || c != nullptr, "chain has cdim=%d but c is NULL", chain->cdim);
+        if (sample) {
+            ZF_REQUIRE(latent_kind >= 0 && latent_kind <= 3, "unknown latent kind %d", latent_kind);
+            ZF_REQUIRE(latent_kind != ZF_LATENT_BETA || peakness >= 1.f, "peakness must be at least 1 (distributions.py:96-97)");
+        }
+        if (mode == kModeLogProb) {
+            ZF_REQUIRE(lp != nullptr, "log_prob output is NULL");
+            ZF_REQUIRE(latent_kind >= 0 && latent_kind <= 3, "unknown latent kind %d", latent_kind);
+            ZF_REQUIRE(latent_kind != ZF_LATENT_BETA || peakness >= 1.f, "peakness must be at least 1 (distributions.py:96-97)");
+        }
     }
     const size_t need = plan.ws_floats * sizeof(float);
     if (workspace_bytes < need || (need && !workspace))
@@ -2265,17 +2314,19 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     if (int rc = get_device_info(&di)) return rc;
 
     float* ws = static_cast<float*>(workspace);
-    // latency-bound re-layout of ~50k parameters per coupling: one thin wave over all SMs per step, all steps of the
-    // chain (up to kPackBatch) in one launch
-    for (size_t j0 = 0; j0 < plan.jobs.size(); j0 += kPackBatch) {
-        const size_t nb = std::min<size_t>(kPackBatch, plan.jobs.size() - j0);
-        PackBatch* batch = new PackBatch;   // 25 KB: keep it off the stack
-        for (size_t j = 0; j < nb; ++j) batch->jobs[j] = plan.jobs[j0 + j];
-        pack_step_kernel<<<dim3((unsigned)di.sm_count, (unsigned)nb), 256, 0, stream>>>(*batch, ws);
-        delete batch;
-        count_launch();
+    if (pack_mode != kRunPacked) {
+        // latency-bound re-layout of ~50k parameters per coupling: one thin wave over all SMs per step, all steps of
+        // the chain (up to kPackBatch) in one launch.  The 25 KB parameter block lives in a per-thread buffer.
+        static thread_local PackBatch batch;
+        for (size_t j0 = 0; j0 < plan.jobs.size(); j0 += kPackBatch) {
+            const size_t nb = std::min<size_t>(kPackBatch, plan.jobs.size() - j0);
+            for (size_t j = 0; j < nb; ++j) batch.jobs[j] = plan.jobs[j0 + j];
+            pack_step_kernel<<<dim3((unsigned)di.sm_count, (unsigned)nb), 256, 0, stream>>>(batch, ws);
+            count_launch();
+        }
+        ZF_CUDA_CHECK(cudaGetLastError());
+        if (pack_mode == kPackOnly) return ZF_OK;
     }
-    ZF_CUDA_CHECK(cudaGetLastError());
 
     ChainArgs a{};
     a.x = x; a.c = c; a.y = y; a.log_det = log_det; a.lp = lp;
@@ -2289,12 +2340,28 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     a.seed = seed;
     a.peakness = peakness;
     a.lc = make_latent(latent_kind, peakness);
+    a.idx_out = idx_out;
+    a.n_couplings = plan.n_couplings;
+
+    // once per device and kernel: opt in to the large dynamic shared-memory carve-out
+    auto set_smem = [&](const void* fn, size_t bytes) -> int {
+        static std::mutex mu;
+        static std::map<std::pair<const void*, int>, size_t> done;
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = done[{fn, di.device}];
+        if (have < bytes) {
+            ZF_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            have = bytes;
+        }
+        return ZF_OK;
+    };
 
     // tensor-core kernel when every coupling fits it (ZF_CHAIN_IMPL=simt forces the FFMA kernel)
-    const char* impl = getenv("ZF_CHAIN_IMPL");
+    const char* impl = chain_impl_env();
     const bool want_umma = plan.umma_ok && plan.n_couplings > 0 && !(impl && impl[0] == 's');
     if (impl && strcmp(impl, "umma") == 0 && !want_umma)
         return fail(ZF_ERR_UNSUPPORTED, "ZF_CHAIN_IMPL=umma but this chain does not fit the tensor-core kernel");
+#ifdef ZF_EXPERIMENTAL
     // ZF_CHAIN_IMPL=umma2 opts into the two-pipeline variant (measured slower on B200: 602M vs 692M events/s on
     // two_moons_conditional, 61M vs 80M on the 16-D config - each MMA computes 128 lanes for 64 useful ones)
     if (want_umma && impl && strcmp(impl, "umma2") == 0) {
@@ -2304,10 +2371,10 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
             const long long tiles = (M + U2M - 1) / U2M;
             const unsigned g2 = (unsigned)std::min<long long>((tiles + 1) / 2, (long long)di.sm_count);
             if (mode == kModeInverse) {
-                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                if (int rc = set_smem((const void*)chain_umma2_kernel<true>, smem2)) return rc;
                 chain_umma2_kernel<true><<<g2, U2THREADS, smem2, stream>>>(a, plan.Fmax, plan.Hmax, plan.BLmax);
             } else {
-                ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                if (int rc = set_smem((const void*)chain_umma2_kernel<false>, smem2)) return rc;
                 chain_umma2_kernel<false><<<g2, U2THREADS, smem2, stream>>>(a, plan.Fmax, plan.Hmax, plan.BLmax);
             }
             count_launch();
@@ -2315,6 +2382,7 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
             return ZF_OK;
         }
     }
+#endif
     if (want_umma) {
         a.u_fmax = plan.Fmax;
         a.u_hmax = plan.Hmax;
@@ -2330,10 +2398,10 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
                 if (psmem <= (size_t)di.max_smem_optin) {
                     const unsigned pgrid = (unsigned)std::min<long long>((tiles + 1) / 2, (long long)di.sm_count);
                     if (mode == kModeInverse) {
-                        ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                        if (int rc = set_smem((const void*)chain_umma_pp_kernel<true>, psmem)) return rc;
                         chain_umma_pp_kernel<true><<<pgrid, PP_THREADS, psmem, stream>>>(a);
                     } else {
-                        ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_umma_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                        if (int rc = set_smem((const void*)chain_umma_pp_kernel<false>, psmem)) return rc;
                         chain_umma_pp_kernel<false><<<pgrid, PP_THREADS, psmem, stream>>>(a);
                     }
                     count_launch();
@@ -2341,17 +2409,22 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
                     return ZF_OK;
                 }
             }
-            // ZF_CHAIN_IMPL=umma16: 16 epilogue warps with a setmaxnreg register split.  Measured no faster than the
-            // default 8 (the activation phases are bound by the SFU / tensor-memory-store port, not by latency).
-            const bool eight = !(impl && strcmp(impl, "umma16") == 0);
             auto launch = [&](auto kern, unsigned threads) -> int {
-                ZF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+                if (int rc = set_smem((const void*)kern, usmem)) return rc;
                 kern<<<ugrid, threads, usmem, stream>>>(a);
                 return ZF_OK;
             };
             int rc;
+#ifdef ZF_EXPERIMENTAL
+            // ZF_CHAIN_IMPL=umma16: 16 epilogue warps with a setmaxnreg register split.  Measured no faster than the
+            // default 8 (the activation phases are bound by the SFU / tensor-memory-store port, not by latency).
+            const bool eight = !(impl && strcmp(impl, "umma16") == 0);
             if (mode == kModeInverse) rc = eight ? launch(chain_umma_kernel<true, 2>, 320) : launch(chain_umma_kernel<true, 4>, 640);
             else rc = eight ? launch(chain_umma_kernel<false, 2>, 320) : launch(chain_umma_kernel<false, 4>, 640);
+#else
+            if (mode == kModeInverse) rc = launch(chain_umma_kernel<true, 2>, 320);
+            else rc = launch(chain_umma_kernel<false, 2>, 320);
+#endif
             if (rc != ZF_OK) return rc;
             count_launch();
             ZF_CUDA_CHECK(cudaGetLastError());
@@ -2367,10 +2440,10 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     const unsigned grid = (unsigned)std::min<long long>(n_tiles, (long long)di.sm_count * bps);
 
     if (mode == kModeInverse) {
-        ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (int rc = set_smem((const void*)chain_kernel<true>, smem)) return rc;
         chain_kernel<true><<<grid, kChainThreads, smem, stream>>>(a);
     } else {
-        ZF_CUDA_CHECK(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (int rc = set_smem((const void*)chain_kernel<false>, smem)) return rc;
         chain_kernel<false><<<grid, kChainThreads, smem, stream>>>(a);
     }
     count_launch();
@@ -2399,6 +2472,13 @@ extern "C" int zf_chain_forward_acc(void* stream, const zf_chain* chain, const f
                          nullptr, workspace, workspace_bytes, 1);
 }
 
+extern "C" int zf_chain_bin_indices(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                                    int32_t* idx, void* workspace, size_t workspace_bytes) {
+    ZF_REQUIRE(idx != nullptr || M == 0, "bin_indices: output tensor is NULL");
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeForward, 0, 0.f, x, c, (long long)M, nullptr, nullptr,
+                         nullptr, workspace, workspace_bytes, 0, 0, 0, idx);
+}
+
 extern "C" int zf_chain_inverse(void* stream, const zf_chain* chain, const float* z, const float* c, int64_t M,
                                 float* x, void* workspace, size_t workspace_bytes) {
     ZF_REQUIRE(x != nullptr || M == 0, "output tensor is NULL");
@@ -2418,6 +2498,50 @@ extern "C" int zf_flow_log_prob(void* stream, const zf_chain* chain, int32_t lat
                                 size_t workspace_bytes) {
     return zf::run_chain((cudaStream_t)stream, chain, zf::kModeLogProb, latent_kind, peakness, x, c, (long long)M,
                          nullptr, nullptr, log_prob, workspace, workspace_bytes);
+}
+
+extern "C" int zf_debug_set_impl(const char* chain_impl, const char* gemm_impl) {
+    zf::ImplSwitch& sw = zf::impl_switch();
+    memset(sw.chain, 0, sizeof(sw.chain));
+    memset(sw.gemm, 0, sizeof(sw.gemm));
+    if (chain_impl) strncpy(sw.chain, chain_impl, sizeof(sw.chain) - 1);
+    if (gemm_impl) strncpy(sw.gemm, gemm_impl, sizeof(sw.gemm) - 1);
+    return ZF_OK;
+}
+
+// ---- the same passes with the parameter re-layout hoisted out (pack once per parameter update, run many times) ----
+extern "C" int zf_chain_pack(void* stream, const zf_chain* chain, void* workspace, size_t workspace_bytes) {
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeForward, 0, 0.f, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                         workspace, workspace_bytes, 0, 0, 0, nullptr, zf::kPackOnly);
+}
+
+extern "C" int zf_chain_forward_packed(void* stream, const zf_chain* chain, const float* x, const float* c, int64_t M,
+                                       float* y, float* log_det, void* workspace, size_t workspace_bytes) {
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeForward, 0, 0.f, x, c, (long long)M, y, log_det, nullptr,
+                         workspace, workspace_bytes, 0, 0, 0, nullptr, zf::kRunPacked);
+}
+
+extern "C" int zf_chain_inverse_packed(void* stream, const zf_chain* chain, const float* z, const float* c, int64_t M,
+                                       float* x, void* workspace, size_t workspace_bytes) {
+    ZF_REQUIRE(x != nullptr || M == 0, "output tensor is NULL");
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeInverse, 0, 0.f, z, c, (long long)M, x, nullptr, nullptr,
+                         workspace, workspace_bytes, 0, 0, 0, nullptr, zf::kRunPacked);
+}
+
+extern "C" int zf_flow_log_prob_packed(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness,
+                                       const float* x, const float* c, int64_t M, float* log_prob, void* workspace,
+                                       size_t workspace_bytes) {
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeLogProb, latent_kind, peakness, x, c, (long long)M, nullptr,
+                         nullptr, log_prob, workspace, workspace_bytes, 0, 0, 0, nullptr, zf::kRunPacked);
+}
+
+extern "C" int zf_flow_sample_packed(void* stream, const zf_chain* chain, int32_t latent_kind, float peakness,
+                                     uint64_t seed, const float* c, int64_t M, float* x, void* workspace,
+                                     size_t workspace_bytes) {
+    ZF_REQUIRE(x != nullptr || M == 0, "output tensor is NULL");
+    return zf::run_chain((cudaStream_t)stream, chain, zf::kModeInverse, latent_kind, peakness, nullptr, c, (long long)M, x,
+                         nullptr, nullptr, workspace, workspace_bytes, 0, 1, (unsigned long long)seed, nullptr,
+                         zf::kRunPacked);
 }
 
 #ifdef ZF_TRACE

@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_grad_kernel(LatentConst lc, const float* __restrict__ z,
                                                         const float* __restrict__ log_det, long long M, int D,
-                                                        float wgt, float* __restrict__ lp_out, float* __restrict__ gz,
+                                                        float wgt, const float* __restrict__ cot,
+                                                        float* __restrict__ lp_out, float* __restrict__ gz,
                                                         float* __restrict__ glp, double* lp_sum) {
     __shared__ double red[256];
     double local = 0.0;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LatentConst lc, const fl
         const float raw = lat + log_det[m];
         const float lp = nan_to_num_lp(raw);
         const bool fin = (raw == raw) && fabsf(raw) <= FLT_MAX;
-        const float w = fin ? wgt : 0.f;   // nan_to_num replaces non-finite lp by constants: zero gradient
+        const float w = fin ? (cot ? cot[m] : wgt) : 0.f;   // nan_to_num replaces non-finite lp by constants: zero gradient
         if (lp_out) lp_out[m] = lp;
         glp[m] = w;
         local += (double)lp;
@@ -366,14 +367,16 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmA
     if (MODE == 2 && g.colsum && blockIdx.x == 0 && tid < GT && j0 + tid < g.J) atomicAdd(&g.colsum[j0 + tid], csum);
 }
 
+struct ImplSwitch { char chain[16]; char gemm[16]; };
+ImplSwitch& impl_switch();
 int launch_umma_gemm(cudaStream_t st, int mode, const float* A, long long lda, const float* B, long long ldb, float* C,
                      long long ldc, const float* bias, float* colsum, const float* Z, long long ldz, int a_swish,
                      long long I, long long J, long long R, long long r_slab);
 
 static int launch_gemm(cudaStream_t st, int mode, const GemmArgs& g) {
     // tensor-core (tcgen05, 3xTF32) GEMM by default; ZF_GEMM_IMPL=simt keeps the fp32 FFMA kernel
-    const char* impl = getenv("ZF_GEMM_IMPL");
-    if (!(impl && impl[0] == 's'))
+    const char* impl = impl_switch().gemm;   // read once per process (zf_chain.cu)
+    if (impl[0] != 's')
         return launch_umma_gemm(st, mode, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.bias, g.colsum, g.Z, g.ldz, g.a_swish,
                                 g.I, g.J, g.R, mode == 2 ? 4096 : 0);
     dim3 grid((unsigned)((g.I + GT - 1) / GT), (unsigned)((g.J + GT - 1) / GT), 1);
@@ -760,9 +763,9 @@ extern "C" int zf_bn_finalize(void* stream, const double* sums, double count, in
     return ZF_OK;
 }
 
-extern "C" int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
-                                 int64_t M, int32_t D, double global_count, float* lp, float* gz, float* glp,
-                                 double* lp_sum) {
+extern "C" int zf_flow_loss_grad_ct(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
+                                    int64_t M, int32_t D, double global_count, const float* lp_cotangent, float* lp,
+                                    float* gz, float* glp, double* lp_sum) {
     ZF_REQUIRE(z && log_det && gz && glp && lp_sum && M >= 1 && D >= 1 && global_count >= 1, "flow_loss_grad: bad argument");
     LatentConst lc{};
     lc.kind = latent_kind;
@@ -771,11 +774,17 @@ extern "C" int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakne
     lc.lognorm = (float)log(2.0 * M_PI * 0.1 * 0.1);
     lc.logmass = (float)log(0.5 * (erf(5.0 / sqrt(2.0)) - erf(-5.0 / sqrt(2.0))));
     loss_grad_kernel<<<grid_for(M, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(lc, z, log_det, M, D,
-                                                                                  (float)(-1.0 / global_count), lp, gz, glp,
-                                                                                  lp_sum);
+                                                                                  (float)(-1.0 / global_count),
+                                                                                  lp_cotangent, lp, gz, glp, lp_sum);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;
+}
+
+extern "C" int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakness, const float* z, const float* log_det,
+                                 int64_t M, int32_t D, double global_count, float* lp, float* gz, float* glp,
+                                 double* lp_sum) {
+    return zf_flow_loss_grad_ct(stream, latent_kind, peakness, z, log_det, M, D, global_count, nullptr, lp, gz, glp, lp_sum);
 }
 
 static size_t cpl_bwd_floats_per_sample(const zf_coupling* cp, int D, int C) {

@@ -338,8 +338,7 @@ int launch_umma_gemm(cudaStream_t st, int mode, const float* A, long long lda, c
                      long long ldc, const float* bias, float* colsum, const float* Z, long long ldz, int a_swish,
                      long long I, long long J, long long R, long long r_slab) {
     UGemmArgs g{A, lda, B, ldb, C, ldc, bias, colsum, Z, ldz, a_swish, I, J, R, r_slab};
-    const char* w = getenv("ZF_GEMM_WIDE");
-    const bool wide = J > 128 && !(w && w[0] == '0');
+    const bool wide = J > 128;
     if (mode == 2) {
         // grad-weight: the output is tiny, the reduction (samples) is split into slabs so that at least
         // ~3 waves of CTAs are in flight; each CTA adds its partial tile with atomics

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._device import ptr, require_cuda, stream_ptr, to_device_f32
-from ._train import TrainEngine
+from ._train import TrainEngine, _allreduce, _dist_world
 from .flow import Flow
 
 __all__ = ["train", "nadamw", "adamw", "Optimizer", "DEFAULT_OPTIMIZER"]
@@ -75,8 +75,13 @@ def train(
     """Trains the normalizing flow on the provided inputs (train.py:18-138).
 
     Returns (best_variables, best_epoch, loss_train, loss_test); the variables are a FLAX-shaped
-    pytree of device tensors.  ``group``: optional torch.distributed group for data-parallel
-    training (every rank passes its own shard of X_train / C_train).
+    pytree of device tensors.
+
+    Data-parallel training: initialise torch.distributed (or pass ``group``) and give every rank its own row
+    shard of X_train / C_train AND of X_test / C_test.  The shards must give every rank the same number of
+    minibatch steps per epoch (checked up front: ``ValueError`` on every rank otherwise); the losses in the
+    returned histories are global (sums and counts are all-reduced), so the non-finite abort, the best-epoch
+    bookkeeping and the early stop take the same decision on every rank.
     """
     if warmup < 1:
         warmup = warmup * epochs
@@ -105,12 +110,18 @@ def train(
                          eps=optimizer.eps, weight_decay=optimizer.weight_decay, nesterov=optimizer.nesterov, group=group)
 
     lib = _lib.load()
-    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)   # [-sum(lp), count]
+    _, world = _dist_world(group)
+    n_rows = X_train.shape[0]
+    step_counts = _global_step_counts(n_rows, batch_size, dev, group, world)
 
-    def metric_fn(vs, x, c) -> float:  # train.py:75-78
+    def metric_fn(vs, x, c) -> float:  # train.py:75-78, over all ranks' rows
         lp = flow.apply(vs, x, c)
         _lib.check(lib.zf_neg_sum(stream_ptr(), ptr(lp), lp.shape[0], ptr(acc)), "zf_neg_sum")
-        return float(acc.item()) / lp.shape[0]
+        acc[1] = lp.shape[0]
+        _allreduce(acc, group, "sum")
+        total, count = acc.tolist()
+        return total / count
 
     def shuffled(t, epoch_seed, out):  # X_train[perm], train.py:104-108
         tt = t if t.ndim == 2 else t.reshape(-1, 1)
@@ -125,7 +136,6 @@ def train(
     X_perm = torch.empty_like(X_train)
     C_perm = None if C_train is None else torch.empty_like(C_train if C_train.ndim == 2 else C_train.reshape(-1, 1))
     best_epoch, best_variables = 0, engine.snapshot()
-    n_rows = X_train.shape[0]
     for epoch in epoch_iter:
         # one pass over a fresh shuffle of the training set (train.py:104-117)
         epoch_seed = (int(seed) * 0x9E3779B97F4A7C15 + epoch + 1) & 0xFFFFFFFFFFFFFFFF  # fold_in(iter_key, epoch)
@@ -133,10 +143,10 @@ def train(
         if C_train is not None:
             shuffled(C_train, epoch_seed, C_perm)
         xb = cb = None
-        for lo in range(0, n_rows, batch_size):
+        for k, lo in enumerate(range(0, n_rows, batch_size)):
             xb = X_perm[lo:lo + batch_size]
             cb = None if C_perm is None else C_perm[lo:lo + batch_size]
-            engine.step(xb, cb)
+            engine.step(xb, cb, global_count=step_counts[k])
 
         # metrics on the last minibatch and on the test set (train.py:119-121)
         current = engine.variables()
@@ -152,6 +162,23 @@ def train(
             break
 
     return best_variables, best_epoch, history_train, history_test
+
+
+def _global_step_counts(n_rows: int, batch_size: int, dev, group, world: int) -> List[int]:
+    """Global number of rows of every minibatch step of an epoch.  Every rank must run the same number of steps
+    (each step all-reduces statistics and gradients): raises ValueError on EVERY rank when the shards disagree."""
+    local = [min(batch_size, n_rows - lo) for lo in range(0, n_rows, batch_size)]
+    if world == 1:
+        return local
+    n = torch.tensor([len(local), -len(local)], dtype=torch.int64, device=dev)
+    _allreduce(n, group, "max")
+    n_max, n_min = int(n[0].item()), -int(n[1].item())
+    if n_max != n_min:
+        raise ValueError(f"data-parallel train(): ranks disagree on the number of minibatch steps per epoch "
+                         f"({n_min} .. {n_max}); shard X_train so that ceil(rows / batch_size) is the same everywhere")
+    t = torch.tensor(local, dtype=torch.int64, device=dev)
+    _allreduce(t, group, "sum")
+    return [int(v) for v in t.tolist()]
 
 
 def _progress_iter(epochs: int):

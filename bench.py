@@ -231,6 +231,7 @@ def build_flow(w, dev):
 
     from zenflow_b200 import Flow
     from zenflow_b200 import bijectors as bi
+    from zenflow_b200.distributions import Beta
 
     ops, v = make_variables(w)
     mods = []
@@ -241,7 +242,7 @@ def build_flow(w, dev):
             mods.append(bi.Roll(op["shift"]))
         else:
             mods.append(bi.NeuralSplineCoupling(knots=op["knots"], layers=op["layers"]))
-    flow = Flow(bi.Chain(mods))
+    flow = Flow(bi.Chain(mods), latent=Beta())   # its own latent: the default instance is shared and latches one dim
     tree = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
     variables = torch.utils._pytree.tree_map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev), tree)
     flow.latent._latch_dim(w["D"])

@@ -132,6 +132,11 @@ int zf_selftest_exact_math(void* stream, uint64_t* mismatches);
 int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
                      int32_t mask_mode /* 0: all lanes; 1: lanes 64-127 keep a 777 sentinel; 2: lanes 0-63 do */);
 
+/* The same product with the 3xFP16 split on kind::f16 (A as fp16 pairs in tensor memory, separate cross accumulator
+ * at scale 2^11), N % 16 == 0 <= 128, K % 16 == 0 <= 128.  variant 0 is the product layout; bit 0 swaps the halves of
+ * every A word (layout probe), bit 1 drops the cross products (plain fp16). */
+int zf_selftest_umma_f16(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out, int32_t variant);
+
 /* Self-test of the tcgen05 GEMM family used by the train step (zf_umma_gemm.cu), fp32 in/out:
  * mode 0: C[I][J] = opA(A[I][R]) B[R][J] + bias; mode 1: C[I][J] = (A[I][R] B[J][R]^T) * swish'(Z[I][J]);
  * mode 2: C[I][J] += opA(A[R][I])^T B[R][J], colsum[J] += column sums of B (r_slab rows per CTA). */

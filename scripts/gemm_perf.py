@@ -7,6 +7,8 @@ if os.environ.get("ZF_LIB"):
     _zb.LIB_PATH = os.path.abspath(os.environ["ZF_LIB"]); os.environ["ZENFLOW_B200_NO_BUILD"] = "1"
 from zenflow_b200 import _lib
 lib = _lib.load()
+if len(sys.argv) > 1:
+    _lib.set_impl(None, sys.argv[1])   # 'legacy': register-path loaders
 M = 262144
 dev = "cuda"
 def t(fn, n=5):

@@ -126,6 +126,20 @@ class ChainSpec:
                                         ptr(ws), nbytes), "zf_chain_forward")
         return y, ld
 
+    def bin_indices(self, x, c):
+        """Bin index of every spline evaluation of the forward chain: (M, n_couplings, D//2) int32 in [0, K]
+        (zf_chain_bin_indices; parity evidence)."""
+        lib = _lib.load()
+        xd, cd = self._inputs(x, c)
+        M = xd.shape[0]
+        ch = self._chain()
+        ws, nbytes = self._workspace(lib, ch, M)
+        n_c = sum(1 for op in self._ops if op.kind == _lib.OP_COUPLING)
+        idx = torch.full((M, n_c, max(1, self.dim // 2)), -1, dtype=torch.int32, device=self.device)
+        _lib.check(lib.zf_chain_bin_indices(stream_ptr(), C.byref(ch), ptr(xd), ptr(cd), M, ptr(idx), ptr(ws), nbytes),
+                   "zf_chain_bin_indices")
+        return idx
+
     def inverse(self, z, c):
         lib = _lib.load()
         zd, cd = self._inputs(z, c)

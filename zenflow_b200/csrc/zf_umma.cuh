@@ -5,6 +5,8 @@
 #pragma once
 #include "zf_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace zf {
 namespace umma {
 
@@ -74,6 +76,44 @@ __device__ __forceinline__ float to_tf32(float x) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = to_tf32(x);
     lo = x - hi;
+}
+
+// ---- 3xFP16 split ----------------------------------------------------------------------------------
+// The same idea on kind::f16 (twice the tensor rate of kind::tf32, half the operand bytes): hi = x rounded to
+// fp16 (11 significant bits, like tf32), lo' = (x - hi) * 2^11 rounded to fp16.  hi * hi products are exact in
+// the fp32 accumulator; the two cross products are accumulated SEPARATELY at scale 2^11 and added as
+// cross * 2^-11 in the epilogue (the scaling keeps lo' in fp16's normal range whenever hi is).  Valid for
+// |x| < 65504 (fp16 range); tiny |x| < 2^-14 lose relative but not absolute accuracy (error < 2^-25 + 2^-36).
+constexpr float kF16LoScale = 2048.0f, kF16LoUnscale = 1.0f / 2048.0f;
+// two consecutive reduction indices (k even in the low half-word) -> one 32-bit word of hi parts, one of lo' parts
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((x0 - hf.x) * kF16LoScale, (x1 - hf.y) * kF16LoScale);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__host__ __device__ constexpr uint32_t instr_desc_f16(int N) {   // kind::f16, fp16 x fp16 -> fp32, K-major, M = 128
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem, fp16 pairs] * B[smem, fp16]; K = 16 per instruction; issued by ONE thread
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u, z = 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+// half-word offset of element (n, k) in an fp16 B image of N rows: [k/8][n/8][n%8][k%8]
+__host__ __device__ inline int b_image_index_f16(int n, int k, int N) { return ((k >> 3) * (N >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7); }
+__device__ __forceinline__ void st8u(uint32_t a, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(a), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 
 // ---- descriptors ----------------------------------------------------------------------------------

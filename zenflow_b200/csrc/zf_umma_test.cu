@@ -79,6 +79,100 @@ __global__ void __launch_bounds__(160) umma_selftest_kernel(const float* __restr
 }
 }  // namespace zf
 
+// The same product with the 3xFP16 split (kind::f16): A as fp16 pairs in tensor memory (K / 2 columns per part),
+// B as fp16 K-major images, main and cross accumulators.  variant bit 0: swap the two halves of every A word
+// (layout probe); bit 1: skip the cross products (plain fp16).
+namespace zf {
+__global__ void __launch_bounds__(160) umma_selftest_f16_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                int N, int K, float* __restrict__ out, int variant) {
+    extern __shared__ __align__(128) float sBf[];  // hi image then lo image, N*K halves each
+    __half* sB = reinterpret_cast<__half*>(sBf);
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 4) umma::tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int e = tid; e < N * K; e += blockDim.x) {
+        const int n = e / K, k = e - n * K;
+        const float x = B[e];
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn((x - __half2float(h)) * umma::kF16LoScale);
+        sB[umma::b_image_index_f16(n, k, N)] = h;
+        sB[N * K + umma::b_image_index_f16(n, k, N)] = l;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    const uint32_t colAhi = 0, colAlo = 64, colD = 128, colX = 256;
+    if (warp < 4) {
+        const int m = warp * 32 + lane;
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float x0 = A[m * K + k0 + 2 * i], x1 = A[m * K + k0 + 2 * i + 1];
+                if (variant & 1) umma::split_f16x2(x1, x0, hi[i], lo[i]);
+                else umma::split_f16x2(x0, x1, hi[i], lo[i]);
+            }
+            umma::st8u(umma::taddr(tb, warp * 32, colAhi + k0 / 2), hi);
+            umma::st8u(umma::taddr(tb, warp * 32, colAlo + k0 / 2), lo);
+        }
+        umma::wait_st();
+    }
+    fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (warp == 4) {
+        if (umma::elect_one()) {
+            const uint32_t idesc = umma::instr_desc_f16(N);
+            const uint32_t lbo = (uint32_t)(N >> 3) * 128u, sbo = 128u;
+            const uint32_t bhi = smem_u32(sB), blo = smem_u32(sB + N * K);
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, sbo);
+                const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, sbo);
+                if (!(variant & 2)) {
+                    umma::mma_f16_ts(tb + colX, tb + colAlo + ks * 8, dhi, idesc, ks > 0);
+                    umma::mma_f16_ts(tb + colX, tb + colAhi + ks * 8, dlo, idesc, true);
+                }
+                umma::mma_f16_ts(tb + colD, tb + colAhi + ks * 8, dhi, idesc, ks > 0);
+            }
+            umma::commit(&bar);
+        }
+        __syncwarp();
+    }
+    if (warp < 4) {
+        mbar_wait(&bar, 0);
+        umma::fence_after_sync();
+        const int m = warp * 32 + lane;
+        for (int n0 = 0; n0 < N; n0 += 8) {
+            float v[8], w[8];
+            umma::ld8(umma::taddr(tb, warp * 32, colD + n0), v);
+            umma::ld8(umma::taddr(tb, warp * 32, colX + n0), w);
+            umma::wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[m * N + n0 + i] = (variant & 2) ? v[i] : fmaf(w[i], umma::kF16LoUnscale, v[i]);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) umma::tmem_dealloc(tb, 512);
+}
+}  // namespace zf
+
+extern "C" int zf_selftest_umma_f16(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
+                                    int32_t variant) {
+    ZF_REQUIRE(A && B && out, "selftest_umma_f16: null argument");
+    ZF_REQUIRE(N >= 16 && N <= 128 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0, "selftest_umma_f16: bad N/K");
+    const size_t smem = (size_t)2 * N * K * sizeof(__half);
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(zf::umma_selftest_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    zf::umma_selftest_f16_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, N, K, out, variant);
+    zf::count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
 extern "C" int zf_selftest_umma(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
                                 int32_t mask_mode) {
     ZF_REQUIRE(A && B && out, "selftest_umma: null argument");

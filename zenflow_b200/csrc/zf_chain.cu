@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
         }
     }
     // tensor-core images: per unit (hidden layer l >= 1, or one transformed dim of the last layer)
-    // 4 K-chunks of 32, each [hi image | lo image], image = [k/4][n/8][n%8][k%4]  (zf_umma.cuh)
+    // 4 K-chunks of 32, each [hi image | lo image] in fp16 (3xFP16 split, zf_umma.cuh), image = [k/8][n/8][n%8][k%8]
     if (s.umma_ok) {
         const int L = s.n_hidden, P = 3 * s.K - 1, NL = ru(P, 16), d = s.d;
         {   // the constant block the producer warp fetches with one bulk copy per coupling
@@ -193,10 +193,10 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
                 float val = 0.f;
                 if (l < L) val = W[(size_t)k * ldw + n];
                 else if (n < P) val = W[(size_t)k * ldw + u * P + n];
-                float hi, lo;
-                umma::split_tf32(val, hi, lo);
-                float* dst = ws + s.off_U[l] + (size_t)u * N * 256 + (size_t)(k >> 5) * N * 64;
-                const int ii = umma::b_image_index(n, k & 31, N);
+                const __half hi = __float2half_rn(val);
+                const __half lo = __float2half_rn((val - __half2float(hi)) * umma::kF16LoScale);
+                __half* dst = reinterpret_cast<__half*>(ws + s.off_U[l] + (size_t)u * N * 128 + (size_t)(k >> 5) * N * 32);
+                const int ii = umma::b_image_index_f16(n, k & 31, N);
                 dst[ii] = hi;
                 dst[N * 32 + ii] = lo;
             }
@@ -510,8 +510,13 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
 // Tensor memory (512 columns): A_hi [0,128) | A_lo [128,256) | D0 [256,384) | D1 [384,512).
 // Hidden layers accumulate into D0; the last layer runs one transformed dim at a time, alternating
 // D0/D1 so that the spline rows of dim j (warps 0-3 for even j, 4-7 for odd j) overlap the MMAs of j+1.
-// 3xTF32: x = hi + lo (tf32 each), D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (fp32-class accuracy;
-// a single TF32/BF16 pass would break the rel-1e-5 parity).
+// 3xFP16 split on kind::f16 (zf_umma.cuh): x = hi + lo' * 2^-11 (fp16 each), main = A_hi*B_hi and
+// cross = A_lo'*B_hi + A_hi*B_lo' in separate accumulators, theta = main + cross * 2^-11: fp32-class accuracy
+// (measured: below fp32 sgemm's error) at twice the tensor rate and half the operand bytes of the 3xTF32 split
+// it replaces; a single TF32/BF16 pass would break the rel-1e-5 parity.  Valid while the
+// conditioner's activations and weights stay below 65504 in magnitude (beyond that the event's result is NaN).
+// Tensor memory (512 columns): A_hi [0,64) | A_lo [64,128) as fp16 pairs; hidden layers main [128,256), cross
+// [256,384); last layer, buffer b: main [128 + 192 b, +96), cross 96 columns further.
 // =============================================================================================
 #ifdef ZF_TRACE   // developer build only (scripts/trace_chain.py): per-phase clock64 stamps of one steady-state tile
 __device__ long long g_zf_trace[4][64];
@@ -530,7 +535,9 @@ constexpr int UM = 128;
 #define ZF_URING 4
 #endif
 constexpr int URING = ZF_URING;   // <= 8 (barrier numbering below)
-constexpr int URING_FLOATS = 8192;  // 32 KB: one K-chunk (32) of a 128-column unit, hi|lo
+constexpr int URING_FLOATS = 4096;  // 16 KB: one K-chunk (32) of a 128-column unit, fp16 hi|lo
+constexpr uint32_t TC_ALO = 64, TC_HMAIN = 128, TC_HCROSS = 256, TC_XOFF = 96;
+__host__ __device__ constexpr uint32_t tc_dmain(int b) { return 128u + 192u * (uint32_t)b; }
 constexpr int UFMAX = 32;           // conditioner inputs handled by the SIMT first layer
 constexpr int UDMAX = 32;           // transformed dims
 // B_AREADY + c: K-chunk c (32 columns) of the current activation version is in tensor memory AND the
@@ -572,58 +579,25 @@ __device__ __forceinline__ float swish_fast(float x) {
     return x * r;
 }
 
-// activation tile column block [n0, n0+16) of this thread's event: swish, split, store to A_hi / A_lo
-__device__ __forceinline__ void store_activation16(uint32_t tb, uint32_t lane_base, int n0, float (&v)[16]) {
-    float hi[8], lo[8];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) umma::split_tf32(swish_fast(v[h * 8 + i]), hi[i], lo[i]);
-        umma::st8(umma::taddr(tb, lane_base, n0 + h * 8), hi);
-        umma::st8(umma::taddr(tb, lane_base, 128 + n0 + h * 8), lo);
-    }
-}
-
-// the same in two steps, so that a barrier arrival can sit between the arithmetic and the stores
-__device__ __forceinline__ void activation16_compute(const float (&v)[16], float (&hi)[16], float (&lo)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) umma::split_tf32(swish_fast(v[i]), hi[i], lo[i]);
-}
-__device__ __forceinline__ void activation16_store(uint32_t tb, uint32_t lane_base, int n0, const float (&hi)[16],
-                                                   const float (&lo)[16]) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float th[8], tl[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { th[i] = hi[h * 8 + i]; tl[i] = lo[h * 8 + i]; }
-        umma::st8(umma::taddr(tb, lane_base, n0 + h * 8), th);
-        umma::st8(umma::taddr(tb, lane_base, 128 + n0 + h * 8), tl);
-    }
-}
-
 // ---- theta row of this thread's event from a D buffer in tensor memory ---------------------------
-// issue the TMEM loads of one raw K-block (main accumulator, and the separate cross accumulator at
-// +3K when K = 16); tcgen05.wait::ld must follow before the registers are read
+// issue the TMEM loads of one raw K-block (main accumulator and the cross accumulator cross_off columns further);
+// tcgen05.wait::ld must follow before the registers are read
 template <int KT>
 __device__ __forceinline__ void theta_block_issue(uint32_t dbase, uint32_t cross_off, int col, float (&p)[KT], float (&w)[KT]) {
-    constexpr bool kSplit = (2 * 3 * KT <= 128);
 #pragma unroll
     for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + col + c0, p + c0);
-    if (kSplit) {
 #pragma unroll
-        for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + cross_off + col + c0, w + c0);
-    }
+    for (int c0 = 0; c0 < KT; c0 += 16) umma::ld16(dbase + cross_off + col + c0, w + c0);
 }
-// main + cross + bias; returns max |theta| of the block (NaN-poisoned to +inf)
+// main + cross * 2^-11 + bias; returns max |theta| of the block (NaN-poisoned to +inf)
 template <int KT>
 __device__ __forceinline__ float theta_block_finish(int col, const float* __restrict__ bias, float (&p)[KT],
                                                     const float (&w)[KT]) {
-    constexpr bool kSplit = (2 * 3 * KT <= 128);
     float amax = 0.f;
     bool nan = false;
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
-        p[j] = kSplit ? (p[j] + w[j]) + bias[col + j] : p[j] + bias[col + j];
+        p[j] = fmaf(w[j], umma::kF16LoUnscale, p[j]) + bias[col + j];
         amax = fmaxf(amax, fabsf(p[j]));
         nan = nan || (p[j] != p[j]);
     }
@@ -646,17 +620,17 @@ __device__ __forceinline__ void spline_row_tmem(uint32_t dbase, uint32_t cross_o
     RqsCheck chk;
     theta_block_issue<KT>(dbase, cross_off, cs_, pa, wa);
     umma::wait_ld();
+    const float amax_s = theta_block_finish<KT>(cs_, bias, pa, wa);   // (wa is dead before pb / wb come alive)
     theta_block_issue<KT>(dbase, cross_off, co_, pb, wb);          // in flight during the search pass
-    const float amax_s = theta_block_finish<KT>(cs_, bias, pa, wa);
     if (__any_sync(0xffffffffu, !(amax_s < kThetaFastBound)))
         rqs_block_search<KT, true>(pa, v, kn, b.idx, b.ks, b.bs, chk);
     else
         rqs_block_search<KT, false>(pa, v, kn, b.idx, b.ks, b.bs, chk);
     umma::wait_ld();
+    const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
     theta_block_issue<KT>(dbase, cross_off, 2 * KT, pa, wa);       // slopes reuse the searched block's registers
     umma::wait_ld();
     release();                                          // every TMEM read of this row is done
-    const float amax_o = theta_block_finish<KT>(co_, bias, pb, wb);
     if (__any_sync(0xffffffffu, !(amax_o < kThetaFastBound)))
         rqs_block_other<KT, true>(pb, b.idx, kn, b.ko, b.bo, chk);
     else
@@ -736,25 +710,24 @@ __device__ __forceinline__ void tmem_load(uint32_t addr, float (&v)[CW]) {
     if constexpr (CW == 16) umma::ld16(addr, v);
     else umma::ld8(addr, v);
 }
+// swish + 3xFP16 split of CW consecutive activations (k = n0 .. n0 + CW) -> CW / 2 words of fp16 pairs each
 template <int CW>
-__device__ __forceinline__ void activation_compute(const float (&v)[CW], float (&hi)[CW], float (&lo)[CW]) {
+__device__ __forceinline__ void activation_compute(const float (&v)[CW], uint32_t (&hi)[CW / 2], uint32_t (&lo)[CW / 2]) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) umma::split_tf32(swish_fast(v[i]), hi[i], lo[i]);
+    for (int i = 0; i < CW / 2; ++i) umma::split_f16x2(swish_fast(v[2 * i]), swish_fast(v[2 * i + 1]), hi[i], lo[i]);
 }
 template <int CW>
-__device__ __forceinline__ void activation_store(uint32_t tb, uint32_t lane_base, int n0, const float (&hi)[CW],
-                                                 const float (&lo)[CW]) {
-    if constexpr (CW == 16) {
-        umma::st16(umma::taddr(tb, lane_base, n0), hi);
-        umma::st16(umma::taddr(tb, lane_base, 128 + n0), lo);
-    } else {
-        umma::st8(umma::taddr(tb, lane_base, n0), hi);
-        umma::st8(umma::taddr(tb, lane_base, 128 + n0), lo);
-    }
+__device__ __forceinline__ void activation_store(uint32_t tb, uint32_t lane_base, int n0, const uint32_t (&hi)[CW / 2],
+                                                 const uint32_t (&lo)[CW / 2]) {
+    static_assert(CW == 16, "one tcgen05.st.x8 per part");
+    umma::st8u(umma::taddr(tb, lane_base, n0 >> 1), hi);
+    umma::st8u(umma::taddr(tb, lane_base, TC_ALO + (n0 >> 1)), lo);
 }
 
-template <bool INVERSE, int NG, bool HELPER>
+template <bool INVERSE>
 __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
+    constexpr int NG = 2;
+    constexpr bool HELPER = false;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;   // half = column group g in [0, NG)
     constexpr int ET = NG * 128, CW = 32 / NG;                    // epilogue threads; columns per thread and K-chunk
@@ -854,7 +827,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int n0 = c * 32 + half * CW;
-                float acc[CW], ahi[CW], alo[CW];
+                float acc[CW];
+                uint32_t ahi[CW / 2], alo[CW / 2];
                 {
                     const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
 #pragma unroll
@@ -908,27 +882,28 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 // chunk c: accumulator columns [32c + CW g, +CW) -> the same columns of the next activations.
                 // The TMEM loads of chunk c+1 are in flight during the arithmetic of chunk c.
                 float vn[CW], wn[CW];
-                tmem_load<CW>(umma::taddr(tb, lane_base, 256 + half * CW), vn);     // main products
-                tmem_load<CW>(umma::taddr(tb, lane_base, 384 + half * CW), wn);     // cross products
+                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + half * CW), vn);     // main products
+                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + half * CW), wn);    // cross products (scale 2^11)
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = c * 32 + half * CW;
-                    float v[CW], ahi[CW], alo[CW];
+                    float v[CW];
+                    uint32_t ahi[CW / 2], alo[CW / 2];
                     umma::wait_ld();
                     {
                         const float4* bv = reinterpret_cast<const float4*>(bh + n0);
 #pragma unroll
                         for (int g4 = 0; g4 < CW / 4; ++g4) {
                             const float4 t = bv[g4];
-                            v[g4 * 4 + 0] = (vn[g4 * 4 + 0] + wn[g4 * 4 + 0]) + t.x;
-                            v[g4 * 4 + 1] = (vn[g4 * 4 + 1] + wn[g4 * 4 + 1]) + t.y;
-                            v[g4 * 4 + 2] = (vn[g4 * 4 + 2] + wn[g4 * 4 + 2]) + t.z;
-                            v[g4 * 4 + 3] = (vn[g4 * 4 + 3] + wn[g4 * 4 + 3]) + t.w;
+                            v[g4 * 4 + 0] = fmaf(wn[g4 * 4 + 0], umma::kF16LoUnscale, vn[g4 * 4 + 0]) + t.x;
+                            v[g4 * 4 + 1] = fmaf(wn[g4 * 4 + 1], umma::kF16LoUnscale, vn[g4 * 4 + 1]) + t.y;
+                            v[g4 * 4 + 2] = fmaf(wn[g4 * 4 + 2], umma::kF16LoUnscale, vn[g4 * 4 + 2]) + t.z;
+                            v[g4 * 4 + 3] = fmaf(wn[g4 * 4 + 3], umma::kF16LoUnscale, vn[g4 * 4 + 3]) + t.w;
                         }
                     }
                     if (c < 3) {
-                        tmem_load<CW>(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
-                        tmem_load<CW>(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + n0 + 32), vn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
                     }
                     activation_compute<CW>(v, ahi, alo);
                     activation_store<CW>(tb, lane_base, n0, ahi, alo);
@@ -946,8 +921,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 p_fd ^= 1u;
                 umma::fence_after_sync();
                 ZF_TR(trs);   // theta ready
-                const uint32_t dbase = umma::taddr(tb, lane_base, 256);
-                const uint32_t cross = (K == 16) ? 128u : 0u;
+                const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(0));
+                const uint32_t cross = TC_XOFF;
                 float* px = xs + pmod(0 - rot, D) * UM + m;
                 const float v = *px;
                 float* ex = cx.pairx;   // [7][UM]: idx, ks, bs | ko, bo, dk, dkp1
@@ -977,7 +952,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 p_fd ^= 1u;
                 umma::fence_after_sync();
                 ZF_TR(trs);   // theta ready
-                const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * (K == 16 ? 64 : 128));
+                const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(half));
                 float* px = xs + pmod(jj - rot, D) * UM + m;
                 const float v = *px;
                 RqsBin bin;
@@ -986,8 +961,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
                     ZF_TR(trs);   // released
                 };
-                if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls + jj * NL, v, bin, release);
-                else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
+                if (K == 16) spline_row_tmem<16, INVERSE>(dbase, TC_XOFF, bls + jj * NL, v, bin, release);
+                else spline_row_tmem<32, INVERSE>(dbase, TC_XOFF, bls + jj * NL, v, bin, release);
                 if (m < nm) put_idx(a, s, m0 + m, jj, bin.idx);
                 if (!INVERSE) {
                     float y, ld;
@@ -1034,12 +1009,10 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// NG = 2: 8 epilogue warps + producer + MMA issuer (320 threads).
-// NG = 4: 16 epilogue warps (two spline-capable groups, two helper groups) + a fifth warpgroup holding the
-//         producer and the MMA issuer (640 threads); the register file is re-divided with setmaxnreg: the spline
-//         groups grow, the helpers and the fifth warpgroup shrink.
-template <bool INVERSE, int NG>
-__global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(const __grid_constant__ ChainArgs a) {
+// 8 epilogue warps (two column groups) + producer + MMA issuer (320 threads).
+template <bool INVERSE>
+__global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constant__ ChainArgs a) {
+    constexpr int NG = 2;
     extern __shared__ __align__(128) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int ET = NG * 128, PW = NG * 4, MW = NG * 4 + 1;   // epilogue threads, producer warp, MMA warp
@@ -1136,12 +1109,12 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
                     for (int u = 0; u < (L - 1) + s.d; ++u) {
                         const bool hid = u < L - 1;
                         const int N = hid ? 128 : NL;
-                        const float* base = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L] + (size_t)(u - (L - 1)) * NL * 256;
-                        const uint32_t bytes = (uint32_t)N * 256u;
+                        const float* base = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L] + (size_t)(u - (L - 1)) * NL * 128;
+                        const uint32_t bytes = (uint32_t)N * 128u;   // one K-chunk (32): fp16 hi | lo images
                         for (int c = 0; c < 4; ++c) {
                             mbar_wait(&bars[B_EMPTY + stage], phase ^ 1u);
                             mbar_arrive_expect_tx(&bars[B_FULL + stage], bytes);
-                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, base + (size_t)c * N * 64, bytes,
+                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, base + (size_t)c * N * 32, bytes,
                                           &bars[B_FULL + stage]);
                             if (++stage == URING) { stage = 0; phase ^= 1u; }
                         }
@@ -1159,11 +1132,11 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
     };
     auto mma_role = [&]() {
         // ------------------------------------------------------------------ MMA issuer
-        // The tensor core's fp32 accumulator truncates at every accumulate step (measured: -2.3e-8 relative
-        // per step, tests/test_gpu_umma.py), so the two small cross products (2^-11 of the main one) go to
-        // their own accumulator wherever tensor memory has room: hidden layers main -> D0, cross -> D1;
-        // last-layer dims with NL <= 64 (K = 16) main -> D0[64b, 64b+NL), cross -> D1[64b, 64b+NL) (b = dim & 1);
-        // wider ones (K = 32) have no room for a cross accumulator and use D0 / D1 whole.
+        // Main and cross products go to separate accumulators (the cross products carry the 2^11 scale of the lo'
+        // parts; the tensor core's fp32 accumulator also truncates at every accumulate step - measured -2.3e-8
+        // relative per step, tests/test_gpu_umma.py - which the small cross terms would otherwise suffer at the
+        // main product's magnitude): hidden layers main [128,256), cross [256,384); last-layer dim in buffer
+        // b = dim & 1: main [128 + 192 b, +NL), cross 96 columns further.
         // The epilogue publishes a new activation version one 32-column K-chunk at a time (B_AREADY + c), and the
         // MMAs of chunk c are issued as soon as it has arrived, so the layer's GEMM runs underneath the
         // bias/swish/split of the chunks behind it.  The arrival of chunk c also says that accumulator columns
@@ -1183,10 +1156,10 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
                     const int b = hid ? 0 : ((u - (L - 1)) & 1);
                     ZF_TR(2);
                     const bool newver = hid || u == L - 1;   // this unit reads a new version of the activations
-                    const bool split_acc = hid || NL <= 64;
                     // chunks that must have arrived before the first MMA: those whose accumulator columns this unit
-                    // overwrites (u == 0 follows the SIMT first layer: nothing to drain)
-                    const int nfree = (u == 0) ? 0 : (hid ? 4 : (split_acc ? 2 : 3));
+                    // overwrites (u == 0 follows the SIMT first layer: nothing to drain); the last-layer buffers overlap
+                    // all of the hidden accumulators
+                    const int nfree = (u == 0) ? 0 : 4;
                     int waited = 0;
 #ifdef ZF_TRACE
                     long long w_pend = clock64(), w_full = 0, w_a = 0;
@@ -1197,8 +1170,8 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
 #ifdef ZF_TRACE
                     w_pend = clock64() - w_pend;
 #endif
-                    const uint32_t dmain = hid ? tb + 256u : (split_acc ? tb + 256u + (uint32_t)b * 64u : tb + 256u + (uint32_t)b * 128u);
-                    const uint32_t dcross = split_acc ? dmain + 128u : dmain;
+                    const uint32_t dmain = hid ? tb + TC_HMAIN : tb + tc_dmain(b);
+                    const uint32_t dcross = hid ? tb + TC_HCROSS : dmain + TC_XOFF;
                     // One unit = 4 K-chunks = one lap of the 4-stage ring, so chunk c always sits in stage c and every
                     // descriptor is (a hoisted ring address) + (a compile-time offset): the issuing thread's
                     // per-MMA work is what bounds the small-N units, keep it to a couple of instructions.
@@ -1206,7 +1179,7 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
                     auto issue_unit = [&](auto ntag) {
                         constexpr int N = decltype(ntag)::value;
                         constexpr uint32_t lbo = (uint32_t)(N >> 3) * 128u;
-                        constexpr uint32_t idesc = umma::instr_desc_tf32(N);
+                        constexpr uint32_t idesc = umma::instr_desc_f16(N);
                         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO, descriptor version
                         const uint32_t ring16 = (smem_u32(ring) >> 4) | ((lbo >> 4) << 16);
 #pragma unroll
@@ -1232,16 +1205,16 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
                             umma::fence_after_sync();
                             if (umma::elect_one()) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
+                                for (int ks = 0; ks < 2; ++ks) {   // K = 16 per kind::f16 instruction
                                     const uint32_t off_hi = (uint32_t)(c * URING_FLOATS * 4 + ks * 2 * (int)lbo) >> 4;
-                                    const uint32_t off_lo = off_hi + ((uint32_t)N * 128u >> 4);   // lo image follows the hi image
+                                    const uint32_t off_lo = off_hi + ((uint32_t)N * 64u >> 4);   // lo image follows the hi image
                                     const uint64_t dhi = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_hi);
                                     const uint64_t dlo = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_lo);
-                                    const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                                    const uint32_t acol = (uint32_t)(c * 16 + ks * 8);   // fp16 pairs: 8 columns per k-step
                                     const bool first = (c | ks) == 0;
-                                    umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, !first);          // A_lo * B_hi
-                                    umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);                   // A_hi * B_lo
-                                    umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, split_acc ? !first : true);  // A_hi * B_hi
+                                    umma::mma_f16_ts(dcross, tb + TC_ALO + acol, dhi, idesc, !first);   // A_lo' * B_hi
+                                    umma::mma_f16_ts(dcross, tb + acol, dlo, idesc, true);              // A_hi * B_lo'
+                                    umma::mma_f16_ts(dmain, tb + acol, dhi, idesc, !first);             // A_hi * B_hi
                                 }
                                 umma::commit(&bars[B_EMPTY + c]);
                                 if (c == 3) umma::commit(&bars[hid ? B_DFULL_H : (B_DFULL_D + b)]);
@@ -1262,29 +1235,10 @@ __global__ void __launch_bounds__(NG == 2 ? 320 : 640, 1) chain_umma_kernel(cons
         }
     };
     // ------------------------------------------------------------------ role dispatch
-    // Each setmaxnreg dominates exactly the code of its warpgroup (no join before the role ends), which is what lets
-    // ptxas give every role its own register budget: groups 0,1 | groups 2,3 | producer + MMA issuer + two idle warps.
-    // setmaxnreg moves registers inside the pool the CTA was launched with (640 threads x 96 registers; the rest of
-    // the register file is not reachable), so the three allocations must add up to it or the increase never succeeds.
-    static_assert(256 * 144 + 256 * 56 + 128 * 80 == 640 * 96, "setmaxnreg split must equal the launch allocation");
     const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, bars, steps, tb, n_tiles, cl, in16, in_bytes};
-    if constexpr (NG == 4) {
-        if (warp < 8) {
-            reg_inc<144>();
-            umma_epilogue_role<INVERSE, NG, false>(cx);
-        } else if (warp < 16) {
-            reg_dec<56>();
-            umma_epilogue_role<INVERSE, NG, true>(cx);
-        } else {
-            reg_dec<80>();
-            if (warp == PW) producer_role();
-            else if (warp == MW) mma_role();
-        }
-    } else {
-        if (warp == PW) producer_role();
-        else if (warp == MW) mma_role();
-        else umma_epilogue_role<INVERSE, NG, false>(cx);
-    }
+    if (warp == PW) producer_role();
+    else if (warp == MW) mma_role();
+    else umma_epilogue_role<INVERSE>(cx);
 
     umma::fence_before_sync();
     __syncthreads();
@@ -1434,11 +1388,11 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         const bool hid = u < L - 1;
                         const int N = hid ? 128 : NL;
                         const float* base = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L];
-                        const uint32_t bytes = (uint32_t)N * 256u;
+                        const uint32_t bytes = (uint32_t)N * 128u;
                         for (int c = 0; c < 4; ++c) {
                             mbar_wait(&bars[PP_EMPTY + stage], phase ^ 1u);
                             mbar_arrive_expect_tx(&bars[PP_FULL + stage], bytes);
-                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, base + (size_t)c * N * 64, bytes, &bars[PP_FULL + stage]);
+                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, base + (size_t)c * N * 32, bytes, &bars[PP_FULL + stage]);
                             if (++stage == URING) { stage = 0; phase ^= 1u; }
                         }
                         if (u == 0) {
@@ -1464,18 +1418,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                 for (int slot = 0; slot < nslots; ++slot) {
                     for (int u = 0; u < L; ++u) {
                         const bool hid = u < L - 1;
-                        const bool split_acc = hid || NL <= 64;
-                        const int nfree = (u == 0) ? 0 : (hid ? 4 : (split_acc ? 2 : 3));
+                        const int nfree = (u == 0) ? 0 : 4;
                         int waited = 0;
                         if (theta_pending) { mbar_wait(&bars[PP_DEMPTY_D], p_ed); p_ed ^= 1u; theta_pending = false; }
                         umma::fence_after_sync();
-                        const uint32_t dmain = tb + 256u;
-                        const uint32_t dcross = split_acc ? dmain + 128u : dmain;
+                        const uint32_t dmain = hid ? tb + TC_HMAIN : tb + tc_dmain(0);
+                        const uint32_t dcross = hid ? tb + TC_HCROSS : dmain + TC_XOFF;
                         static_assert(URING == 4, "the MMA issuer maps chunk c to ring stage c");
                         auto issue_unit = [&](auto ntag) {
                             constexpr int N = decltype(ntag)::value;
                             constexpr uint32_t lbo = (uint32_t)(N >> 3) * 128u;
-                            constexpr uint32_t idesc = umma::instr_desc_tf32(N);
+                            constexpr uint32_t idesc = umma::instr_desc_f16(N);
                             constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
                             const uint32_t ring16 = (smem_u32(ring) >> 4) | ((lbo >> 4) << 16);
 #pragma unroll
@@ -1489,16 +1442,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                                 umma::fence_after_sync();
                                 if (umma::elect_one()) {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) {
+                                    for (int ks = 0; ks < 2; ++ks) {
                                         const uint32_t off_hi = (uint32_t)(c * URING_FLOATS * 4 + ks * 2 * (int)lbo) >> 4;
-                                        const uint32_t off_lo = off_hi + ((uint32_t)N * 128u >> 4);
+                                        const uint32_t off_lo = off_hi + ((uint32_t)N * 64u >> 4);
                                         const uint64_t dhi = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_hi);
                                         const uint64_t dlo = ((uint64_t)desc_hi << 32) | (uint64_t)(ring16 + off_lo);
-                                        const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
+                                        const uint32_t acol = (uint32_t)(c * 16 + ks * 8);
                                         const bool first = (c | ks) == 0;
-                                        umma::mma_tf32_ts(dcross, tb + 128u + acol, dhi, idesc, !first);
-                                        umma::mma_tf32_ts(dcross, tb + acol, dlo, idesc, true);
-                                        umma::mma_tf32_ts(dmain, tb + acol, dhi, idesc, split_acc ? !first : true);
+                                        umma::mma_f16_ts(dcross, tb + TC_ALO + acol, dhi, idesc, !first);
+                                        umma::mma_f16_ts(dcross, tb + acol, dlo, idesc, true);
+                                        umma::mma_f16_ts(dmain, tb + acol, dhi, idesc, !first);
                                     }
                                     umma::commit(&bars[PP_EMPTY + c]);
                                     if (c == 3) umma::commit(&bars[hid ? PP_DFULL_H : PP_DFULL_D]);
@@ -1568,7 +1521,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
                         const int n0 = c * 32 + half * CW;
-                        float acc[CW], ahi[CW], alo[CW];
+                        float acc[CW];
+                        uint32_t ahi[CW / 2], alo[CW / 2];
                         {
                             const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
 #pragma unroll
@@ -1620,27 +1574,28 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         umma::fence_after_sync();
                         const float* bh = bhs + (l - 1) * 128;
                         float vn[CW], wn[CW];
-                        tmem_load<CW>(umma::taddr(tb, lane_base, 256 + half * CW), vn);
-                        tmem_load<CW>(umma::taddr(tb, lane_base, 384 + half * CW), wn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + half * CW), vn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + half * CW), wn);
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = c * 32 + half * CW;
-                            float v[CW], ahi[CW], alo[CW];
+                            float v[CW];
+                            uint32_t ahi[CW / 2], alo[CW / 2];
                             umma::wait_ld();
                             {
                                 const float4* bv = reinterpret_cast<const float4*>(bh + n0);
 #pragma unroll
                                 for (int g4 = 0; g4 < CW / 4; ++g4) {
                                     const float4 t = bv[g4];
-                                    v[g4 * 4 + 0] = (vn[g4 * 4 + 0] + wn[g4 * 4 + 0]) + t.x;
-                                    v[g4 * 4 + 1] = (vn[g4 * 4 + 1] + wn[g4 * 4 + 1]) + t.y;
-                                    v[g4 * 4 + 2] = (vn[g4 * 4 + 2] + wn[g4 * 4 + 2]) + t.z;
-                                    v[g4 * 4 + 3] = (vn[g4 * 4 + 3] + wn[g4 * 4 + 3]) + t.w;
+                                    v[g4 * 4 + 0] = fmaf(wn[g4 * 4 + 0], umma::kF16LoUnscale, vn[g4 * 4 + 0]) + t.x;
+                                    v[g4 * 4 + 1] = fmaf(wn[g4 * 4 + 1], umma::kF16LoUnscale, vn[g4 * 4 + 1]) + t.y;
+                                    v[g4 * 4 + 2] = fmaf(wn[g4 * 4 + 2], umma::kF16LoUnscale, vn[g4 * 4 + 2]) + t.z;
+                                    v[g4 * 4 + 3] = fmaf(wn[g4 * 4 + 3], umma::kF16LoUnscale, vn[g4 * 4 + 3]) + t.w;
                                 }
                             }
                             if (c < 3) {
-                                tmem_load<CW>(umma::taddr(tb, lane_base, 256 + n0 + 32), vn);
-                                tmem_load<CW>(umma::taddr(tb, lane_base, 384 + n0 + 32), wn);
+                                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + n0 + 32), vn);
+                                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
                             }
                             activation_compute<CW>(v, ahi, alo);
                             activation_store<CW>(tb, lane_base, n0, ahi, alo);
@@ -1736,7 +1691,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         mbar_wait(&bars[PP_DFULL_D], p_fd);
                         p_fd ^= 1u;
                         umma::fence_after_sync();
-                        const uint32_t dbase = umma::taddr(tb, lane_base, 256);
+                        const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(0));
                         float* px = xs + pmod(0 - rot, D) * UM + m;
                         const float v = *px;
                         RqsBin bin;
@@ -1744,8 +1699,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                             umma::fence_before_sync();
                             umma::mbar_arrive(&bars[PP_DEMPTY_D]);
                         };
-                        if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 128u, bls, v, bin, release);
-                        else spline_row_tmem<32, INVERSE>(dbase, 0u, bls, v, bin, release);
+                        if (K == 16) spline_row_tmem<16, INVERSE>(dbase, TC_XOFF, bls, v, bin, release);
+                        else spline_row_tmem<32, INVERSE>(dbase, TC_XOFF, bls, v, bin, release);
                         if (m < nm) put_idx(a, s, m0 + m, 0, bin.idx);
                         umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // last read of this occurrence's constants by S2
                         if (!INVERSE) {
@@ -1808,313 +1763,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
     __syncthreads();
     if (warp == MW) umma::tmem_dealloc(tb, 512);
 }
-
-#ifdef ZF_EXPERIMENTAL   // measured-slower negative results: kept out of the product library
-// =============================================================================================
-// Two-pipeline variant: tensor memory is full with one tile's operands and accumulators, so a second
-// 128-event tile cannot be in flight and the MMA and epilogue phases of a tile serialise.  Here a CTA
-// runs TWO independent pipelines ("contexts") over 64-event half-tiles that share the same TMEM columns
-// on disjoint lanes (context 0: lanes 0-63, context 1: lanes 64-127).  Every MMA is issued for all 128
-// lanes with the other context's lanes masked out of the write (tcgen05.mma disable-output-lane), so
-// the contexts never touch each other's rows; while one waits for its MMAs the other runs its epilogue.
-// Per context: 4 epilogue warps (lane quarters 2c, 2c+1 x 2 column halves), 1 producer warp with its own
-// 2-stage weight ring, 1 MMA warp, its own barriers and tile-state buffers.  384 threads.
-// =============================================================================================
-constexpr int U2M = 64;           // events per half-tile
-constexpr int U2THREADS = 384;
-constexpr int U2RING = 2;
-enum U2Bar : int { C_FULL = 0, C_EMPTY = 2, C_AREADY = 4, C_DFULL_H = 5, C_DFULL_D = 6, C_DEMPTY_H = 8, C_DEMPTY_D = 9, C_COUNT = 12 };
-
-struct U2Layout {   // per-context shared-memory carve-up in floats (host and device agree through this)
-    int xs, cs, hs, w0, b0, bn, bh, bl, ldx, ring, bars, total;
-};
-__host__ __device__ inline U2Layout u2_layout(int D, int C, int Fmax, int Hmax, int BLmax) {
-    U2Layout l;
-    int o = 0;
-    auto take = [&](int n) { int r = o; o += (n + 31) / 32 * 32; return r; };
-    l.xs = take(D * U2M); l.cs = take(C * U2M); l.hs = take(Fmax * U2M); l.w0 = take(Fmax * 128); l.b0 = take(128);
-    l.bn = take(96); l.bh = take(Hmax * 128); l.bl = take(BLmax); l.ldx = take(U2M);
-    l.ring = take(U2RING * URING_FLOATS); l.bars = take(2 * C_COUNT);
-    l.total = o;
-    return l;
-}
-
-template <bool INVERSE>
-__global__ void __launch_bounds__(U2THREADS, 1) chain_umma2_kernel(const __grid_constant__ ChainArgs a, int Fmax, int Hmax, int BLmax) {
-    extern __shared__ __align__(128) float smem[];
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = a.D, C = a.C;
-    const U2Layout L2 = u2_layout(D, C, Fmax, Hmax, BLmax);
-    // role and context of this warp
-    const int ctx = (warp < 8) ? ((warp & 3) >> 1) : ((warp - 8) & 1);
-    float* base = smem + (size_t)ctx * L2.total;
-    float* xs = base + L2.xs;
-    float* cs = base + L2.cs;
-    float* hs = base + L2.hs;
-    float* w0s = base + L2.w0;
-    float* b0s = base + L2.b0;
-    float* bns = base + L2.bn;
-    float* bhs = base + L2.bh;
-    float* bls = base + L2.bl;
-    float* ldx = base + L2.ldx;
-    float* ring = base + L2.ring;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + L2.bars);
-    const StepDesc* steps = reinterpret_cast<const StepDesc*>(a.ws);
-    const float* wsf = a.ws;
-
-    if (tid < 2) {  // one thread per context initialises that context's barriers
-        uint64_t* b = reinterpret_cast<uint64_t*>(smem + (size_t)tid * L2.total + L2.bars);
-        for (int i = 0; i < U2RING; ++i) { mbar_init(&b[C_FULL + i], 1); mbar_init(&b[C_EMPTY + i], 1); }
-        mbar_init(&b[C_AREADY], 128);
-        mbar_init(&b[C_DFULL_H], 1);
-        mbar_init(&b[C_DFULL_D + 0], 1);
-        mbar_init(&b[C_DFULL_D + 1], 1);
-        mbar_init(&b[C_DEMPTY_H], 128);
-        mbar_init(&b[C_DEMPTY_D + 0], 64);
-        mbar_init(&b[C_DEMPTY_D + 1], 64);
-        mbar_fence_init();
-    }
-    if (warp == 10) umma::tmem_alloc(&tmem_slot, 512);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tb = tmem_slot;
-    const long long n_tiles = (a.M + U2M - 1) / U2M;
-    const long long tile0 = 2ll * blockIdx.x + ctx, tstride = 2ll * gridDim.x;
-
-    if (warp == 8 || warp == 9) {
-        // ------------------------------------------------------------------ weight producer of this context
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (long long tile = tile0; tile < n_tiles; tile += tstride) {
-                for (int si = 0; si < a.n_steps; ++si) {
-                    const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
-                    if (s.kind != kStepKindCoupling) continue;
-                    const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
-                    for (int u = 0; u < (L - 1) + s.d; ++u) {
-                        const bool hid = u < L - 1;
-                        const int N = hid ? 128 : NL;
-                        const float* src = hid ? wsf + s.off_U[u + 1] : wsf + s.off_U[L] + (size_t)(u - (L - 1)) * NL * 256;
-                        const uint32_t bytes = (uint32_t)N * 256u;
-                        for (int c = 0; c < 4; ++c) {
-                            mbar_wait(&bars[C_EMPTY + stage], phase ^ 1u);
-                            mbar_arrive_expect_tx(&bars[C_FULL + stage], bytes);
-                            bulk_copy_g2s(ring + (size_t)stage * URING_FLOATS, src + (size_t)c * N * 64, bytes,
-                                          &bars[C_FULL + stage]);
-                            if (++stage == U2RING) { stage = 0; phase ^= 1u; }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp >= 10) {
-        // ------------------------------------------------------------------ MMA issuer of this context
-        const uint32_t mlo = ctx ? 0xffffffffu : 0u, mhi = ctx ? 0u : 0xffffffffu;  // lanes NOT written
-        uint32_t stage = 0, phase = 0, p_ar = 0, p_eh = 0, p_ed0 = 0, p_ed1 = 0;
-        bool hid_pending = false, dim_pending0 = false, dim_pending1 = false;
-        for (long long tile = tile0; tile < n_tiles; tile += tstride) {
-            for (int si = 0; si < a.n_steps; ++si) {
-                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
-                if (s.kind != kStepKindCoupling) continue;
-                const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
-                for (int u = 0; u < (L - 1) + s.d; ++u) {
-                    const bool hid = u < L - 1;
-                    const int N = hid ? 128 : NL;
-                    const int b = hid ? 0 : ((u - (L - 1)) & 1);
-                    if (hid || u == L - 1) { mbar_wait(&bars[C_AREADY], p_ar); p_ar ^= 1u; }
-                    if (hid_pending) { mbar_wait(&bars[C_DEMPTY_H], p_eh); p_eh ^= 1u; hid_pending = false; }
-                    if ((hid || b == 0) && dim_pending0) { mbar_wait(&bars[C_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; dim_pending0 = false; }
-                    if ((hid || b == 1) && dim_pending1) { mbar_wait(&bars[C_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; dim_pending1 = false; }
-                    umma::fence_after_sync();
-                    const uint32_t dmain = tb + 256u + (uint32_t)b * 128u;
-                    const bool split_acc = hid || (2 * NL <= 128);
-                    const uint32_t dcross = hid ? (tb + 384u) : (split_acc ? dmain + (uint32_t)NL : dmain);
-                    const uint32_t idesc = umma::instr_desc_tf32(N);
-                    const uint32_t lbo = (uint32_t)(N >> 3) * 128u;
-                    for (int c = 0; c < 4; ++c) {
-                        mbar_wait(&bars[C_FULL + stage], phase);
-                        umma::fence_after_sync();
-                        if (umma::elect_one()) {
-                            const uint32_t bhi = smem_u32(ring + (size_t)stage * URING_FLOATS);
-                            const uint32_t blo = bhi + (uint32_t)N * 128u;
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t dhi = umma::smem_desc_kmajor(bhi + ks * 2 * lbo, lbo, 128u);
-                                const uint64_t dlo = umma::smem_desc_kmajor(blo + ks * 2 * lbo, lbo, 128u);
-                                const uint32_t acol = (uint32_t)(c * 32 + ks * 8);
-                                const bool first = (c | ks) == 0;
-                                umma::mma_tf32_ts_masked(dcross, tb + 128u + acol, dhi, idesc, !first, mlo, mlo, mhi, mhi);
-                                umma::mma_tf32_ts_masked(dcross, tb + acol, dlo, idesc, true, mlo, mlo, mhi, mhi);
-                                umma::mma_tf32_ts_masked(dmain, tb + acol, dhi, idesc, split_acc ? !first : true, mlo, mlo, mhi, mhi);
-                            }
-                            umma::commit(&bars[C_EMPTY + stage]);
-                            if (c == 3) umma::commit(&bars[hid ? C_DFULL_H : (C_DFULL_D + b)]);
-                        }
-                        __syncwarp();
-                        if (++stage == U2RING) { stage = 0; phase ^= 1u; }
-                    }
-                    if (hid) hid_pending = true;
-                    else if (b) dim_pending1 = true;
-                    else dim_pending0 = true;
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue / SIMT warps of this context
-        const int q = warp & 3, half = warp >> 2;
-        const int m = (q & 1) * 32 + lane;                 // event within the half-tile
-        const int etid = half * 64 + m;                    // 0..127 within the context
-        const uint32_t lane_base = (uint32_t)(q * 32);     // TMEM lane quarter of this warp
-        auto ctx_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + ctx) : "memory"); };
-        uint32_t p_fh = 0, p_fd = 0;
-        for (long long tile = tile0; tile < n_tiles; tile += tstride) {
-            const long long m0 = tile * U2M;
-            const int nm = (int)min((long long)U2M, a.M - m0);
-            const int rot_in = INVERSE ? a.rot_total : 0;
-            for (int e = etid; e < U2M * D; e += 128) {
-                const int mm = e / D, j = e - mm * D;
-                xs[pmod(j - rot_in, D) * U2M + mm] =
-                    (mm < nm) ? (a.sample ? latent_draw(a.lc.kind, a.peakness, a.seed, m0 + mm, j) : a.x[m0 * D + e]) : 0.5f;
-            }
-            for (int e = etid; e < U2M * C; e += 128) {
-                const int mm = e / C, j = e - mm * C;
-                cs[j * U2M + mm] = (mm < nm) ? a.c[m0 * C + e] : 0.f;
-            }
-            ctx_barrier();
-
-            float ld_acc = 0.f;
-            for (int si = 0; si < a.n_steps; ++si) {
-                const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
-                if (s.kind == kStepKindShiftBounds) {
-                    if (half == 0) shift_bounds_row<INVERSE>(s, wsf, D, xs, U2M, m, ld_acc);
-                    ctx_barrier();
-                    continue;
-                }
-                const int d = s.d, F = s.F, F_p = ru(F, KC), L = s.n_hidden, rot = s.rot;
-                const int K = s.K, P = 3 * K - 1, NL = ru(P, 16), Pp4 = ru(P, 4);
-                for (int i = etid; i < 3 * F_p; i += 128) bns[i] = wsf[s.off_bn + i];
-                for (int i = etid; i < F * 128; i += 128) w0s[i] = wsf[s.off_W[0] + i];
-                b0s[etid] = wsf[s.off_b[0] + etid];
-                for (int i = etid; i < (L - 1) * 128; i += 128) bhs[i] = wsf[s.off_b[1 + (i >> 7)] + (i & 127)];
-                for (int i = etid; i < d * NL; i += 128) {
-                    const int jj = i / NL, pp = i - jj * NL;
-                    bls[i] = pp < Pp4 ? wsf[s.off_b[L] + jj * Pp4 + pp] : 0.f;
-                }
-                ctx_barrier();
-                for (int f = half; f < F; f += 2) {
-                    const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * U2M + m] : cs[(f - (D - d)) * U2M + m];
-                    hs[f * U2M + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
-                }
-                ctx_barrier();
-#pragma unroll 1
-                for (int nb = 0; nb < 4; ++nb) {
-                    const int n0 = half * 64 + nb * 16;
-                    float acc[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[i] = b0s[n0 + i];
-                    for (int f = 0; f < F; ++f) {
-                        const float h = hs[f * U2M + m];
-                        const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; ++g4) {
-                            const float4 wv = w[g4];
-                            acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
-                            acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
-                            acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
-                            acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
-                        }
-                    }
-                    store_activation16(tb, lane_base, n0, acc);
-                }
-                umma::wait_st();
-                umma::fence_before_sync();
-                umma::mbar_arrive(&bars[C_AREADY]);
-                for (int l = 1; l < L; ++l) {
-                    mbar_wait(&bars[C_DFULL_H], p_fh);
-                    p_fh ^= 1u;
-                    umma::fence_after_sync();
-                    const float* bh = bhs + (l - 1) * 128;
-#pragma unroll 1
-                    for (int nb = 0; nb < 2; ++nb) {
-                        const int n0 = half * 64 + nb * 32;
-                        float v[32], w[32];
-                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0), v);
-                        umma::ld16(umma::taddr(tb, lane_base, 256 + n0 + 16), v + 16);
-                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0), w);
-                        umma::ld16(umma::taddr(tb, lane_base, 384 + n0 + 16), w + 16);
-                        umma::wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = (v[i] + w[i]) + bh[n0 + i];
-                        float lo16[16], hi16[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { lo16[i] = v[i]; hi16[i] = v[16 + i]; }
-                        store_activation16(tb, lane_base, n0, lo16);
-                        store_activation16(tb, lane_base, n0 + 16, hi16);
-                    }
-                    umma::wait_st();
-                    umma::fence_before_sync();
-                    umma::mbar_arrive(&bars[C_AREADY]);
-                    umma::mbar_arrive(&bars[C_DEMPTY_H]);
-                }
-                float ldc = 0.f;
-                for (int jj = half; jj < d; jj += 2) {
-                    mbar_wait(&bars[C_DFULL_D + half], p_fd);
-                    p_fd ^= 1u;
-                    umma::fence_after_sync();
-                    const uint32_t dbase = umma::taddr(tb, lane_base, 256 + half * 128);
-                    float* px = xs + pmod(jj - rot, D) * U2M + m;
-                    const float v = *px;
-                    RqsBin bin;
-                    auto release = [&]() {
-                        umma::fence_before_sync();
-                        umma::mbar_arrive(&bars[C_DEMPTY_D + half]);
-                    };
-                    if (K == 16) spline_row_tmem<16, INVERSE>(dbase, 48u, bls + jj * NL, v, bin, release);
-                    else spline_row_tmem<32, INVERSE>(dbase, 0u, bls + jj * NL, v, bin, release);
-                    if (!INVERSE) {
-                        float y, ld;
-                        rqs_eval_forward(v, bin, y, ld);
-                        *px = y;
-                        ldc += ld;
-                    } else {
-                        *px = rqs_eval_inverse(v, bin);
-                    }
-                }
-                if (half == 1) ldx[m] = ldc;
-                ctx_barrier();
-                if (half == 0) ld_acc += ldc + ldx[m];
-                ctx_barrier();
-            }
-
-            if (a.mode == kModeLogProb) {
-                if (half == 0 && m < nm) {
-                    float lat = 0.f;
-                    for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * U2M + m], a.lc);
-                    a.lp[m0 + m] = nan_to_num_lp(lat + ld_acc);
-                }
-            } else {
-                const int rot_out = INVERSE ? 0 : a.rot_total;
-                if (a.y) {
-                    for (int e = etid; e < nm * D; e += 128) {
-                        const int mm = e / D, j = e - mm * D;
-                        a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * U2M + mm];
-                    }
-                }
-                if (!INVERSE && a.log_det && half == 0 && m < nm)
-                    a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
-            }
-            ctx_barrier();
-        }
-    }
-
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 10) umma::tmem_dealloc(tb, 512);
-}
-
-#endif  // ZF_EXPERIMENTAL
 
 // ---- host side ------------------------------------------------------------------------
 
@@ -2238,8 +1886,8 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
             if (s.umma_ok) {
                 const int NL = ru(3 * s.K - 1, 16);
                 off = (off + 31) / 32 * 32;  // images are fetched by 16-byte-aligned bulk copies
-                for (int l = 1; l < L; ++l) s.off_U[l] = take((size_t)128 * 256);
-                s.off_U[L] = take((size_t)s.d * NL * 256);
+                for (int l = 1; l < L; ++l) s.off_U[l] = take((size_t)128 * 128);
+                s.off_U[L] = take((size_t)s.d * NL * 128);
                 job.cst = ucst_layout(plan.Fmax, plan.Hmax, plan.BLmax);
                 s.off_C = take((size_t)job.cst.total);
             }
@@ -2262,7 +1910,7 @@ static LatentConst make_latent(int kind, float peakness) {
 
 enum PackMode : int { kPackAndRun = 0, kPackOnly = 1, kRunPacked = 2 };
 
-// Developer switches: which chain kernel (simt | umma | umma8 [| umma2 | umma16 in ZF_EXPERIMENTAL builds]) and which
+// Developer switches: which chain kernel (simt | umma | umma8) and which
 // train GEMM (simt | umma) run.  The environment (ZF_CHAIN_IMPL, ZF_GEMM_IMPL) is read ONCE per process;
 // zf_debug_set_impl overrides it afterwards (the parity tests compare the implementations inside one process).
 struct ImplSwitch {
@@ -2361,28 +2009,6 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
     const bool want_umma = plan.umma_ok && plan.n_couplings > 0 && !(impl && impl[0] == 's');
     if (impl && strcmp(impl, "umma") == 0 && !want_umma)
         return fail(ZF_ERR_UNSUPPORTED, "ZF_CHAIN_IMPL=umma but this chain does not fit the tensor-core kernel");
-#ifdef ZF_EXPERIMENTAL
-    // ZF_CHAIN_IMPL=umma2 opts into the two-pipeline variant (measured slower on B200: 602M vs 692M events/s on
-    // two_moons_conditional, 61M vs 80M on the 16-D config - each MMA computes 128 lanes for 64 useful ones)
-    if (want_umma && impl && strcmp(impl, "umma2") == 0) {
-        const U2Layout lay = u2_layout(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax);
-        const size_t smem2 = (size_t)2 * lay.total * sizeof(float);
-        if (smem2 + 256 <= (size_t)di.max_smem_optin) {
-            const long long tiles = (M + U2M - 1) / U2M;
-            const unsigned g2 = (unsigned)std::min<long long>((tiles + 1) / 2, (long long)di.sm_count);
-            if (mode == kModeInverse) {
-                if (int rc = set_smem((const void*)chain_umma2_kernel<true>, smem2)) return rc;
-                chain_umma2_kernel<true><<<g2, U2THREADS, smem2, stream>>>(a, plan.Fmax, plan.Hmax, plan.BLmax);
-            } else {
-                if (int rc = set_smem((const void*)chain_umma2_kernel<false>, smem2)) return rc;
-                chain_umma2_kernel<false><<<g2, U2THREADS, smem2, stream>>>(a, plan.Fmax, plan.Hmax, plan.BLmax);
-            }
-            count_launch();
-            ZF_CUDA_CHECK(cudaGetLastError());
-            return ZF_OK;
-        }
-    }
-#endif
     if (want_umma) {
         a.u_fmax = plan.Fmax;
         a.u_hmax = plan.Hmax;
@@ -2393,7 +2019,7 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
             const unsigned ugrid = (unsigned)std::min<long long>(tiles, (long long)di.sm_count);
             // flows whose couplings transform one dim: two tiles in flight (chain_umma_pp_kernel); ZF_CHAIN_IMPL=umma8
             // keeps the single-tile kernel for them
-            if (plan.all_d1 && a.n_steps <= USTEPS && !(impl && (strcmp(impl, "umma8") == 0 || strcmp(impl, "umma16") == 0))) {
+            if (plan.all_d1 && a.n_steps <= USTEPS && !(impl && strcmp(impl, "umma8") == 0)) {
                 const size_t psmem = umma_pp_smem_floats(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax) * sizeof(float);
                 if (psmem <= (size_t)di.max_smem_optin) {
                     const unsigned pgrid = (unsigned)std::min<long long>((tiles + 1) / 2, (long long)di.sm_count);
@@ -2415,16 +2041,8 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
                 return ZF_OK;
             };
             int rc;
-#ifdef ZF_EXPERIMENTAL
-            // ZF_CHAIN_IMPL=umma16: 16 epilogue warps with a setmaxnreg register split.  Measured no faster than the
-            // default 8 (the activation phases are bound by the SFU / tensor-memory-store port, not by latency).
-            const bool eight = !(impl && strcmp(impl, "umma16") == 0);
-            if (mode == kModeInverse) rc = eight ? launch(chain_umma_kernel<true, 2>, 320) : launch(chain_umma_kernel<true, 4>, 640);
-            else rc = eight ? launch(chain_umma_kernel<false, 2>, 320) : launch(chain_umma_kernel<false, 4>, 640);
-#else
-            if (mode == kModeInverse) rc = launch(chain_umma_kernel<true, 2>, 320);
-            else rc = launch(chain_umma_kernel<false, 2>, 320);
-#endif
+            if (mode == kModeInverse) rc = launch(chain_umma_kernel<true>, 320);
+            else rc = launch(chain_umma_kernel<false>, 320);
             if (rc != ZF_OK) return rc;
             count_launch();
             ZF_CUDA_CHECK(cudaGetLastError());

@@ -61,8 +61,8 @@ def chain_flops_per_event(w):
 
 
 def default_cpu_sample(w):
-    """Bounded CPU sample: about 2e11 conditioner flops (~10-30 s on 8 host cores)."""
-    return int(max(20_000, min(4_000_000, 2e11 // chain_flops_per_event(w))))
+    """Bounded CPU sample: about 3e12 conditioner flops (10-30 s of work for the numpy port on 8-16 host cores)."""
+    return int(max(20_000, min(40_000_000, 3e12 // chain_flops_per_event(w))))
 
 
 def synth(w, M, seed):
@@ -546,6 +546,61 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def bench_deep_set(dev):
+    """BASELINE.json configs[2] (deep_set conditional): examples/deep_set.ipynb's data (1000 sets, sizes
+    int(400 Exp / max Exp) + 1, elements N(0,1)^2 padded to 50,000 rows, y ~ N(sqrt(n), 1)^2), DeepSetFlow =
+    Phi (BatchNorm -> 3 x Dense(128) -> Dense(8) -> Dropout -> sum-pool) feeding rolling_spline_coupling(2,
+    layers=(128,)*6).  Two timings: the flow's fused forward+backward step given c, returning d loss / d c
+    (SURVEY.md 8d cfg3), and the whole joint step (Phi forward, flow value-and-grad, Phi backward, AdamW on both)."""
+    import torch
+
+    from zenflow_b200 import Flow, _lib
+    from zenflow_b200.bijectors import rolling_spline_coupling
+    from zenflow_b200.deep_set import DeepSetFlowTrainer, Phi, SumMatrix
+    from zenflow_b200.distributions import Beta
+
+    rng = np.random.default_rng(1)
+    n = rng.exponential(size=1000)
+    n *= 400 / np.max(n)
+    sizes = (n + 1).astype(int)
+    X = np.concatenate([rng.normal(size=(ni, 2)) for ni in sizes])
+    X = np.concatenate([X, np.zeros((50_000 - len(X), 2))]).astype(np.float32)
+    y = rng.normal(np.sqrt(sizes), 1, size=(2, len(sizes))).T.astype(np.float32)
+    phi = Phi()
+    flow = Flow(rolling_spline_coupling(2, layers=(128,) * 6), latent=Beta())
+    tr = DeepSetFlowTrainer(phi, phi.init(0, X), flow, flow.init(0, y[:1], np.zeros((1, 8), np.float32)), 2, 2)
+    sm = SumMatrix.from_sizes(sizes)
+    Xd, yd = torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev)
+    c = tr.phi_eng.forward(Xd, sm, train=False)
+
+    def timed(fn, reps):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(5 + i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, (_lib.launch_count() - l0) / reps
+
+    flow_ms, flow_l = timed(lambda i: tr.flow_eng.step(yd, c, want_gc=True, update=False), 100)
+    joint_ms, joint_l = timed(lambda i: tr.step(Xd, sm, yd, seed=i), 100)
+    losses = [-float(tr.step(Xd, sm, yd, seed=1000 + i).item()) / len(sizes) for i in range(3)]
+    return {"config": {"workload": "deep_set", "sets": int(len(sizes)), "rows": 50_000, "D": 2, "C": 8, "K": 16,
+                       "layers": [128] * 6, "phi": "BatchNorm -> 3 x Dense(128) -> Dense(8) -> Dropout(0.3) -> sum-pool"},
+            "flow_step_given_c": {"ms_per_step": flow_ms, "events_per_s": len(sizes) / flow_ms * 1e3,
+                                  "gpu_launches_per_step": flow_l,
+                                  "what": "zf_flow_value_and_grad: loss, parameter gradients and d loss / d c, one call"},
+            "joint_step": {"ms_per_step": joint_ms, "sets_per_s": len(sizes) / joint_ms * 1e3,
+                           "rows_per_s": 50_000 / joint_ms * 1e3, "gpu_launches_per_step": joint_l,
+                           "what": "Phi forward (train) + flow value-and-grad + Phi backward + AdamW on both"},
+            "loss_after_205_steps": losses[-1],
+            "note": "1000 events per step: this config is launch-latency-bound (one batch-statistics phase per bijector)"}
+
+
 def bench_config(workload, w, M):
     """The `config` object both arms print (the CPU arm's bounded sample is described in cpu_baseline.sample)."""
     bytes_io = 4 * M * (w["D"] + w["C"] + 1)
@@ -663,7 +718,7 @@ def main():
     ap.add_argument("--train-warmup", type=int, default=1)
     ap.add_argument("--train-micro-batch", type=int, default=0, help="override TrainEngine's micro-batch (0: default)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (other eval config, deep_set)")
-    ap.add_argument("--deep-set", type=int, default=0, help="run the deep_set (configs[2]) train-step leg at N=1")
+    ap.add_argument("--deep-set", type=int, default=1, help="run the deep_set (configs[2]) train-step leg at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -307,6 +307,41 @@ int zf_flow_value_and_grad(void* stream, void* aux_stream, const zf_chain* chain
                            void* dp_comm, void* dp_grad_comm, float* grad_flat, const int64_t* bucket_off,
                            void* workspace, size_t workspace_bytes, int64_t micro_batch);
 
+/* ---- Deep-Set conditioner Phi (examples/deep_set.ipynb:138-160) ---------------------------
+ * The FLAX module on the other side of the flow's conditions in the deep_set config:
+ *   BatchNorm_0 -> NNBlock_0 = (Dense_l + swish) x n_hidden, Dense_{n_hidden} (out_dim) -> Dropout(rate) -> sum_matrix @ .
+ * Leaves exactly as FLAX stores them (kernels (in, out) row-major); bn_mean / bn_var are the running statistics and
+ * are updated in place by a train-mode forward.  The notebook's BCOO sum matrix of ones (deep_set.ipynb:60-74) is
+ * passed as its COO index list: entry e adds row row_idx[e] of the embeddings to set set_idx[e]. */
+typedef struct zf_phi {
+    int32_t in_dim;    /* columns of x */
+    int32_t out_dim;   /* columns of c */
+    int32_t n_hidden;
+    int32_t hidden[ZF_MAX_LAYERS];
+    const float* bn_scale;
+    const float* bn_bias;
+    float* bn_mean;
+    float* bn_var;
+    const float* kernel[ZF_MAX_LAYERS + 1];
+    const float* bias[ZF_MAX_LAYERS + 1];
+} zf_phi;
+
+size_t zf_phi_workspace_bytes(const zf_phi* phi, int64_t N);
+/* Phi.__call__(x, sum_matrix, train): x (N, in_dim) -> c (S, out_dim).  train != 0: batch-moment BatchNorm (over all
+ * N rows, padding included, as in the notebook), running statistics updated, dropout active; the layer
+ * pre-activations stay in `workspace` for zf_phi_backward.  dropout_mask: optional (N, out_dim) multipliers
+ * (0 or 1/(1-rate)); NULL draws the keep-mask from Philox keyed by (dropout_seed, row, column). */
+int zf_phi_forward(void* stream, const zf_phi* phi, const float* x, int64_t N, const int32_t* set_idx,
+                   const int32_t* row_idx, int64_t nnz, int64_t S, int32_t train, float dropout_rate,
+                   uint64_t dropout_seed, const float* dropout_mask, float* c_out, void* workspace, size_t workspace_bytes);
+/* VJP of the train-mode forward above wrt the parameters: grads (+=, same struct as a coupling's: BatchNorm scale /
+ * bias, Dense kernels / biases) from gc (S, out_dim) = d loss / d c, e.g. zf_flow_value_and_grad's gc.  Must follow
+ * the matching zf_phi_forward(train = 1) on the same workspace, with the same dropout arguments. */
+int zf_phi_backward(void* stream, const zf_phi* phi, const zf_coupling_grads* grads, const float* x, int64_t N,
+                    const int32_t* set_idx, const int32_t* row_idx, int64_t nnz, int64_t S, float dropout_rate,
+                    uint64_t dropout_seed, const float* dropout_mask, const float* gc, void* workspace,
+                    size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif

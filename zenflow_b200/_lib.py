@@ -58,6 +58,21 @@ class ZfCouplingGrads(C.Structure):
     ]
 
 
+class ZfPhi(C.Structure):
+    _fields_ = [
+        ("in_dim", C.c_int32),
+        ("out_dim", C.c_int32),
+        ("n_hidden", C.c_int32),
+        ("hidden", C.c_int32 * ZF_MAX_LAYERS),
+        ("bn_scale", C.c_void_p),
+        ("bn_bias", C.c_void_p),
+        ("bn_mean", C.c_void_p),
+        ("bn_var", C.c_void_p),
+        ("kernel", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+        ("bias", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+    ]
+
+
 class ZfOp(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -139,6 +154,13 @@ SIGNATURES = {
                                          C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
+    "zf_phi_workspace_bytes": (C.c_size_t, [C.POINTER(ZfPhi), C.c_int64]),
+    "zf_phi_forward": (C.c_int, [C.c_void_p, C.POINTER(ZfPhi), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_size_t]),
+    "zf_phi_backward": (C.c_int, [C.c_void_p, C.POINTER(ZfPhi), C.POINTER(ZfCouplingGrads), C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_uint64, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_size_t]),
     "zf_coupling_backward_workspace_bytes": (C.c_size_t, [C.POINTER(ZfCoupling), C.c_int32, C.c_int32, C.c_int64]),
     "zf_coupling_backward": (C.c_int, [C.c_void_p, C.POINTER(ZfCoupling), C.POINTER(ZfCouplingGrads), C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,

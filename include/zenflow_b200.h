@@ -116,6 +116,21 @@ int zf_rqs_forward(void* stream, const float* theta, const float* x, int64_t M, 
 int zf_rqs_inverse(void* stream, const float* theta, const float* y, int64_t M, int32_t d,
                    int32_t K, float* x, int32_t* idx);
 
+/* ---- the reference's L0 functions on NORMALISED parameters (zenflow/utils.py public surface) ----------------
+ * The hot path fuses the normalisation into the spline kernels (zf_rqs_forward above); these are the drop-ins for
+ * code written against zenflow.utils.  dx, dy (M, d, K) bin widths / heights, slope (M, d, K-1) knot derivatives. */
+/* utils.py:18-20 squareplus, elementwise. */
+int zf_squareplus(void* stream, const float* x, int64_t n, float* y);
+/* utils.py:37-62 normalize_spline_params on rows of raw theta (rows, 3K-1) = widths | heights | slopes. */
+int zf_normalize_spline_params(void* stream, const float* theta, int64_t rows, int32_t K, float* dx, float* dy,
+                               float* slope);
+/* utils.py:65-141 rational_quadratic_spline_forward: y (M, d), log_det (M,) (may be NULL), idx (M, d) (may be NULL). */
+int zf_rqs_forward_normalized(void* stream, const float* x, const float* dx, const float* dy, const float* slope,
+                              int64_t M, int32_t d, int32_t K, float* y, float* log_det, int32_t* idx);
+/* utils.py:144-202 rational_quadratic_spline_inverse (bins searched in the y knots). */
+int zf_rqs_inverse_normalized(void* stream, const float* y, const float* dx, const float* dy, const float* slope,
+                              int64_t M, int32_t d, int32_t K, float* x, int32_t* idx);
+
 /* Developer switch (parity tests): force a chain kernel ("simt", "umma", "umma8"; NULL / "" = automatic) and a train
  * GEMM ("simt"; NULL = tcgen05).  The ZF_CHAIN_IMPL / ZF_GEMM_IMPL environment variables give the initial values
  * and are read once per process. */

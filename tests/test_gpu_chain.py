@@ -314,6 +314,10 @@ def test_flow_sample_and_steps():
     assert log_prob.shape == (3,)
     x2 = flow.apply(variables, 1000, method="sample").cpu().numpy()
     assert x2.shape == (1000, 2)
+    # one documented convention: int size -> device tensor unless as_numpy=True; numpy conditions -> numpy
+    x2n = flow.apply(variables, 1000, method="sample", as_numpy=True)
+    assert isinstance(x2n, np.ndarray) and np.array_equal(x2n, x2)
+    assert isinstance(flow.latent.sample(5, 1, as_numpy=True), np.ndarray)
     # the fused pass equals "draw the latent, then bijector.inverse" (flow.py:76-77) bit for bit
     u = flow.latent.sample(1000, 0)
     assert np.array_equal(flow.apply(variables, u, method="inverse").cpu().numpy(), x2)

@@ -107,6 +107,13 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "zf_rqs_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]),
+    "zf_squareplus": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "zf_normalize_spline_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
+    "zf_rqs_forward_normalized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zf_rqs_inverse_normalized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "zf_selftest_exact_math": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zf_selftest_umma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "zf_selftest_umma_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),

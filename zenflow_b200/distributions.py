@@ -59,14 +59,19 @@ class Distribution(ABC):
         spec = ChainSpec(x.shape[-1], 0)  # an empty chain: only the latent log-pdf tail runs
         return like_input(spec.log_prob(x, None, kind, peak), x)
 
-    def sample(self, nsamples: int, rngkey=None):
-        """(nsamples, dim) draws on the device: counter-based Philox streams keyed by (seed, row, column)
-        inside the CUDA library (csrc/zf_rng.cuh); needs ``dim`` (latched by an earlier log_prob)."""
+    def sample(self, nsamples: int, rngkey=None, *, as_numpy: bool = False):
+        """(nsamples, dim) draws: counter-based Philox streams keyed by (seed, row, column) inside the CUDA
+        library (csrc/zf_rng.cuh); needs ``dim`` (latched by an earlier log_prob).
+
+        Return type (one convention for every sampler of the package): there is no input array to mirror, so the
+        draws stay where they are produced - a CUDA ``torch.Tensor`` - unless ``as_numpy=True`` asks for a host
+        copy (the reference returns a jax array that numpy can consume directly)."""
         if self.dim is None:
             raise ValueError("dim is not set yet: call log_prob (or evaluate the flow) once before sampling")
         kind, peak = self._native()
         spec = ChainSpec(self.dim, 0)  # an empty chain: the sampler is the inverse pass's tile load
-        return spec.sample(int(nsamples), None, kind, peak, _seed_of(rngkey))
+        x = spec.sample(int(nsamples), None, kind, peak, _seed_of(rngkey))
+        return x.cpu().numpy() if as_numpy else x
 
     def __repr__(self):
         """Return string representation."""

@@ -56,8 +56,14 @@ class Flow(Module):
 
         return _train.flow_train_log_prob(self, x, c)
 
-    def sample(self, conditions_or_size: Union[int, "np.ndarray", "torch.Tensor"], *, seed: int = 0):
-        """Return samples from the learned distribution (flow.py:50-78)."""
+    def sample(self, conditions_or_size: Union[int, "np.ndarray", "torch.Tensor"], *, seed: int = 0,
+               as_numpy: Optional[bool] = None):
+        """Return samples from the learned distribution (flow.py:50-78).
+
+        Return type: like every entry point of the package the result mirrors the input - numpy conditions give a
+        numpy array, torch conditions a CUDA tensor.  An int size has nothing to mirror: the samples stay on the
+        device (CUDA ``torch.Tensor``), as for ``Distribution.sample``.  ``as_numpy=True`` / ``False`` overrides
+        either way (``flow.apply(v, 1000, method="sample", as_numpy=True)`` for host-side plotting code)."""
         if isinstance(conditions_or_size, (int, np.integer)):
             size = int(conditions_or_size)
             c = None
@@ -73,7 +79,9 @@ class Flow(Module):
         kind, peak = self.latent._native()
         # latent.sample(size, PRNGKey(seed)) and bijector.inverse in one fused pass (flow.py:76-77)
         x = spec.sample(size, c, kind, peak, _seed_of(seed))
-        return x if (c is None or isinstance(c, torch.Tensor)) else x.cpu().numpy()
+        if as_numpy is None:
+            as_numpy = not (c is None or isinstance(c, torch.Tensor))
+        return x.cpu().numpy() if as_numpy else x
 
     def inverse(self, u, c=None):
         """bijector.inverse(u, c) with the latent draw given (flow.py:77); the parity-mode

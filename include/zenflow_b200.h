@@ -306,7 +306,8 @@ int zf_dp_allreduce_minmax_f32(void* stream, void* comm, float* minmax, int32_t 
  *   chain        ops as for zf_chain_forward; the coupling's bn_mean / bn_var and the ShiftBounds' xmin / xmax are
  *                the RUNNING statistics ("batch_stats" collection) and are UPDATED IN PLACE (mutable=["batch_stats"],
  *                train.py:66-72).  Layout accepted: [ShiftBounds]? (NeuralSplineCoupling Roll*)+ (bijectors.py:418-423).
- *   grads        one zf_coupling_grads per coupling op, in op order; accumulated into (+=)
+ *   grads        one zf_coupling_grads per coupling op, in op order; accumulated into (+=).  NULL: forward only
+ *                (lp, lp_sum and the statistics updates: Flow.__call__(train=True), the fwd rule of a custom_vjp)
  *   lp (M,)      optional output; lp_sum: DEVICE double, += sum of lp over this rank's rows
  *   gc (M,C)     optional output: d loss / d c (the cotangent a Deep-Set conditioner upstream needs,
  *                examples/deep_set.ipynb:320-323); overwritten

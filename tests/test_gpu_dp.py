@@ -142,3 +142,35 @@ def test_dp_world2_shared_gpu_gloo_matches_single_device():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_dp_world2_nccl_c_abi_matches_single_device():
     _run("nccl", [0, 1])
+
+
+def test_value_and_grad_forward_only_matches_full_call():
+    """grads = NULL (the fwd rule of the jax custom_vjp, ffi/zenflow_jax.py): same lp sum and the same statistics
+    updates as the full call, gradient buffer untouched."""
+    import ctypes as Ct
+
+    from zenflow_b200 import _lib
+    from zenflow_b200._device import ptr, stream_ptr
+
+    ops, v, x, c = _problem()
+    full = _engine(ops, v)
+    full.step(x, c, update=False)
+    ref_lp, ref_stats = float(full.lp_sum.item()), _flat_stats(full)
+
+    eng = _engine(ops, v)
+    lib = _lib.load()
+    xd = torch.as_tensor(x, device="cuda")
+    cd = torch.as_tensor(c, device="cuda")
+    ws = eng._workspace(M)
+    base = (ws.data_ptr() + 255) & ~255
+    eng.G.fill_(7.0)
+    lp = torch.empty(M, dtype=torch.float32, device="cuda")
+    kind, peak = eng.flow.latent._native()
+    _lib.check(lib.zf_flow_value_and_grad(stream_ptr(), None, Ct.byref(eng.chain), None, kind, peak, ptr(xd), ptr(cd), M, float(M),
+                                          None, ptr(lp), ptr(eng.lp_sum), None, None, None, None, eng._bucket_off, base,
+                                          ws.numel() - (base - ws.data_ptr()), eng.micro_batch), "zf_flow_value_and_grad")
+    torch.cuda.synchronize()
+    assert float(eng.lp_sum.item()) == ref_lp
+    np.testing.assert_array_equal(_flat_stats(eng), ref_stats)
+    assert bool((eng.G == 7.0).all())
+    np.testing.assert_allclose(lp.double().sum().item(), ref_lp, rtol=1e-6)

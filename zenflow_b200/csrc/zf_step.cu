@@ -128,7 +128,8 @@ extern "C" int zf_flow_value_and_grad(void* stream, void* aux_stream, const zf_c
                                       void* workspace, size_t workspace_bytes, int64_t micro_batch) {
     StepPlan p;
     if (int rc = build_step_plan(chain, M, micro_batch, p)) return rc;
-    ZF_REQUIRE(x && grads && lp_sum && workspace, "value_and_grad: null argument");
+    ZF_REQUIRE(x && lp_sum && workspace, "value_and_grad: null argument");
+    const bool fwd_only = (grads == nullptr);   // train-mode forward only: lp, lp_sum and the statistics updates
     ZF_REQUIRE(chain->cdim == 0 || c, "value_and_grad: chain has cdim=%d but c is NULL", chain->cdim);
     ZF_REQUIRE(global_count >= 1, "value_and_grad: global_count must be >= 1");
     ZF_REQUIRE(!grad_flat || bucket_off, "value_and_grad: grad_flat needs bucket_off");
@@ -188,6 +189,7 @@ extern "C" int zf_flow_value_and_grad(void* stream, void* aux_stream, const zf_c
     // ---- loss and the cotangents of z and of the log-dets (flow.py:46-47, train.py:73)
     if (int rc = zf_flow_loss_grad_ct(st, latent_kind, peakness, cur, ld, M, D, global_count, lp_cotangent, lp, gy, glp, lp_sum))
         return rc;
+    if (fwd_only) return ZF_OK;
 
     // ---- backward
     const bool bucketed = dp_comm && grad_flat;

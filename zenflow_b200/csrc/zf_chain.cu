@@ -560,7 +560,7 @@ __host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
 }
 constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer programs read them from global)
 __host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
-    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 11 * UM +
+    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 11 * UM + 2 * 8 * UM * 4 +
            (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
 
@@ -639,6 +639,45 @@ __device__ __forceinline__ void spline_row_tmem(uint32_t dbase, uint32_t cross_o
     rqs_block_slopes<KT>(pa, b.idx, b.dk, b.dkp1);
 }
 
+// The same row with the lean block forms of zf_math.cuh (rows are issue-bound: ~1.3k instead of ~1.9k instructions
+// for K = 32).  Bins are bit-identical to spline_row_tmem; the other-axis knot, the bin height / width and the
+// knot derivatives are fp32-tolerance quantities either way.  scr: this thread's scratch column (float4, stride
+// apart, KT / 4 entries).  Rows with |theta| >= kThetaFastBound (or inf) take spline_row_tmem's IEEE path.
+template <int KT>
+__device__ __forceinline__ float theta_block_finish_lean(int col, const float* __restrict__ bias, float (&p)[KT],
+                                                         const float (&w)[KT]) {
+    float amax = 0.f;   // NaN entries are not tracked: they poison the row's sums identically on either path
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        p[j] = fmaf(w[j], umma::kF16LoUnscale, p[j]) + bias[col + j];
+        amax = fmaxf(amax, fabsf(p[j]));
+    }
+    return amax;
+}
+template <int KT, bool INVERSE, class Release>
+__device__ __forceinline__ void spline_row_tmem_lean(uint32_t dbase, uint32_t cross_off, const float* __restrict__ bias, float v,
+                                                     RqsBin& b, float4* scr, int stride, Release release) {
+    constexpr int cs_ = INVERSE ? KT : 0, co_ = INVERSE ? 0 : KT;
+    const KnotNorm kn = make_knot_norm(KT);
+    float pa[KT], pb[KT], wa[KT], wb[KT];
+    theta_block_issue<KT>(dbase, cross_off, cs_, pa, wa);
+    umma::wait_ld();
+    const float amax_s = theta_block_finish_lean<KT>(cs_, bias, pa, wa);
+    theta_block_issue<KT>(dbase, cross_off, co_, pb, wb);          // in flight during the search pass
+    const bool slow_s = __any_sync(0xffffffffu, !(amax_s < kThetaFastBound));
+    RqsCheck chk;
+    if (slow_s) rqs_block_search<KT, true>(pa, v, kn, b.idx, b.ks, b.bs, chk);
+    else rqs_block_search_lean<KT>(pa, v, kn, b.idx, b.ks, b.bs);
+    umma::wait_ld();
+    const float amax_o = theta_block_finish_lean<KT>(co_, bias, pb, wb);
+    theta_block_issue<KT>(dbase, cross_off, 2 * KT, pa, wa);       // raw slopes reuse the searched block's registers
+    umma::wait_ld();
+    release();                                          // every TMEM read of this row is done
+    if (__any_sync(0xffffffffu, !(amax_o < kThetaFastBound))) rqs_block_other<KT, true>(pb, b.idx, kn, b.ko, b.bo, chk);
+    else rqs_block_other_lean<KT>(pb, b.idx, kn, scr, stride, b.ko, b.bo);
+    rqs_block_slopes_lean<KT>(pa, wa, umma::kF16LoUnscale, bias + 2 * KT, b.idx, scr, stride, b.dk, b.dkp1);
+}
+
 // One spline row shared by two threads (the same event in column groups 0 and 1), for couplings that transform a
 // single dim and would otherwise leave group 1 idle: group 0 normalises the searched axis and finds the bin while
 // group 1 normalises the other axis; the bin goes over through shared memory, group 1 selects the other-axis knot
@@ -695,6 +734,7 @@ __device__ __forceinline__ void spline_row_other_half(uint32_t dbase, uint32_t c
 struct UCtx {
     const ChainArgs& a;
     float *xs, *cs, *xraw, *hs, *cst, *ldx, *pairx;
+    float4* scratch;   // per-thread scratch columns of the lean spline row: [2][8][UM] float4 (32 KB)
     uint64_t* bars;
     const StepDesc* steps;
     uint32_t tb;
@@ -961,8 +1001,9 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
                     ZF_TR(trs);   // released
                 };
-                if (K == 16) spline_row_tmem<16, INVERSE>(dbase, TC_XOFF, bls + jj * NL, v, bin, release);
-                else spline_row_tmem<32, INVERSE>(dbase, TC_XOFF, bls + jj * NL, v, bin, release);
+                float4* scr = cx.scratch + (size_t)half * 8 * UM + m;   // [half][K / 4][UM] float4
+                if (K == 16) spline_row_tmem_lean<16, INVERSE>(dbase, TC_XOFF, bls + jj * NL, v, bin, scr, UM, release);
+                else spline_row_tmem_lean<32, INVERSE>(dbase, TC_XOFF, bls + jj * NL, v, bin, scr, UM, release);
                 if (m < nm) put_idx(a, s, m0 + m, jj, bin.idx);
                 if (!INVERSE) {
                     float y, ld;
@@ -1025,7 +1066,8 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
     float* cst = hs + a.u_fmax * UM;          // [2][cl.total] per-coupling constants
     float* ldx = cst + 2 * cl.total;
     float* pairx = ldx + 3 * UM;              // [7][UM] exchange between the two threads of a shared spline row
-    float* ring = pairx + 8 * UM;
+    float* scratch = pairx + 8 * UM;          // [2][8][UM] float4: scratch columns of the lean spline rows
+    float* ring = scratch + 2 * 8 * UM * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
@@ -1235,7 +1277,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
         }
     };
     // ------------------------------------------------------------------ role dispatch
-    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, bars, steps, tb, n_tiles, cl, in16, in_bytes};
+    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, reinterpret_cast<float4*>(scratch), bars, steps, tb, n_tiles, cl, in16, in_bytes};
     if (warp == PW) producer_role();
     else if (warp == MW) mma_role();
     else umma_epilogue_role<INVERSE>(cx);
@@ -1270,7 +1312,7 @@ constexpr int PP_CBUF = 4;   // constant-block buffers: one (coupling, slot) occ
 
 __host__ __device__ inline size_t umma_pp_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
     return (PP_TBUF + 2) * (size_t)UM * (D + C) + 2 * (size_t)Fmax * UM + PP_CBUF * (size_t)ucst_layout(Fmax, Hmax, BLmax).total +
-           PP_TBUF * UM +
+           PP_TBUF * UM + 8 * UM * 4 +
            (size_t)URING * URING_FLOATS + 2 * PP_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float) + USTEPS;
 }
 
@@ -1290,7 +1332,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
     float* hs2 = xraw + 2 * UM * (D + C);       // [2][Fmax][UM]  BatchNorm output by occurrence parity (S1 only)
     float* cst = hs2 + 2 * a.u_fmax * UM;       // [PP_CBUF][cl.total]
     float* ldacc = cst + PP_CBUF * cl.total;    // [PP_TBUF][UM]  log-det accumulator per tile (S2 only)
-    float* ring = ldacc + PP_TBUF * UM;
+    float* scratch = ldacc + PP_TBUF * UM;      // [8][UM] float4: scratch columns of the lean spline rows (S2 only)
+    float* ring = scratch + 8 * UM * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + PP_COUNT);
     StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
@@ -1699,8 +1742,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                             umma::fence_before_sync();
                             umma::mbar_arrive(&bars[PP_DEMPTY_D]);
                         };
-                        if (K == 16) spline_row_tmem<16, INVERSE>(dbase, TC_XOFF, bls, v, bin, release);
-                        else spline_row_tmem<32, INVERSE>(dbase, TC_XOFF, bls, v, bin, release);
+                        float4* scr = reinterpret_cast<float4*>(scratch) + m;
+                        if (K == 16) spline_row_tmem_lean<16, INVERSE>(dbase, TC_XOFF, bls, v, bin, scr, UM, release);
+                        else spline_row_tmem_lean<32, INVERSE>(dbase, TC_XOFF, bls, v, bin, scr, UM, release);
                         if (m < nm) put_idx(a, s, m0 + m, 0, bin.idx);
                         umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // last read of this occurrence's constants by S2
                         if (!INVERSE) {

@@ -19,6 +19,7 @@
 #include "zf_math.cuh"
 #include "zf_umma.cuh"
 #include "zf_rng.cuh"
+#include "zf_vjp.cuh"
 
 #include <float.h>
 #include <math.h>
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
     }
 }
 
-enum ChainMode : int { kModeForward = 0, kModeLogProb = 1, kModeInverse = 2 };
+enum ChainMode : int { kModeForward = 0, kModeLogProb = 1, kModeInverse = 2, kModeVjp = 3 };
 
 struct ChainArgs {
     const float* x;     // (M, D) input (x for forward/log_prob, z for inverse)
@@ -227,6 +228,14 @@ struct ChainArgs {
     int u_fmax, u_hmax, u_blmax;   // tensor-core kernel: max conditioner inputs / hidden biases / last-layer bias floats
     int* idx_out;       // (M, n_couplings, d) bin indices of every spline evaluation, or null (parity evidence)
     int n_couplings;
+    // kModeVjp (chain_umma_kernel<false, true>, a chain of ONE coupling): conditioner recompute + spline VJP
+    const float* gy;    // (M, D) cotangent of the coupling's output; logical column j is read at (j + gy_rot) % D
+    const float* glp;   // (M,) cotangent of the log-det
+    float* gx;          // (M, D) out: d/dx of the transformed columns, pass-through cotangent of the others
+    float* act_h0;      // (M, F) out: BatchNorm output
+    float* act_z[ZF_MAX_LAYERS];   // (M, 128) out: pre-activations of the hidden layers
+    float* dtheta;      // (M, ldt) out: cotangent of theta, dim j in columns [j NL, j NL + 3K-1), padding zero
+    int ldt, gy_rot;
 };
 
 // bin index of event m, coupling s.cidx, transformed dim jj (zf_chain_bin_indices)
@@ -559,8 +568,10 @@ __host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
     return l;
 }
 constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer programs read them from global)
-__host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax) {
-    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 11 * UM + 2 * 8 * UM * 4 +
+constexpr int VJP_ROW = 97;   // floats per theta row of the VJP kernel (odd: one thread per row without bank conflicts)
+__host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax, bool vjp = false) {
+    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 11 * UM +
+           (vjp ? 2 * UM * VJP_ROW : 2 * 8 * UM * 4) +
            (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
 
@@ -764,8 +775,9 @@ __device__ __forceinline__ void activation_store(uint32_t tb, uint32_t lane_base
     umma::st8u(umma::taddr(tb, lane_base, TC_ALO + (n0 >> 1)), lo);
 }
 
-template <bool INVERSE>
+template <bool INVERSE, bool VJP = false>
 __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
+    static_assert(!(INVERSE && VJP), "the VJP kernel recomputes the forward conditioner");
     constexpr int NG = 2;
     constexpr bool HELPER = false;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -857,6 +869,19 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             }
             epi_barrier<ET>();
             ZF_TR(trs);   // batch norm done
+            if (VJP) {
+                // BatchNorm output for the grad-weight GEMM of the first Dense; the conditioning columns' cotangent
+                // passes through unchanged (d y[:, j] / d x[:, j] = 1, bijectors.py:364)
+                for (int e = tid; e < nm * F; e += ET) {
+                    const int mm = e / F, f = e - mm * F;
+                    a.act_h0[(m0 + mm) * F + f] = hs[f * UM + mm];
+                }
+                const int nc = D - d;
+                for (int e = tid; e < nm * nc; e += ET) {
+                    const int mm = e / nc, j = d + (e - mm * nc);
+                    a.gx[(m0 + mm) * D + j] = a.gy[(m0 + mm) * D + pmod(j + a.gy_rot, D)];
+                }
+            }
             // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
             // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
             // the event's first four inputs stay in registers for all chunks (F is 2 on the 2-D flows): the chunk
@@ -892,6 +917,11 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 for (int f = 0; f < 4; ++f)
                     if (f < F) fma_row(hreg[f], f);
                 for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
+                if (VJP && m < nm) {
+                    float4* zo = reinterpret_cast<float4*>(a.act_z[0] + (m0 + m) * 128 + n0);
+#pragma unroll
+                    for (int g4 = 0; g4 < CW / 4; ++g4) zo[g4] = make_float4(acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2], acc[g4 * 4 + 3]);
+                }
                 activation_compute<CW>(acc, ahi, alo);
 #ifdef ZF_TRACE_FINE
                 asm volatile("" :: "f"(ahi[0]), "f"(alo[CW - 1]) : "memory");
@@ -945,6 +975,11 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                         tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + n0 + 32), vn);
                         tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
                     }
+                    if (VJP && m < nm) {
+                        float4* zo = reinterpret_cast<float4*>(a.act_z[l] + (m0 + m) * 128 + n0);
+#pragma unroll
+                        for (int g4 = 0; g4 < CW / 4; ++g4) zo[g4] = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+                    }
                     activation_compute<CW>(v, ahi, alo);
                     activation_store<CW>(tb, lane_base, n0, ahi, alo);
                     umma::wait_st();
@@ -955,7 +990,43 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             }
             // ---- last layer: theta of one transformed dim at a time, read from tensor memory
             float ldc = 0.f;
-            if (!HELPER && d == 1 && half < 2) {
+            if (VJP) {
+                // theta row -> this thread's row buffer in shared memory -> cotangent of theta in place (zf_vjp.cuh)
+                // -> global, one transformed dim per column group at a time
+                float* row = reinterpret_cast<float*>(cx.scratch) + ((size_t)half * UM + m) * VJP_ROW;
+                const KnotNorm kn = make_knot_norm(K);
+                const float gld = m < nm ? a.glp[m0 + m] : 0.f;
+                for (int jj = half; jj < d; jj += 2) {
+                    mbar_wait(&bars[B_DFULL_D + half], p_fd);
+                    p_fd ^= 1u;
+                    umma::fence_after_sync();
+                    const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(half));
+                    const float* bj = bls + jj * NL;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < NL; c0 += 16) {
+                        float pm[16], pc[16];
+                        umma::ld16(dbase + c0, pm);
+                        umma::ld16(dbase + TC_XOFF + c0, pc);
+                        umma::wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) row[c0 + j] = fmaf(pc[j], umma::kF16LoUnscale, pm[j]) + bj[c0 + j];
+                    }
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_DEMPTY_D + half]);   // every TMEM read of this row is done
+                    const float xv = xs[pmod(jj - rot, D) * UM + m];
+                    const float gyv = m < nm ? a.gy[(m0 + m) * D + pmod(jj + a.gy_rot, D)] : 0.f;
+                    float g_x;
+                    if (K == 16) g_x = rqs_row_backward<16>(row, K, xv, gyv, gld, kn);
+                    else g_x = rqs_row_backward<32>(row, K, xv, gyv, gld, kn);
+                    row[P] = 0.f;   // padding column of the NL-wide block
+                    if (m < nm) {
+                        float4* dst = reinterpret_cast<float4*>(a.dtheta + (m0 + m) * a.ldt + jj * NL);
+                        for (int q4 = 0; q4 < NL / 4; ++q4)
+                            dst[q4] = make_float4(row[4 * q4], row[4 * q4 + 1], row[4 * q4 + 2], row[4 * q4 + 3]);
+                        a.gx[(m0 + m) * D + jj] = g_x;
+                    }
+                }
+            } else if (!HELPER && d == 1 && half < 2) {
                 // one transformed dim: the two spline groups share its row (see spline_row_search_half)
                 mbar_wait(&bars[B_DFULL_D + 0], p_fd);
                 p_fd ^= 1u;
@@ -1025,7 +1096,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
         }
 
         // ---- store
-        if (a.mode == kModeLogProb) {
+        if (VJP) {
+        } else if (a.mode == kModeLogProb) {
             if (half == 0 && m < nm) {
                 float lat = 0.f;
                 for (int j = 0; j < D; ++j) lat += latent_logpdf(xs[pmod(j - a.rot_total, D) * UM + m], a.lc);
@@ -1051,7 +1123,7 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // 8 epilogue warps (two column groups) + producer + MMA issuer (320 threads).
-template <bool INVERSE>
+template <bool INVERSE, bool VJP = false>
 __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constant__ ChainArgs a) {
     constexpr int NG = 2;
     extern __shared__ __align__(128) float smem[];
@@ -1067,7 +1139,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
     float* ldx = cst + 2 * cl.total;
     float* pairx = ldx + 3 * UM;              // [7][UM] exchange between the two threads of a shared spline row
     float* scratch = pairx + 8 * UM;          // [2][8][UM] float4: scratch columns of the lean spline rows
-    float* ring = scratch + 2 * 8 * UM * 4;
+    float* ring = scratch + (VJP ? 2 * UM * VJP_ROW : 2 * 8 * UM * 4);   // VJP: [2][UM][VJP_ROW] theta rows instead
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)URING * URING_FLOATS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     StepDesc* steps_s = reinterpret_cast<StepDesc*>(tmem_slot + 32);
@@ -1280,7 +1352,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
     const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, reinterpret_cast<float4*>(scratch), bars, steps, tb, n_tiles, cl, in16, in_bytes};
     if (warp == PW) producer_role();
     else if (warp == MW) mma_role();
-    else umma_epilogue_role<INVERSE>(cx);
+    else umma_epilogue_role<INVERSE, VJP>(cx);
 
     umma::fence_before_sync();
     __syncthreads();
@@ -2108,6 +2180,87 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
         if (int rc = set_smem((const void*)chain_kernel<false>, smem)) return rc;
         chain_kernel<false><<<grid, kChainThreads, smem, stream>>>(a);
     }
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+// ---- fused conditioner recompute + spline VJP of ONE coupling (tensor-core path of zf_coupling_backward) ---------
+// The coupling is planned and packed as a chain of one op; the kernel is chain_umma_kernel<false, true>.
+static int vjp_plan(const zf_coupling* cp, int D, int C, Plan& plan, zf_op& op, zf_chain& chain) {
+    op = zf_op{};
+    op.kind = ZF_OP_COUPLING;
+    op.coupling = cp;
+    chain = zf_chain{D, C, 1, &op};
+    return build_plan(&chain, plan);
+}
+
+// floats of packed parameters the fused VJP kernel needs, 0 when this coupling / device does not fit it
+size_t coupling_vjp_ws_floats(const zf_coupling* cp, int D, int C) {
+    Plan plan;
+    zf_op op;
+    zf_chain chain;
+    const char* impl = chain_impl_env();
+    if (impl && impl[0] == 's') return 0;
+    if (vjp_plan(cp, D, C, plan, op, chain) != ZF_OK || !plan.umma_ok || plan.n_couplings != 1) return 0;
+    DeviceInfo di;
+    if (get_device_info(&di) != ZF_OK) return 0;
+    if (umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true) * sizeof(float) > (size_t)di.max_smem_optin) return 0;
+    return plan.ws_floats;
+}
+
+int coupling_vjp_pack(cudaStream_t stream, const zf_coupling* cp, int D, int C, float* ws) {
+    Plan plan;
+    zf_op op;
+    zf_chain chain;
+    if (int rc = vjp_plan(cp, D, C, plan, op, chain)) return rc;
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    static thread_local PackBatch batch;
+    batch.jobs[0] = plan.jobs[0];
+    pack_step_kernel<<<dim3((unsigned)di.sm_count, 1u), 256, 0, stream>>>(batch, ws);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, const float* ws, const float* x_in, const float* c,
+                     const float* gy, int gy_rot, const float* glp, long long M, float* gx, float* act_h0, float* const* act_z,
+                     float* dtheta, int ldt) {
+    Plan plan;
+    zf_op op;
+    zf_chain chain;
+    if (int rc = vjp_plan(cp, D, C, plan, op, chain)) return rc;
+    DeviceInfo di;
+    if (int rc = get_device_info(&di)) return rc;
+    ChainArgs a{};
+    a.x = x_in; a.c = c; a.ws = ws; a.M = M; a.D = D; a.C = C;
+    a.n_steps = 1;
+    a.rot_total = 0;
+    a.act_rows = plan.act_rows;
+    a.mode = kModeVjp;
+    a.n_couplings = 1;
+    a.u_fmax = plan.Fmax; a.u_hmax = plan.Hmax; a.u_blmax = plan.BLmax;
+    a.gy = gy; a.glp = glp; a.gx = gx; a.act_h0 = act_h0; a.dtheta = dtheta; a.ldt = ldt;
+    a.gy_rot = ((gy_rot % D) + D) % D;
+    for (int l = 0; l < cp->n_hidden; ++l) a.act_z[l] = act_z[l];
+    ZF_REQUIRE((reinterpret_cast<uintptr_t>(dtheta) & 15) == 0 && (ldt & 3) == 0, "coupling_vjp: dtheta must be 16-byte aligned");
+    for (int l = 0; l < cp->n_hidden; ++l)
+        ZF_REQUIRE((reinterpret_cast<uintptr_t>(act_z[l]) & 15) == 0, "coupling_vjp: activations must be 16-byte aligned");
+    const size_t smem = umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true) * sizeof(float);
+    static std::mutex mu;
+    static std::map<int, size_t> done;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = done[di.device];
+        if (have < smem) {
+            ZF_CUDA_CHECK(cudaFuncSetAttribute((const void*)chain_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            have = smem;
+        }
+    }
+    const long long tiles = (M + UM - 1) / UM;
+    if (tiles == 0) return ZF_OK;
+    chain_umma_kernel<false, true><<<(unsigned)std::min<long long>(tiles, (long long)di.sm_count), 320, smem, stream>>>(a);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;

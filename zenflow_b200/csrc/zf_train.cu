@@ -15,6 +15,7 @@
 //   zf_nadamw_update                    <- optax.nadamw / adamw (train.py:12-15,84-85)
 #include "zf_common.cuh"
 #include "zf_math.cuh"
+#include "zf_vjp.cuh"
 
 #include <float.h>
 #include <stdlib.h>
@@ -394,128 +395,6 @@ static int launch_gemm(cudaStream_t st, int mode, const GemmArgs& g) {
 // spline VJP: theta row -> d(theta) row in place; d/dx of the transformed columns; pass-through
 // of the conditioning columns' cotangent
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float squareplus_grad(float a) {  // d/da 0.5*(a + sqrt(a^2+4))
-    return 0.5f * (1.0f + a * rsqrtf(a * a + 4.0f));
-}
-
-// row: raw theta (3K-1) in shared memory, overwritten by its cotangent.  Returns d/dx.
-// KT > 0: K known at compile time (loops unrolled); KT == 0: runtime K.
-template <int KT>
-__device__ __forceinline__ float rqs_row_backward(float* row, int K_rt, float x, float gy, float gld, const KnotNorm& kn) {
-    const int K = KT > 0 ? KT : K_rt;
-    RqsBin b;
-    rqs_locate<KT>(row, K, true, x, kn, b);
-    const int P = 3 * K - 1;
-    const bool oob = (x < 0.f) || (x >= 1.f);
-    const int idx = b.idx;
-    if (oob || idx >= K || !(x == x)) {  // identity branch (or the reference's NaN corner): no parameter gradient
-        for (int p = 0; p < P; ++p) row[p] = 0.f;
-        return oob ? gy : 0.f;
-    }
-    const float xk = b.ks, w = b.bs, h = b.bo, d0 = b.dk, d1 = b.dkp1;
-    const float s = h / w;
-    const float xi_raw = (x - xk) / w;
-    const bool clipped = !(xi_raw > kEps && xi_raw < kOneMinusEps);
-    const float xi = fminf(fmaxf(xi_raw, kEps), kOneMinusEps);
-    const float az = 1.0f - xi;
-    const float beta = d1 + d0 - 2.0f * s;
-    const float u = s * xi + d0 * az;
-    const float num = h * xi * u;
-    const float den = s + beta * xi * az;
-    const float Dn = den + kEps;
-    const float v = d1 * xi + 2.0f * s * az;
-    const float num2 = xi * v + d0 * az * az;
-
-    // adjoints (Appendix A)
-    const float g_yk = gy;
-    const float g_num = gy / Dn;
-    const float g_den = -gy * num / (Dn * Dn) - 2.0f * gld / Dn;
-    const float g_num2 = gld / (num2 + kEps);
-    float g_s = gld * 2.0f / (s + kEps);
-    float g_h = g_num * xi * u;
-    float g_xi = g_num * h * u;
-    const float g_u = g_num * h * xi;
-    g_s += g_u * xi;
-    g_xi += g_u * s;
-    float g_d0 = g_u * az;
-    float g_az = g_u * d0;
-    g_s += g_den;
-    const float g_beta = g_den * xi * az;
-    g_xi += g_den * beta * az;
-    g_az += g_den * beta * xi;
-    float g_d1 = g_beta;
-    g_d0 += g_beta;
-    g_s -= 2.0f * g_beta;
-    g_xi += g_num2 * v;
-    const float g_v = g_num2 * xi;
-    g_d0 += g_num2 * az * az;
-    g_az += g_num2 * d0 * 2.0f * az;
-    g_d1 += g_v * xi;
-    g_xi += g_v * d1;
-    g_s += g_v * 2.0f * az;
-    g_az += g_v * 2.0f * s;
-    g_xi -= g_az;
-    const float g_xr = clipped ? 0.f : g_xi;
-    const float g_x = g_xr / w;
-    const float g_xk = -g_xr / w;
-    float g_w = -g_xr * xi_raw / w;
-    g_h += g_s / w;
-    g_w -= g_s * s / w;
-
-    // slopes first (their raw values are needed before the row is overwritten)
-    const float c_lo = (idx >= 1) ? row[2 * K + idx - 1] : 0.f;
-    const float c_hi = (idx + 1 <= K - 1) ? row[2 * K + idx] : 0.f;
-
-    // widths / heights: W_j = kappa*(s_j/S + c); cotangent of W_j is g_lt (j<idx), g_at (j==idx), 0 otherwise
-    const float kappa = kn.rden;
-#pragma unroll
-    for (int blk = 0; blk < 2; ++blk) {
-        float* pr = row + blk * K;
-        const float g_lt = blk == 0 ? g_xk : g_yk;
-        const float g_at = blk == 0 ? g_w : g_h;
-        float S = 0.f, Slt = 0.f, s_at = 0.f;
-        constexpr int KS = KT > 0 ? KT : 1;
-        if (KT > 0) {
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                const float aj = pr[j];
-                const float sj = 0.5f * (aj + sqrtf(fmaf(aj, aj, 4.0f)));   // fp32-tolerance path: plain sqrt
-                S += sj;
-                Slt += (j < idx) ? sj : 0.f;
-                s_at = (j == idx) ? sj : s_at;
-            }
-        } else {
-            for (int j = 0; j < K; ++j) {
-                const float sj = squareplus_rn(pr[j]);
-                S += sj;
-                if (j < idx) Slt += sj;
-                if (j == idx) s_at = sj;
-            }
-        }
-        const float A = (g_lt * Slt + g_at * s_at) / S;
-        const float ks = kappa / S;
-        if (KT > 0) {
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-                const float a = pr[j];
-                const float gW = (j < idx) ? g_lt : ((j == idx) ? g_at : 0.f);
-                // d squareplus/da = 0.5*(1 + a/sqrt(a^2+4)) = s/(2s - a) ... use the rsqrt form
-                pr[j] = ks * (gW - A) * squareplus_grad(a);
-            }
-        } else {
-            for (int j = 0; j < K; ++j) {
-                const float a = pr[j];
-                const float gW = (j < idx) ? g_lt : ((j == idx) ? g_at : 0.f);
-                pr[j] = ks * (gW - A) * squareplus_grad(a);
-            }
-        }
-    }
-    for (int j = 0; j < K - 1; ++j) row[2 * K + j] = 0.f;
-    if (idx >= 1) row[2 * K + idx - 1] = g_d0 * squareplus_grad(c_lo);
-    if (idx + 1 <= K - 1) row[2 * K + idx] = g_d1 * squareplus_grad(c_hi);
-    return g_x;
-}
-
 struct SplineBwdArgs {
     float* theta;          // (Mb, d, P) in: raw params, out: their cotangent
     const float* x_in;     // (M, D) rows m0..m0+Mb of the coupling input
@@ -787,17 +666,66 @@ extern "C" int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakne
     return zf_flow_loss_grad_ct(stream, latent_kind, peakness, z, log_det, M, D, global_count, nullptr, lp, gz, glp, lp_sum);
 }
 
-static size_t cpl_bwd_floats_per_sample(const zf_coupling* cp, int D, int C) {
-    const int d = D / 2, F = D - d + C;
+// tensor-core path (zf_chain.cu): conditioner recompute + spline VJP in one kernel, theta never leaves the SM
+namespace zf {
+size_t coupling_vjp_ws_floats(const zf_coupling* cp, int D, int C);
+int coupling_vjp_pack(cudaStream_t stream, const zf_coupling* cp, int D, int C, float* ws);
+int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, const float* ws, const float* x_in, const float* c,
+                     const float* gy, int gy_rot, const float* glp, long long M, float* gx, float* act_h0, float* const* act_z,
+                     float* dtheta, int ldt);
+}  // namespace zf
+
+// Workspace of zf_coupling_backward.  Fused path: the cotangent of theta is kept with each dim's 3K-1 columns padded
+// to NL = a multiple of 16 (rows of 16-byte multiples for the kernel's vector stores), and the last Dense is
+// differentiated in that padded column space: [packed parameters | W_L padded | dW_L padded | db_L padded], then per
+// micro-batch H0 | Z_1 .. Z_L | dTheta.
+struct CplBwdLayout {
+    bool fused;
+    int NL;               // columns per transformed dim in the theta / dTheta block
+    size_t pack_floats;   // packed parameters of the fused kernel
+    size_t fixed_floats;  // everything that does not scale with the micro-batch
+    size_t per_sample;
+};
+static CplBwdLayout cpl_bwd_layout(const zf_coupling* cp, int D, int C) {
+    const int d = D / 2, F = D - d + C, P = 3 * cp->knots - 1, L = cp->n_hidden;
+    CplBwdLayout lay{};
+    lay.pack_floats = coupling_vjp_ws_floats(cp, D, C);
+    lay.fused = lay.pack_floats > 0;
+    lay.NL = lay.fused ? (P + 15) / 16 * 16 : P;
     size_t n = F;
-    for (int l = 0; l < cp->n_hidden; ++l) n += cp->hidden[l];
-    n += (size_t)d * (3 * cp->knots - 1);
-    return n;
+    for (int l = 0; l < L; ++l) n += cp->hidden[l];
+    n += (size_t)d * lay.NL;
+    lay.per_sample = n;
+    if (lay.fused) {
+        const size_t wl = (size_t)cp->hidden[L - 1] * d * lay.NL;
+        lay.fixed_floats = (lay.pack_floats + 63) / 64 * 64 + 2 * wl + (size_t)(d * lay.NL + 63) / 64 * 64;
+    }
+    return lay;
 }
 
 extern "C" size_t zf_coupling_backward_workspace_bytes(const zf_coupling* cp, int32_t D, int32_t C, int64_t micro_batch) {
     if (!cp || D < 2 || micro_batch < 1) return 0;
-    return (cpl_bwd_floats_per_sample(cp, D, C) * (size_t)micro_batch + 64) * sizeof(float);
+    const CplBwdLayout lay = cpl_bwd_layout(cp, D, C);
+    return (lay.fixed_floats + lay.per_sample * (size_t)micro_batch + 64) * sizeof(float);
+}
+
+// W (Hin, d P) -> Wp (Hin, d NL), zero padded per dim
+__global__ void __launch_bounds__(256) pad_last_layer_kernel(const float* __restrict__ W, int Hin, int d, int P, int NL, float* __restrict__ Wp) {
+    const int n = Hin * d * NL;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
+        const int h = e / (d * NL), r = e - h * (d * NL), jj = r / NL, p = r - jj * NL;
+        Wp[e] = p < P ? W[(size_t)h * d * P + jj * P + p] : 0.f;
+    }
+}
+// gW (Hin, d P) += gWp (Hin, d NL) without the padding; gb (d P) += gbp (d NL)
+__global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict__ gWp, const float* __restrict__ gbp, int Hin, int d, int P,
+                                                        int NL, float* __restrict__ gW, float* __restrict__ gb) {
+    const int n = (Hin + 1) * d * P;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
+        const int h = e / (d * P), r = e - h * (d * P), jj = r / P, p = r - jj * P;
+        if (h < Hin) gW[e] += gWp[(size_t)h * d * NL + jj * NL + p];
+        else gb[r] += gbp[jj * NL + p];
+    }
 }
 
 extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const zf_coupling_grads* gr, int32_t D, int32_t C,
@@ -809,31 +737,47 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
     ZF_REQUIRE(d > 0 && d < D && (C == 0 || c) && M >= 1 && micro_batch >= 1, "coupling_backward: bad shape");
     ZF_REQUIRE(F <= 256, "coupling_backward: at most 256 conditioner inputs");
     const int K = cp->knots, P = 3 * K - 1, L = cp->n_hidden;
-    const size_t per = cpl_bwd_floats_per_sample(cp, D, C);
-    if (workspace_bytes < (per * (size_t)micro_batch + 64) * sizeof(float))
+    CplBwdLayout lay = cpl_bwd_layout(cp, D, C);
+    if (workspace_bytes < (lay.fixed_floats + lay.per_sample * (size_t)micro_batch + 64) * sizeof(float))
         return fail(ZF_ERR_WORKSPACE, "coupling_backward: workspace too small");
+    const bool fused = lay.fused && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+    const int NL = lay.NL, TW = d * NL;   // theta block width
     cudaStream_t st = (cudaStream_t)stream;
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
 
-    // spline tile: TS samples (multiple of 4) x d rows, ~256 rows; two or three ring stages
+    // spline tile (unfused path): TS samples (multiple of 4) x d rows, ~256 rows; two or three ring stages
     int TS = std::max(4, (256 / d) & ~3);
     while (TS > 4 && (size_t)TS * d * P * 4 > 96 * 1024) TS -= 4;
     const size_t tile_bytes = (size_t)TS * d * P * 4;
     int sp_stages = (int)std::min<size_t>(3, ((size_t)di.max_smem_optin - 256) / tile_bytes);
     int sp_bps = 1;
     if (2 * (2 * tile_bytes + 256) + 2048 <= (size_t)di.max_smem_optin) { sp_stages = 2; sp_bps = 2; }
-    if (sp_stages < 1) return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
+    if (!fused && sp_stages < 1) return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
     const size_t sp_smem = (size_t)sp_stages * tile_bytes + 64;
     auto sp_kernel = (K == 16) ? spline_bwd_kernel<16> : (K == 32) ? spline_bwd_kernel<32> : spline_bwd_kernel<0>;
-    ZF_CUDA_CHECK(cudaFuncSetAttribute(sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+    if (!fused) ZF_CUDA_CHECK(cudaFuncSetAttribute(sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
 
     ZF_CUDA_CHECK(cudaMemsetAsync(bn_sums, 0, 2 * F * sizeof(double), st));
     float* ws = static_cast<float*>(workspace);
     int widths[ZF_MAX_LAYERS + 2];
     widths[0] = F;
     for (int l = 0; l < L; ++l) widths[l + 1] = cp->hidden[l];
-    widths[L + 1] = d * P;
+    widths[L + 1] = fused ? TW : d * P;
+
+    float *pack = nullptr, *Wp = nullptr, *gWp = nullptr, *gbp = nullptr;
+    if (fused) {
+        const size_t wl = (size_t)widths[L] * TW;
+        pack = ws;
+        Wp = ws + (lay.pack_floats + 63) / 64 * 64;
+        gWp = Wp + wl;
+        gbp = gWp + wl;
+        ws += lay.fixed_floats;
+        if (int rc = coupling_vjp_pack(st, cp, D, C, pack)) return rc;
+        pad_last_layer_kernel<<<grid_for((long long)wl, 256, 148 * 4), 256, 0, st>>>(cp->kernel[L], widths[L], d, P, NL, Wp);
+        count_launch();
+        ZF_CUDA_CHECK(cudaMemsetAsync(gWp, 0, (wl + TW) * sizeof(float), st));
+    }
 
     for (long long m0 = 0; m0 < M; m0 += micro_batch) {
         const long long Mb = std::min<long long>(micro_batch, M - m0);
@@ -842,25 +786,31 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
         size_t off = 0;
         for (int l = 0; l <= L + 1; ++l) {
             act[l] = ws + off;
-            off += (size_t)widths[l] * Mb;
+            off += ((size_t)widths[l] * Mb + 3) / 4 * 4;
         }
-        bn_apply_kernel<<<grid_for(Mb * F, 256 * 8, 148 * 16), 256, 0, st>>>(x_in + m0 * D, c ? c + m0 * C : nullptr, Mb, D, C,
-                                                                             cp->bn_scale, cp->bn_bias, cp->bn_mean,
-                                                                             cp->bn_var, act[0]);
-        count_launch();
-        // forward recompute: Z_{l+1} = act(Z_l) W_l + b_l   (pre-activations are stored)
-        for (int l = 0; l <= L; ++l) {
-            GemmArgs g{};
-            g.A = act[l]; g.lda = widths[l];
-            g.B = cp->kernel[l]; g.ldb = widths[l + 1];
-            g.C = act[l + 1]; g.ldc = widths[l + 1];
-            g.bias = cp->bias[l];
-            g.a_swish = l > 0;
-            g.I = Mb; g.J = widths[l + 1]; g.R = widths[l];
-            if (int rc = launch_gemm(st, 0, g)) return rc;
-        }
-        // spline VJP: Theta -> dTheta in place, gx for all columns
-        {
+        if (fused) {
+            // BatchNorm, the conditioner (tensor cores, theta in tensor memory) and the spline VJP in one kernel:
+            // writes H0, the pre-activations, the cotangent of theta and gx
+            if (int rc = coupling_vjp_run(st, cp, D, C, pack, x_in + m0 * D, c ? c + m0 * C : nullptr, gy + m0 * D, gy_rot, glp + m0,
+                                          Mb, gx + m0 * D, act[0], &act[1], act[L + 1], TW))
+                return rc;
+        } else {
+            bn_apply_kernel<<<grid_for(Mb * F, 256 * 8, 148 * 16), 256, 0, st>>>(x_in + m0 * D, c ? c + m0 * C : nullptr, Mb, D, C,
+                                                                                 cp->bn_scale, cp->bn_bias, cp->bn_mean,
+                                                                                 cp->bn_var, act[0]);
+            count_launch();
+            // forward recompute: Z_{l+1} = act(Z_l) W_l + b_l   (pre-activations are stored)
+            for (int l = 0; l <= L; ++l) {
+                GemmArgs g{};
+                g.A = act[l]; g.lda = widths[l];
+                g.B = cp->kernel[l]; g.ldb = widths[l + 1];
+                g.C = act[l + 1]; g.ldc = widths[l + 1];
+                g.bias = cp->bias[l];
+                g.a_swish = l > 0;
+                g.I = Mb; g.J = widths[l + 1]; g.R = widths[l];
+                if (int rc = launch_gemm(st, 0, g)) return rc;
+            }
+            // spline VJP: Theta -> dTheta in place, gx for all columns
             SplineBwdArgs a{};
             a.theta = act[L + 1]; a.x_in = x_in; a.gy = gy; a.glp = glp; a.gx = gx;
             a.m0 = m0; a.Mb = Mb; a.D = D; a.d = d; a.K = K; a.rot = ((gy_rot % D) + D) % D; a.TS = TS;
@@ -870,19 +820,20 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             sp_kernel<<<(unsigned)std::min<long long>(tiles, (long long)di.sm_count * sp_bps), 256, sp_smem, st>>>(a);
             count_launch();
         }
-        // backward through the dense layers
+        // backward through the dense layers (fused path: the last one in the padded column space)
         for (int l = L; l >= 0; --l) {
+            const bool padded = fused && l == L;
             GemmArgs gw{};  // dW_l += act(Z_l)^T dZ_{l+1}; db_l += colsum(dZ_{l+1})
             gw.A = act[l]; gw.lda = widths[l];
             gw.B = act[l + 1]; gw.ldb = widths[l + 1];
-            gw.C = gr->kernel[l]; gw.ldc = widths[l + 1];
-            gw.colsum = gr->bias[l];
+            gw.C = padded ? gWp : gr->kernel[l]; gw.ldc = widths[l + 1];
+            gw.colsum = padded ? gbp : gr->bias[l];
             gw.a_swish = l > 0;
             gw.I = widths[l]; gw.J = widths[l + 1]; gw.R = Mb; gw.r_slab = 2048;
             if (int rc = launch_gemm(st, 2, gw)) return rc;
             GemmArgs ga{};  // dZ_l = (dZ_{l+1} W_l^T) * swish'(Z_l)   (l = 0: d/d(BN output), no activation)
             ga.A = act[l + 1]; ga.lda = widths[l + 1];
-            ga.B = cp->kernel[l]; ga.ldb = widths[l + 1];
+            ga.B = padded ? Wp : cp->kernel[l]; ga.ldb = widths[l + 1];
             ga.C = (l == 0) ? gh0 + m0 * F : act[l]; ga.ldc = widths[l];
             ga.Z = (l == 0) ? nullptr : act[l]; ga.ldz = widths[l];
             ga.I = Mb; ga.J = widths[l]; ga.R = widths[l + 1];
@@ -891,6 +842,11 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
         const int R = 256 / F;
         bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(
             x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
+        count_launch();
+    }
+    if (fused) {
+        unpad_add_kernel<<<grid_for((long long)(widths[L] + 1) * d * P, 256, 148 * 4), 256, 0, st>>>(gWp, gbp, widths[L], d, P, NL,
+                                                                                               gr->kernel[L], gr->bias[L]);
         count_launch();
     }
     ZF_CUDA_CHECK(cudaGetLastError());

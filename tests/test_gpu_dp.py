@@ -125,7 +125,10 @@ def _run(backend, devices):
             res = got[r]
             assert abs(res[f"loss{it}"] - loss) <= 1e-6 * abs(loss), (it, r, res[f"loss{it}"], loss)
             eg = np.abs(res[f"G{it}"] - G).max() / np.abs(G).max()
-            assert eg <= 1e-6, f"step {it} rank {r}: flat gradient differs by {eg:.2e} of its largest entry"
+            # step 0: identical parameters on both sides, only the summation order of the all-reduced sums differs.
+            # step 1 starts from parameters that already differ by the amplified last bits noted below (up to 2e-5
+            # of the largest weight), so its gradient can only be expected to agree to a few 1e-6.
+            assert eg <= (1e-6 if it == 0 else 5e-6), f"step {it} rank {r}: flat gradient differs by {eg:.2e} of its largest entry"
             np.testing.assert_allclose(res[f"S{it}"], S, rtol=1e-6, atol=1e-7)
             # NAdamW divides by sqrt(nu): entries with tiny gradients amplify the last-bit differences
             assert np.abs(res[f"P{it}"] - P).max() <= 2e-5 * np.abs(P).max()

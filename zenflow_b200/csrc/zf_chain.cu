@@ -737,6 +737,43 @@ __device__ __forceinline__ void spline_row_other_half(uint32_t dbase, uint32_t c
     rqs_block_slopes<KT>(ps, b.idx, b.dk, b.dkp1);
 }
 
+// ---- VJP row of the fused train kernel: theta from tensor memory -> cotangent of theta in this thread's row buffer
+// (row[0, 3 KT - 1), row[3 KT - 1] = 0).  Fast path: theta stays in registers (rqs_row_vjp_regs); rows with
+// |theta| >= kThetaFastBound, inf or NaN go through the IEEE path on the row buffer (rqs_row_backward).
+template <int KT, class Release>
+__device__ __forceinline__ float vjp_row_tmem(uint32_t dbase, const float* __restrict__ bias, float* row, float x, float gy,
+                                              float gld, Release release) {
+    const KnotNorm kn = make_knot_norm(KT);
+    float pa[KT], pb[KT], wa[KT], wb[KT];
+    theta_block_issue<KT>(dbase, TC_XOFF, 0, pa, wa);
+    theta_block_issue<KT>(dbase, TC_XOFF, KT, pb, wb);
+    umma::wait_ld();
+    const float amax_w = theta_block_finish<KT>(0, bias, pa, wa);
+    const float amax_h = theta_block_finish<KT>(KT, bias, pb, wb);
+    theta_block_issue<KT>(dbase, TC_XOFF, 2 * KT, wa, wb);       // slopes: main in wa, cross in wb
+    umma::wait_ld();
+    release();                                                    // every TMEM read of this row is done
+    float amax_s = 0.f;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+        wa[j] = fmaf(wb[j], umma::kF16LoUnscale, wa[j]) + bias[2 * KT + j];
+        if (j < KT - 1) amax_s = fmaxf(amax_s, fabsf(wa[j]));
+    }
+    const bool slow = !(fmaxf(fmaxf(amax_w, amax_h), amax_s) < kThetaFastBound) || !(amax_s == amax_s);
+    if (__any_sync(0xffffffffu, slow)) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) { row[j] = pa[j]; row[KT + j] = pb[j]; row[2 * KT + j] = wa[j]; }
+        const float g = rqs_row_backward<KT>(row, KT, x, gy, gld, kn);
+        row[3 * KT - 1] = 0.f;
+        return g;
+    }
+#pragma unroll
+    for (int j = 0; j < KT - 1; ++j) row[j] = wa[j];
+    const float g = rqs_row_vjp_regs<KT>(pa, pb, row, x, gy, gld, kn);
+    row[3 * KT - 1] = 0.f;
+    return g;
+}
+
 // ---- the epilogue / SIMT role of the tensor-core chain kernel ------------------------------------------------
 // NG column groups of 4 warps each (group g = warp / 4 owns CW = 32 / NG columns of every 32-column K-chunk and
 // every NG-th feature / bounded column); TMEM lane quarter = warp % 4 (hardware rule).  Spline rows are run by
@@ -993,38 +1030,47 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             if (VJP) {
                 // theta row -> this thread's row buffer in shared memory -> cotangent of theta in place (zf_vjp.cuh)
                 // -> global, one transformed dim per column group at a time
-                float* row = reinterpret_cast<float*>(cx.scratch) + ((size_t)half * UM + m) * VJP_ROW;
+                float* wrows = reinterpret_cast<float*>(cx.scratch) + ((size_t)half * UM + q * 32) * VJP_ROW;   // this warp's 32 rows
+                float* row = wrows + lane * VJP_ROW;
                 const KnotNorm kn = make_knot_norm(K);
                 const float gld = m < nm ? a.glp[m0 + m] : 0.f;
+                float gy_next = (half < d && m < nm) ? a.gy[(m0 + m) * D + pmod(half + a.gy_rot, D)] : 0.f;
                 for (int jj = half; jj < d; jj += 2) {
+                    const float gyv = gy_next;
+                    if (jj + 2 < d && m < nm) gy_next = a.gy[(m0 + m) * D + pmod(jj + 2 + a.gy_rot, D)];   // under this row's work
                     mbar_wait(&bars[B_DFULL_D + half], p_fd);
                     p_fd ^= 1u;
                     umma::fence_after_sync();
                     const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(half));
-                    const float* bj = bls + jj * NL;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < NL; c0 += 16) {
-                        float pm[16], pc[16];
-                        umma::ld16(dbase + c0, pm);
-                        umma::ld16(dbase + TC_XOFF + c0, pc);
-                        umma::wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) row[c0 + j] = fmaf(pc[j], umma::kF16LoUnscale, pm[j]) + bj[c0 + j];
-                    }
-                    umma::fence_before_sync();
-                    umma::mbar_arrive(&bars[B_DEMPTY_D + half]);   // every TMEM read of this row is done
+                    auto release = [&]() {
+                        umma::fence_before_sync();
+                        umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                    };
                     const float xv = xs[pmod(jj - rot, D) * UM + m];
-                    const float gyv = m < nm ? a.gy[(m0 + m) * D + pmod(jj + a.gy_rot, D)] : 0.f;
                     float g_x;
-                    if (K == 16) g_x = rqs_row_backward<16>(row, K, xv, gyv, gld, kn);
-                    else g_x = rqs_row_backward<32>(row, K, xv, gyv, gld, kn);
-                    row[P] = 0.f;   // padding column of the NL-wide block
-                    if (m < nm) {
-                        float4* dst = reinterpret_cast<float4*>(a.dtheta + (m0 + m) * a.ldt + jj * NL);
-                        for (int q4 = 0; q4 < NL / 4; ++q4)
-                            dst[q4] = make_float4(row[4 * q4], row[4 * q4 + 1], row[4 * q4 + 2], row[4 * q4 + 3]);
-                        a.gx[(m0 + m) * D + jj] = g_x;
+                    if (K == 16) g_x = vjp_row_tmem<16>(dbase, bls + jj * NL, row, xv, gyv, gld, release);
+                    else g_x = vjp_row_tmem<32>(dbase, bls + jj * NL, row, xv, gyv, gld, release);
+                    if (m < nm) a.gx[(m0 + m) * D + jj] = g_x;
+                    // the warp writes its 32 rows out together: lane l takes floats l, l + 32, l + 64 of every row
+                    // (conflict-free reads, 128 contiguous bytes per store instruction)
+                    __syncwarp();
+                    {
+                        const int rmax = min(32, nm - q * 32);
+                        float* dst = a.dtheta + (m0 + q * 32) * a.ldt + jj * NL + lane;
+                        for (int r = 0; r < rmax; ++r) {
+                            const float* rr = wrows + r * VJP_ROW + lane;
+                            float* dr = dst + (size_t)r * a.ldt;
+                            if (NL == 96) {
+                                const float v0 = rr[0], v1 = rr[32], v2 = rr[64];
+                                dr[0] = v0; dr[32] = v1; dr[64] = v2;
+                            } else {
+                                const float v0 = rr[0];
+                                dr[0] = v0;
+                                if (lane < NL - 32) dr[32] = rr[32];
+                            }
+                        }
                     }
+                    __syncwarp();   // the rows are rewritten by the next dim's theta
                 }
             } else if (!HELPER && d == 1 && half < 2) {
                 // one transformed dim: the two spline groups share its row (see spline_row_search_half)

@@ -232,10 +232,12 @@ struct ChainArgs {
     const float* gy;    // (M, D) cotangent of the coupling's output; logical column j is read at (j + gy_rot) % D
     const float* glp;   // (M,) cotangent of the log-det
     float* gx;          // (M, D) out: d/dx of the transformed columns, pass-through cotangent of the others
-    float* act_h0;      // (M, F) out: BatchNorm output
-    float* act_z[ZF_MAX_LAYERS];   // (M, 128) out: pre-activations of the hidden layers
-    float* dtheta;      // (M, ldt) out: cotangent of theta, dim j in columns [j NL, j NL + 3K-1), padding zero
-    int ldt, gy_rot;
+    // outputs for the Dense VJPs, as event-row images (bf16 x 2, csrc/zf_img_gemm.cu) of whole 128-event tiles
+    char* img_h0;       // width wh0: BatchNorm output, feature F = 1 (the bias column), zero padding
+    char* img_act[ZF_MAX_LAYERS];   // width 128: swish of the hidden pre-activations
+    float* act_g[ZF_MAX_LAYERS];    // (M, 128) fp32: swish' of the hidden pre-activations
+    char* img_dtheta;   // width d NL: cotangent of theta, dim j in columns [j NL, j NL + 3K-1), padding zero
+    int wh0, gy_rot;
 };
 
 // bin index of event m, coupling s.cidx, transformed dim jj (zf_chain_bin_indices)
@@ -737,6 +739,42 @@ __device__ __forceinline__ void spline_row_other_half(uint32_t dbase, uint32_t c
     rqs_block_slopes<KT>(ps, b.idx, b.dk, b.dkp1);
 }
 
+// Activation phase of the VJP kernel: swish for the next GEMM (fp16 x 3 split into tensor memory, as in the eval
+// kernels) plus what the Dense VJPs need of this layer: the activations as an event-row image (bf16 x 2) and
+// swish' of the pre-activations (fp32).  Rows beyond the batch are written as zeros.
+template <int CW>
+__device__ __forceinline__ void vjp_activation(const ChainArgs& a, int layer, long long tile, long long m0, int m, int nm, int n0,
+                                               const float (&z)[CW], uint32_t (&ahi)[CW / 2], uint32_t (&alo)[CW / 2]) {
+    float sw[CW], gs[CW];
+    const bool valid = m < nm;
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z[j] * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        sw[j] = z[j] * r;                       // swish(z) = z sigmoid(z)
+        gs[j] = fmaf(sw[j], 1.0f - r, r);       // swish'(z) = sigmoid(z) (1 + z (1 - sigmoid(z)))
+    }
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) umma::split_f16x2(sw[2 * i], sw[2 * i + 1], ahi[i], alo[i]);
+    if (valid) {
+        float4* go = reinterpret_cast<float4*>(a.act_g[layer] + (m0 + m) * 128 + n0);
+#pragma unroll
+        for (int g4 = 0; g4 < CW / 4; ++g4) go[g4] = make_float4(gs[g4 * 4], gs[g4 * 4 + 1], gs[g4 * 4 + 2], gs[g4 * 4 + 3]);
+    }
+    char* it = a.img_act[layer] + (size_t)tile * 2 * 128 * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16;
+#pragma unroll
+    for (int u = 0; u < CW / 8; ++u) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2)
+            umma::split_bf16x2(valid ? sw[8 * u + 2 * q2] : 0.f, valid ? sw[8 * u + 2 * q2 + 1] : 0.f, hi[q2], lo[q2]);
+        char* dst = it + (size_t)((n0 >> 3) + u) * 2048;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + 128 * 256) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // ---- VJP row of the fused train kernel: theta from tensor memory -> cotangent of theta in this thread's row buffer
 // (row[0, 3 KT - 1), row[3 KT - 1] = 0).  Fast path: theta stays in registers (rqs_row_vjp_regs); rows with
 // |theta| >= kThetaFastBound, inf or NaN go through the IEEE path on the row buffer (rqs_row_backward).
@@ -909,9 +947,21 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             if (VJP) {
                 // BatchNorm output for the grad-weight GEMM of the first Dense; the conditioning columns' cotangent
                 // passes through unchanged (d y[:, j] / d x[:, j] = 1, bijectors.py:364)
-                for (int e = tid; e < nm * F; e += ET) {
-                    const int mm = e / F, f = e - mm * F;
-                    a.act_h0[(m0 + mm) * F + f] = hs[f * UM + mm];
+                {
+                    char* ht = a.img_h0 + (size_t)tile * 2 * a.wh0 * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16;
+                    for (int g8 = half; g8 < (a.wh0 >> 3); g8 += NG) {
+                        float hv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int f = g8 * 8 + i;
+                            hv[i] = (m < nm) ? (f < F ? hs[f * UM + m] : (f == F ? 1.0f : 0.f)) : 0.f;
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int q2 = 0; q2 < 4; ++q2) umma::split_bf16x2(hv[2 * q2], hv[2 * q2 + 1], hi[q2], lo[q2]);
+                        *reinterpret_cast<uint4*>(ht + (size_t)g8 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(ht + (size_t)a.wh0 * 256 + (size_t)g8 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
                 }
                 const int nc = D - d;
                 for (int e = tid; e < nm * nc; e += ET) {
@@ -954,12 +1004,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 for (int f = 0; f < 4; ++f)
                     if (f < F) fma_row(hreg[f], f);
                 for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
-                if (VJP && m < nm) {
-                    float4* zo = reinterpret_cast<float4*>(a.act_z[0] + (m0 + m) * 128 + n0);
-#pragma unroll
-                    for (int g4 = 0; g4 < CW / 4; ++g4) zo[g4] = make_float4(acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2], acc[g4 * 4 + 3]);
-                }
-                activation_compute<CW>(acc, ahi, alo);
+                if (VJP) vjp_activation<CW>(a, 0, tile, m0, m, nm, n0, acc, ahi, alo);
+                else activation_compute<CW>(acc, ahi, alo);
 #ifdef ZF_TRACE_FINE
                 asm volatile("" :: "f"(ahi[0]), "f"(alo[CW - 1]) : "memory");
                 ZF_TR(trs);
@@ -1012,12 +1058,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                         tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + n0 + 32), vn);
                         tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
                     }
-                    if (VJP && m < nm) {
-                        float4* zo = reinterpret_cast<float4*>(a.act_z[l] + (m0 + m) * 128 + n0);
-#pragma unroll
-                        for (int g4 = 0; g4 < CW / 4; ++g4) zo[g4] = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
-                    }
-                    activation_compute<CW>(v, ahi, alo);
+                    if (VJP) vjp_activation<CW>(a, l, tile, m0, m, nm, n0, v, ahi, alo);
+                    else activation_compute<CW>(v, ahi, alo);
                     activation_store<CW>(tb, lane_base, n0, ahi, alo);
                     umma::wait_st();
                     umma::fence_before_sync();
@@ -1051,26 +1093,21 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     if (K == 16) g_x = vjp_row_tmem<16>(dbase, bls + jj * NL, row, xv, gyv, gld, release);
                     else g_x = vjp_row_tmem<32>(dbase, bls + jj * NL, row, xv, gyv, gld, release);
                     if (m < nm) a.gx[(m0 + m) * D + jj] = g_x;
-                    // the warp writes its 32 rows out together: lane l takes floats l, l + 32, l + 64 of every row
-                    // (conflict-free reads, 128 contiguous bytes per store instruction)
-                    __syncwarp();
-                    {
-                        const int rmax = min(32, nm - q * 32);
-                        float* dst = a.dtheta + (m0 + q * 32) * a.ldt + jj * NL + lane;
-                        for (int r = 0; r < rmax; ++r) {
-                            const float* rr = wrows + r * VJP_ROW + lane;
-                            float* dr = dst + (size_t)r * a.ldt;
-                            if (NL == 96) {
-                                const float v0 = rr[0], v1 = rr[32], v2 = rr[64];
-                                dr[0] = v0; dr[32] = v1; dr[64] = v2;
-                            } else {
-                                const float v0 = rr[0];
-                                dr[0] = v0;
-                                if (lane < NL - 32) dr[32] = rr[32];
-                            }
+                    {   // this thread's row -> the event-row image: 16-byte units of 8 columns, hi and lo parts; the 32 lanes of a
+                        // warp write 512 contiguous bytes per unit
+                        const int TW = d * NL;
+                        char* dt = a.img_dtheta + (size_t)tile * 2 * TW * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16 +
+                                   (size_t)(jj * NL >> 3) * 2048;
+                        const bool valid = m < nm;
+                        for (int u = 0; u < (NL >> 3); ++u) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int q2 = 0; q2 < 4; ++q2)
+                                umma::split_bf16x2(valid ? row[8 * u + 2 * q2] : 0.f, valid ? row[8 * u + 2 * q2 + 1] : 0.f, hi[q2], lo[q2]);
+                            *reinterpret_cast<uint4*>(dt + (size_t)u * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(dt + (size_t)TW * 256 + (size_t)u * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
-                    __syncwarp();   // the rows are rewritten by the next dim's theta
                 }
             } else if (!HELPER && d == 1 && half < 2) {
                 // one transformed dim: the two spline groups share its row (see spline_row_search_half)
@@ -2271,8 +2308,8 @@ int coupling_vjp_pack(cudaStream_t stream, const zf_coupling* cp, int D, int C, 
 }
 
 int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, const float* ws, const float* x_in, const float* c,
-                     const float* gy, int gy_rot, const float* glp, long long M, float* gx, float* act_h0, float* const* act_z,
-                     float* dtheta, int ldt) {
+                     const float* gy, int gy_rot, const float* glp, long long M, float* gx, void* img_h0, int wh0, void* const* img_act,
+                     float* const* act_g, void* img_dtheta) {
     Plan plan;
     zf_op op;
     zf_chain chain;
@@ -2287,12 +2324,17 @@ int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, c
     a.mode = kModeVjp;
     a.n_couplings = 1;
     a.u_fmax = plan.Fmax; a.u_hmax = plan.Hmax; a.u_blmax = plan.BLmax;
-    a.gy = gy; a.glp = glp; a.gx = gx; a.act_h0 = act_h0; a.dtheta = dtheta; a.ldt = ldt;
+    a.gy = gy; a.glp = glp; a.gx = gx;
+    a.img_h0 = static_cast<char*>(img_h0); a.wh0 = wh0; a.img_dtheta = static_cast<char*>(img_dtheta);
     a.gy_rot = ((gy_rot % D) + D) % D;
-    for (int l = 0; l < cp->n_hidden; ++l) a.act_z[l] = act_z[l];
-    ZF_REQUIRE((reinterpret_cast<uintptr_t>(dtheta) & 15) == 0 && (ldt & 3) == 0, "coupling_vjp: dtheta must be 16-byte aligned");
-    for (int l = 0; l < cp->n_hidden; ++l)
-        ZF_REQUIRE((reinterpret_cast<uintptr_t>(act_z[l]) & 15) == 0, "coupling_vjp: activations must be 16-byte aligned");
+    ZF_REQUIRE((reinterpret_cast<uintptr_t>(img_h0) & 15) == 0 && (reinterpret_cast<uintptr_t>(img_dtheta) & 15) == 0 && wh0 % 16 == 0,
+               "coupling_vjp: images must be 16-byte aligned");
+    for (int l = 0; l < cp->n_hidden; ++l) {
+        a.img_act[l] = static_cast<char*>(img_act[l]);
+        a.act_g[l] = act_g[l];
+        ZF_REQUIRE(((reinterpret_cast<uintptr_t>(img_act[l]) | reinterpret_cast<uintptr_t>(act_g[l])) & 15) == 0,
+                   "coupling_vjp: images must be 16-byte aligned");
+    }
     const size_t smem = umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true) * sizeof(float);
     static std::mutex mu;
     static std::map<int, size_t> done;

@@ -666,57 +666,77 @@ extern "C" int zf_flow_loss_grad(void* stream, int32_t latent_kind, float peakne
     return zf_flow_loss_grad_ct(stream, latent_kind, peakness, z, log_det, M, D, global_count, nullptr, lp, gz, glp, lp_sum);
 }
 
-// tensor-core path (zf_chain.cu): conditioner recompute + spline VJP in one kernel, theta never leaves the SM
+// tensor-core path: conditioner recompute + spline VJP in one kernel (zf_chain.cu), Dense VJPs on event-row images
+// (zf_img_gemm.cu)
 namespace zf {
 size_t coupling_vjp_ws_floats(const zf_coupling* cp, int D, int C);
 int coupling_vjp_pack(cudaStream_t stream, const zf_coupling* cp, int D, int C, float* ws);
 int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, const float* ws, const float* x_in, const float* c,
-                     const float* gy, int gy_rot, const float* glp, long long M, float* gx, float* act_h0, float* const* act_z,
-                     float* dtheta, int ldt);
+                     const float* gy, int gy_rot, const float* glp, long long M, float* gx, void* img_h0, int wh0, void* const* img_act,
+                     float* const* act_g, void* img_dtheta);
+size_t img_bytes(long long M, int W);
+size_t w_image_bytes(int N, int KW);
+int pack_w_image(cudaStream_t st, const float* W, int ldw, int n_valid, int N, int KW, int P, int NL, void* img);
+int launch_img_nt(cudaStream_t st, const void* X, int KW, const void* Wimg, int N, const float* G, int ldg, void* out_img,
+                  float* out_f32, int ldo, int n_valid, long long M);
+int launch_img_tn(cudaStream_t st, const void* A, const void* B, int WB, float* C, long long ldca, long long ldcb, int a_valid,
+                  int b_valid, float* colsum, float* arow_sum, int arow_col, long long M);
 }  // namespace zf
 
-// Workspace of zf_coupling_backward.  Fused path: the cotangent of theta is kept with each dim's 3K-1 columns padded
-// to NL = a multiple of 16 (rows of 16-byte multiples for the kernel's vector stores), and the last Dense is
-// differentiated in that padded column space: [packed parameters | W_L padded | dW_L padded | db_L padded], then per
-// micro-batch H0 | Z_1 .. Z_L | dTheta.
+// Workspace of zf_coupling_backward.
+// Fused path (hidden width 128, K in {16, 32}: the tensor-core kernels): the cotangent of theta has each dim's 3K-1
+// columns padded to NL = a multiple of 16 and the last Dense is differentiated in that padded column space.
+//   fixed   [packed parameters | weight images of every Dense | dW_L padded | db_L padded]
+//   per micro-batch   images: dTheta, swish(Z_l), H0 (+ bias column), two dZ buffers;  fp32: swish'(Z_l)
+// Otherwise: per micro-batch H0 | Z_1 .. Z_L | Theta in fp32.
 struct CplBwdLayout {
     bool fused;
-    int NL;               // columns per transformed dim in the theta / dTheta block
-    size_t pack_floats;   // packed parameters of the fused kernel
-    size_t fixed_floats;  // everything that does not scale with the micro-batch
-    size_t per_sample;
+    int NL, TW, WH, WF0;  // columns per dim / of the theta block; widths of the H0 image and of the first Dense's weight image
+    size_t pack_floats;
+    size_t fixed_bytes;
+    size_t off_wimg[ZF_MAX_LAYERS + 1], off_gwp, off_gbp;
 };
+static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 static CplBwdLayout cpl_bwd_layout(const zf_coupling* cp, int D, int C) {
     const int d = D / 2, F = D - d + C, P = 3 * cp->knots - 1, L = cp->n_hidden;
     CplBwdLayout lay{};
     lay.pack_floats = coupling_vjp_ws_floats(cp, D, C);
     lay.fused = lay.pack_floats > 0;
     lay.NL = lay.fused ? (P + 15) / 16 * 16 : P;
-    size_t n = F;
-    for (int l = 0; l < L; ++l) n += cp->hidden[l];
-    n += (size_t)d * lay.NL;
-    lay.per_sample = n;
+    lay.TW = d * lay.NL;
+    lay.WH = (F + 1 + 15) / 16 * 16;
+    lay.WF0 = (F + 15) / 16 * 16;
     if (lay.fused) {
-        const size_t wl = (size_t)cp->hidden[L - 1] * d * lay.NL;
-        lay.fixed_floats = (lay.pack_floats + 63) / 64 * 64 + 2 * wl + (size_t)(d * lay.NL + 63) / 64 * 64;
+        size_t off = up256(lay.pack_floats * 4);
+        for (int l = 0; l <= L; ++l) {
+            lay.off_wimg[l] = off;
+            off += up256(l == 0 ? zf::w_image_bytes(lay.WF0, 128) : l == L ? zf::w_image_bytes(128, lay.TW) : zf::w_image_bytes(128, 128));
+        }
+        lay.off_gwp = off; off += up256((size_t)128 * lay.TW * 4);
+        lay.off_gbp = off; off += up256((size_t)lay.TW * 4);
+        lay.fixed_bytes = off;
     }
     return lay;
+}
+static size_t cpl_bwd_batch_bytes(const zf_coupling* cp, const CplBwdLayout& lay, int D, int C, long long Mb) {
+    const int d = D / 2, F = D - d + C, L = cp->n_hidden;
+    if (!lay.fused) {
+        size_t n = F;
+        for (int l = 0; l < L; ++l) n += cp->hidden[l];
+        n += (size_t)d * lay.NL;
+        return (n * (size_t)Mb + 64) * sizeof(float);
+    }
+    size_t b = up256(zf::img_bytes(Mb, lay.TW)) + up256(zf::img_bytes(Mb, lay.WH)) + 2 * up256(zf::img_bytes(Mb, 128));
+    b += (size_t)L * (up256(zf::img_bytes(Mb, 128)) + up256((size_t)Mb * 128 * 4));
+    return b;
 }
 
 extern "C" size_t zf_coupling_backward_workspace_bytes(const zf_coupling* cp, int32_t D, int32_t C, int64_t micro_batch) {
     if (!cp || D < 2 || micro_batch < 1) return 0;
     const CplBwdLayout lay = cpl_bwd_layout(cp, D, C);
-    return (lay.fixed_floats + lay.per_sample * (size_t)micro_batch + 64) * sizeof(float);
+    return lay.fixed_bytes + cpl_bwd_batch_bytes(cp, lay, D, C, micro_batch) + 256;
 }
 
-// W (Hin, d P) -> Wp (Hin, d NL), zero padded per dim
-__global__ void __launch_bounds__(256) pad_last_layer_kernel(const float* __restrict__ W, int Hin, int d, int P, int NL, float* __restrict__ Wp) {
-    const int n = Hin * d * NL;
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
-        const int h = e / (d * NL), r = e - h * (d * NL), jj = r / NL, p = r - jj * NL;
-        Wp[e] = p < P ? W[(size_t)h * d * P + jj * P + p] : 0.f;
-    }
-}
 // gW (Hin, d P) += gWp (Hin, d NL) without the padding; gb (d P) += gbp (d NL)
 __global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict__ gWp, const float* __restrict__ gbp, int Hin, int d, int P,
                                                         int NL, float* __restrict__ gW, float* __restrict__ gb) {
@@ -728,6 +748,66 @@ __global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict_
     }
 }
 
+// Fused path of zf_coupling_backward (see CplBwdLayout).
+static int coupling_backward_fused(cudaStream_t st, const zf_coupling* cp, const zf_coupling_grads* gr, int D, int C, const float* x_in,
+                                   const float* c, const float* gy, int gy_rot, const float* glp, long long M, float* gx, float* gh0,
+                                   double* bn_sums, char* ws, long long micro_batch, const CplBwdLayout& lay) {
+    const int d = D / 2, F = D - d + C, K = cp->knots, P = 3 * K - 1, L = cp->n_hidden, NL = lay.NL, TW = lay.TW;
+    float* pack = reinterpret_cast<float*>(ws);
+    float* gWp = reinterpret_cast<float*>(ws + lay.off_gwp);
+    float* gbp = reinterpret_cast<float*>(ws + lay.off_gbp);
+    if (int rc = coupling_vjp_pack(st, cp, D, C, pack)) return rc;
+    for (int l = 0; l <= L; ++l) {   // Dense_l kernel (in, out) as the image [n = in][k = out]
+        int rc;
+        if (l == 0) rc = pack_w_image(st, cp->kernel[0], 128, F, lay.WF0, 128, 128, 128, ws + lay.off_wimg[0]);
+        else if (l == L) rc = pack_w_image(st, cp->kernel[L], d * P, 128, 128, TW, P, NL, ws + lay.off_wimg[L]);
+        else rc = pack_w_image(st, cp->kernel[l], 128, 128, 128, 128, 128, 128, ws + lay.off_wimg[l]);
+        if (rc) return rc;
+    }
+    ZF_CUDA_CHECK(cudaMemsetAsync(gWp, 0, lay.fixed_bytes - lay.off_gwp, st));
+    char* wb = ws + lay.fixed_bytes;
+    for (long long m0 = 0; m0 < M; m0 += micro_batch) {
+        const long long Mb = std::min<long long>(micro_batch, M - m0);
+        char* p = wb;
+        auto take = [&](size_t bytes) { char* o = p; p += up256(bytes); return o; };
+        void* img_dt = take(img_bytes(Mb, TW));
+        void* img_h0 = take(img_bytes(Mb, lay.WH));
+        void* img_dz[2] = {take(img_bytes(Mb, 128)), take(img_bytes(Mb, 128))};
+        void* img_act[ZF_MAX_LAYERS];
+        float* act_g[ZF_MAX_LAYERS];
+        for (int l = 0; l < L; ++l) {
+            img_act[l] = take(img_bytes(Mb, 128));
+            act_g[l] = reinterpret_cast<float*>(take((size_t)Mb * 128 * 4));
+        }
+        // BatchNorm, conditioner (theta in tensor memory), spline VJP: writes gx and the images
+        if (int rc = coupling_vjp_run(st, cp, D, C, pack, x_in + m0 * D, c ? c + m0 * C : nullptr, gy + m0 * D, gy_rot, glp + m0, Mb,
+                                      gx + m0 * D, img_h0, lay.WH, img_act, act_g, img_dt))
+            return rc;
+        // last Dense (padded column space): dW_L, db_L, dZ_L = (dTheta W_L^T) swish'(Z_L)
+        if (int rc = launch_img_tn(st, img_act[L - 1], img_dt, TW, gWp, TW, 1, 128, TW, gbp, nullptr, -1, Mb)) return rc;
+        if (int rc = launch_img_nt(st, img_dt, TW, ws + lay.off_wimg[L], 128, act_g[L - 1], 128, img_dz[0], nullptr, 0, 0, Mb)) return rc;
+        int cur = 0;
+        for (int l = L - 1; l >= 1; --l) {   // hidden Dense_l: input swish(Z_l), output cotangent dZ_{l+1}
+            if (int rc = launch_img_tn(st, img_act[l - 1], img_dz[cur], 128, gr->kernel[l], 128, 1, 128, 128, gr->bias[l], nullptr, -1, Mb))
+                return rc;
+            if (int rc = launch_img_nt(st, img_dz[cur], 128, ws + lay.off_wimg[l], 128, act_g[l - 1], 128, img_dz[cur ^ 1], nullptr, 0, 0, Mb))
+                return rc;
+            cur ^= 1;
+        }
+        // first Dense: dW_0[f][h] = sum_e H0[e][f] dZ_1[e][h] (transposed product; H0's bias column gives db_0), d/dH0
+        if (int rc = launch_img_tn(st, img_dz[cur], img_h0, lay.WH, gr->kernel[0], 1, 128, 128, F, nullptr, gr->bias[0], F, Mb)) return rc;
+        if (int rc = launch_img_nt(st, img_dz[cur], 128, ws + lay.off_wimg[0], lay.WF0, nullptr, 0, nullptr, gh0 + m0 * F, F, F, Mb)) return rc;
+        const int R = 256 / F;
+        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(
+            x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
+        count_launch();
+    }
+    unpad_add_kernel<<<grid_for((long long)(128 + 1) * d * P, 256, 148 * 4), 256, 0, st>>>(gWp, gbp, 128, d, P, NL, gr->kernel[L], gr->bias[L]);
+    count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
 extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const zf_coupling_grads* gr, int32_t D, int32_t C,
                                     const float* x_in, const float* c, const float* gy, int32_t gy_rot, const float* glp,
                                     int64_t M, float* gx, float* gh0, double* bn_sums, void* workspace,
@@ -737,47 +817,36 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
     ZF_REQUIRE(d > 0 && d < D && (C == 0 || c) && M >= 1 && micro_batch >= 1, "coupling_backward: bad shape");
     ZF_REQUIRE(F <= 256, "coupling_backward: at most 256 conditioner inputs");
     const int K = cp->knots, P = 3 * K - 1, L = cp->n_hidden;
-    CplBwdLayout lay = cpl_bwd_layout(cp, D, C);
-    if (workspace_bytes < (lay.fixed_floats + lay.per_sample * (size_t)micro_batch + 64) * sizeof(float))
+    const CplBwdLayout lay = cpl_bwd_layout(cp, D, C);
+    if (workspace_bytes < lay.fixed_bytes + cpl_bwd_batch_bytes(cp, lay, D, C, std::min<long long>(micro_batch, M)))
         return fail(ZF_ERR_WORKSPACE, "coupling_backward: workspace too small");
-    const bool fused = lay.fused && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
-    const int NL = lay.NL, TW = d * NL;   // theta block width
     cudaStream_t st = (cudaStream_t)stream;
+    ZF_CUDA_CHECK(cudaMemsetAsync(bn_sums, 0, 2 * F * sizeof(double), st));
+    if (lay.fused) {
+        ZF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "coupling_backward: workspace must be 256-byte aligned");
+        return coupling_backward_fused(st, cp, gr, D, C, x_in, c, gy, gy_rot, glp, M, gx, gh0, bn_sums, static_cast<char*>(workspace),
+                                       micro_batch, lay);
+    }
     DeviceInfo di;
     if (int rc = get_device_info(&di)) return rc;
 
-    // spline tile (unfused path): TS samples (multiple of 4) x d rows, ~256 rows; two or three ring stages
+    // spline tile: TS samples (multiple of 4) x d rows, ~256 rows; two or three ring stages
     int TS = std::max(4, (256 / d) & ~3);
     while (TS > 4 && (size_t)TS * d * P * 4 > 96 * 1024) TS -= 4;
     const size_t tile_bytes = (size_t)TS * d * P * 4;
     int sp_stages = (int)std::min<size_t>(3, ((size_t)di.max_smem_optin - 256) / tile_bytes);
     int sp_bps = 1;
     if (2 * (2 * tile_bytes + 256) + 2048 <= (size_t)di.max_smem_optin) { sp_stages = 2; sp_bps = 2; }
-    if (!fused && sp_stages < 1) return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
+    if (sp_stages < 1) return fail(ZF_ERR_UNSUPPORTED, "coupling_backward: spline tile does not fit shared memory");
     const size_t sp_smem = (size_t)sp_stages * tile_bytes + 64;
     auto sp_kernel = (K == 16) ? spline_bwd_kernel<16> : (K == 32) ? spline_bwd_kernel<32> : spline_bwd_kernel<0>;
-    if (!fused) ZF_CUDA_CHECK(cudaFuncSetAttribute(sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
 
-    ZF_CUDA_CHECK(cudaMemsetAsync(bn_sums, 0, 2 * F * sizeof(double), st));
     float* ws = static_cast<float*>(workspace);
     int widths[ZF_MAX_LAYERS + 2];
     widths[0] = F;
     for (int l = 0; l < L; ++l) widths[l + 1] = cp->hidden[l];
-    widths[L + 1] = fused ? TW : d * P;
-
-    float *pack = nullptr, *Wp = nullptr, *gWp = nullptr, *gbp = nullptr;
-    if (fused) {
-        const size_t wl = (size_t)widths[L] * TW;
-        pack = ws;
-        Wp = ws + (lay.pack_floats + 63) / 64 * 64;
-        gWp = Wp + wl;
-        gbp = gWp + wl;
-        ws += lay.fixed_floats;
-        if (int rc = coupling_vjp_pack(st, cp, D, C, pack)) return rc;
-        pad_last_layer_kernel<<<grid_for((long long)wl, 256, 148 * 4), 256, 0, st>>>(cp->kernel[L], widths[L], d, P, NL, Wp);
-        count_launch();
-        ZF_CUDA_CHECK(cudaMemsetAsync(gWp, 0, (wl + TW) * sizeof(float), st));
-    }
+    widths[L + 1] = d * P;
 
     for (long long m0 = 0; m0 < M; m0 += micro_batch) {
         const long long Mb = std::min<long long>(micro_batch, M - m0);
@@ -786,31 +855,25 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
         size_t off = 0;
         for (int l = 0; l <= L + 1; ++l) {
             act[l] = ws + off;
-            off += ((size_t)widths[l] * Mb + 3) / 4 * 4;
+            off += (size_t)widths[l] * Mb;
         }
-        if (fused) {
-            // BatchNorm, the conditioner (tensor cores, theta in tensor memory) and the spline VJP in one kernel:
-            // writes H0, the pre-activations, the cotangent of theta and gx
-            if (int rc = coupling_vjp_run(st, cp, D, C, pack, x_in + m0 * D, c ? c + m0 * C : nullptr, gy + m0 * D, gy_rot, glp + m0,
-                                          Mb, gx + m0 * D, act[0], &act[1], act[L + 1], TW))
-                return rc;
-        } else {
-            bn_apply_kernel<<<grid_for(Mb * F, 256 * 8, 148 * 16), 256, 0, st>>>(x_in + m0 * D, c ? c + m0 * C : nullptr, Mb, D, C,
-                                                                                 cp->bn_scale, cp->bn_bias, cp->bn_mean,
-                                                                                 cp->bn_var, act[0]);
-            count_launch();
-            // forward recompute: Z_{l+1} = act(Z_l) W_l + b_l   (pre-activations are stored)
-            for (int l = 0; l <= L; ++l) {
-                GemmArgs g{};
-                g.A = act[l]; g.lda = widths[l];
-                g.B = cp->kernel[l]; g.ldb = widths[l + 1];
-                g.C = act[l + 1]; g.ldc = widths[l + 1];
-                g.bias = cp->bias[l];
-                g.a_swish = l > 0;
-                g.I = Mb; g.J = widths[l + 1]; g.R = widths[l];
-                if (int rc = launch_gemm(st, 0, g)) return rc;
-            }
-            // spline VJP: Theta -> dTheta in place, gx for all columns
+        bn_apply_kernel<<<grid_for(Mb * F, 256 * 8, 148 * 16), 256, 0, st>>>(x_in + m0 * D, c ? c + m0 * C : nullptr, Mb, D, C,
+                                                                             cp->bn_scale, cp->bn_bias, cp->bn_mean,
+                                                                             cp->bn_var, act[0]);
+        count_launch();
+        // forward recompute: Z_{l+1} = act(Z_l) W_l + b_l   (pre-activations are stored)
+        for (int l = 0; l <= L; ++l) {
+            GemmArgs g{};
+            g.A = act[l]; g.lda = widths[l];
+            g.B = cp->kernel[l]; g.ldb = widths[l + 1];
+            g.C = act[l + 1]; g.ldc = widths[l + 1];
+            g.bias = cp->bias[l];
+            g.a_swish = l > 0;
+            g.I = Mb; g.J = widths[l + 1]; g.R = widths[l];
+            if (int rc = launch_gemm(st, 0, g)) return rc;
+        }
+        // spline VJP: Theta -> dTheta in place, gx for all columns
+        {
             SplineBwdArgs a{};
             a.theta = act[L + 1]; a.x_in = x_in; a.gy = gy; a.glp = glp; a.gx = gx;
             a.m0 = m0; a.Mb = Mb; a.D = D; a.d = d; a.K = K; a.rot = ((gy_rot % D) + D) % D; a.TS = TS;
@@ -820,20 +883,19 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             sp_kernel<<<(unsigned)std::min<long long>(tiles, (long long)di.sm_count * sp_bps), 256, sp_smem, st>>>(a);
             count_launch();
         }
-        // backward through the dense layers (fused path: the last one in the padded column space)
+        // backward through the dense layers
         for (int l = L; l >= 0; --l) {
-            const bool padded = fused && l == L;
             GemmArgs gw{};  // dW_l += act(Z_l)^T dZ_{l+1}; db_l += colsum(dZ_{l+1})
             gw.A = act[l]; gw.lda = widths[l];
             gw.B = act[l + 1]; gw.ldb = widths[l + 1];
-            gw.C = padded ? gWp : gr->kernel[l]; gw.ldc = widths[l + 1];
-            gw.colsum = padded ? gbp : gr->bias[l];
+            gw.C = gr->kernel[l]; gw.ldc = widths[l + 1];
+            gw.colsum = gr->bias[l];
             gw.a_swish = l > 0;
             gw.I = widths[l]; gw.J = widths[l + 1]; gw.R = Mb; gw.r_slab = 2048;
             if (int rc = launch_gemm(st, 2, gw)) return rc;
             GemmArgs ga{};  // dZ_l = (dZ_{l+1} W_l^T) * swish'(Z_l)   (l = 0: d/d(BN output), no activation)
             ga.A = act[l + 1]; ga.lda = widths[l + 1];
-            ga.B = padded ? Wp : cp->kernel[l]; ga.ldb = widths[l + 1];
+            ga.B = cp->kernel[l]; ga.ldb = widths[l + 1];
             ga.C = (l == 0) ? gh0 + m0 * F : act[l]; ga.ldc = widths[l];
             ga.Z = (l == 0) ? nullptr : act[l]; ga.ldz = widths[l];
             ga.I = Mb; ga.J = widths[l]; ga.R = widths[l + 1];
@@ -842,11 +904,6 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
         const int R = 256 / F;
         bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(
             x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
-        count_launch();
-    }
-    if (fused) {
-        unpad_add_kernel<<<grid_for((long long)(widths[L] + 1) * d * P, 256, 148 * 4), 256, 0, st>>>(gWp, gbp, widths[L], d, P, NL,
-                                                                                               gr->kernel[L], gr->bias[L]);
         count_launch();
     }
     ZF_CUDA_CHECK(cudaGetLastError());

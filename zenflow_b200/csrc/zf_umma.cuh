@@ -108,6 +108,39 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
         : "memory");
 }
+// ---- bf16 x 2 split (train-step GEMMs on event-row images) -------------------------------------------------
+// hi = x rounded to bf16, lo = (x - hi) rounded to bf16: 16 significant bits, fp32's exponent range (gradients as
+// small as 1 / global_count stay normal).  Products hi*hi + hi*lo + lo*hi on kind::f16 with bf16 operands.
+// idesc: a_format / b_format = 1 (bf16); a_mn / b_mn: the operand is MN-major in shared memory (bits 15 / 16).
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    // round-to-nearest-even bf16 of both, packed (x0 in the low half-word)
+    uint32_t h;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
+    uint32_t l;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
+    hi = h;
+    lo = l;
+}
+// D[tmem] (+)= A[smem] * B[smem]; K = 16 per instruction; issued by ONE thread
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u, z = 0u;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+        : "memory");
+}
+// half-word offset of element (r, k) of an R-row operand in an "event-row" image: [r/8][k/8][k%8][r%8] is the MN-major
+// reading of the same bytes a K-major image of the transposed operand has
+__host__ __device__ inline int mn_image_index_bf16(int r, int k, int Ktile) { return ((r >> 3) * (Ktile >> 3) + (k >> 3)) * 64 + (k & 7) * 8 + (r & 7); }
 // half-word offset of element (n, k) in an fp16 B image of N rows: [k/8][n/8][n%8][k%8]
 __host__ __device__ inline int b_image_index_f16(int n, int k, int N) { return ((k >> 3) * (N >> 3) + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7); }
 __device__ __forceinline__ void st8u(uint32_t a, const uint32_t (&v)[8]) {

@@ -161,6 +161,85 @@ __global__ void __launch_bounds__(160) umma_selftest_f16_kernel(const float* __r
 }
 }  // namespace zf
 
+// out[128][N] = A[128][K] * B[N][K]^T with the bf16 x 2 split, BOTH operands from shared memory, each either as a
+// K-major image ([k/8][r/8][r%8][k%8]) or as an MN-major one ([r/8][k/8][k%8][r%8]).  flags bit 0 / 1: A / B MN-major;
+// bit 2: descriptor probe - swap which of LBO / SBO carries the MN-direction stride of an MN-major operand.
+namespace zf {
+__global__ void __launch_bounds__(160) umma_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                 int N, int K, float* __restrict__ out, int flags) {
+    extern __shared__ __align__(128) float sraw[];
+    uint16_t* sA = reinterpret_cast<uint16_t*>(sraw);          // hi image then lo image, 128*K half-words each
+    uint16_t* sB = sA + 2 * 128 * K;                            // hi image then lo image, N*K each
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool a_mn = flags & 1, b_mn = flags & 2, swap = flags & 4;
+    if (warp == 4) umma::tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    auto put = [&](uint16_t* img, int R, bool mn, int r, int k, float x) {
+        uint32_t hi, lo;
+        umma::split_bf16x2(x, 0.f, hi, lo);
+        const int ii = mn ? umma::mn_image_index_bf16(r, k, K) : umma::b_image_index_f16(r, k, R);
+        img[ii] = (uint16_t)(hi & 0xffffu);
+        img[R * K + ii] = (uint16_t)(lo & 0xffffu);
+    };
+    for (int e = tid; e < 128 * K; e += blockDim.x) put(sA, 128, a_mn, e / K, e % K, A[e]);
+    for (int e = tid; e < N * K; e += blockDim.x) put(sB, N, b_mn, e / K, e % K, B[e]);
+    fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    if (warp == 4) {
+        if (umma::elect_one()) {
+            const uint32_t idesc = umma::instr_desc_bf16(N, a_mn, b_mn);
+            // operand of R rows: byte strides between core matrices along K and along MN, and the step of one MMA (K = 16)
+            auto desc = [&](uint32_t base, int R, bool mn, int ks) {
+                const uint32_t k_stride = mn ? 128u : (uint32_t)(R >> 3) * 128u;
+                const uint32_t mn_stride = mn ? (uint32_t)(K >> 3) * 128u : 128u;
+                const uint32_t lbo = (mn && swap) ? mn_stride : k_stride, sbo = (mn && swap) ? k_stride : mn_stride;
+                return umma::smem_desc_kmajor(base + (uint32_t)ks * 2u * k_stride, lbo, sbo);
+            };
+            const uint32_t ahi = smem_u32(sA), alo = smem_u32(sA + 128 * K), bhi = smem_u32(sB), blo = smem_u32(sB + N * K);
+            for (int ks = 0; ks < K / 16; ++ks) {
+                umma::mma_f16_ss(tb, desc(alo, 128, a_mn, ks), desc(bhi, N, b_mn, ks), idesc, ks > 0);
+                umma::mma_f16_ss(tb, desc(ahi, 128, a_mn, ks), desc(blo, N, b_mn, ks), idesc, true);
+                umma::mma_f16_ss(tb, desc(ahi, 128, a_mn, ks), desc(bhi, N, b_mn, ks), idesc, true);
+            }
+            umma::commit(&bar);
+        }
+        __syncwarp();
+    }
+    if (warp < 4) {
+        mbar_wait(&bar, 0);
+        umma::fence_after_sync();
+        const int m = warp * 32 + lane;
+        for (int n0 = 0; n0 < N; n0 += 8) {
+            float v[8];
+            umma::ld8(umma::taddr(tb, warp * 32, n0), v);
+            umma::wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) out[m * N + n0 + i] = v[i];
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) umma::tmem_dealloc(tb, 128);
+}
+}  // namespace zf
+
+extern "C" int zf_selftest_umma_bf16(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
+                                     int32_t flags) {
+    ZF_REQUIRE(A && B && out, "selftest_umma_bf16: null argument");
+    ZF_REQUIRE(N >= 16 && N <= 128 && N % 16 == 0 && K >= 16 && K <= 128 && K % 16 == 0, "selftest_umma_bf16: bad N/K");
+    const size_t smem = (size_t)2 * (128 + N) * K * sizeof(uint16_t);
+    ZF_CUDA_CHECK(cudaFuncSetAttribute(zf::umma_selftest_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    zf::umma_selftest_bf16_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, N, K, out, flags);
+    zf::count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
 extern "C" int zf_selftest_umma_f16(void* stream, const float* A, const float* B, int32_t N, int32_t K, float* out,
                                     int32_t variant) {
     ZF_REQUIRE(A && B && out, "selftest_umma_f16: null argument");

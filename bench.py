@@ -505,16 +505,17 @@ def run_gpu(args):
     roofline = {
         "kernel": ("chain_kernel<false>: fused conditioner MLPs (fp32 FFMA) + splines + latent" if simt else
                    ("chain_umma_pp_kernel<false>" if pp else "chain_umma_kernel<false>") +
-                   " (zf_flow_log_prob): conditioner GEMMs on tcgen05 (3xTF32, A in TMEM), "
+                   " (zf_flow_log_prob): conditioner GEMMs on tcgen05 (3xFP16 split on kind::f16, A in TMEM), "
                    "spline rows read theta from TMEM, latent fused" + ("; two tiles in flight" if pp else "")),
         "bound": "tensor", "achieved": tflops, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tflops / pk["bf16"],
         "traffic": ncu_traffic(args.workload, M), "flops_per_event": flops,
-        "note": "algorithmic fp32 flops (not x3 for the 3xTF32 split; kind::tf32 runs at half the bf16 rate, so the "
-                "tensor pipe executes 6 bf16-equivalents per algorithmic flop); achieved uses the whole step time "
+        "note": "algorithmic fp32 flops (not x3 for the 3xFP16 split: kind::f16 runs at the bf16 rate, so the tensor "
+                "pipe executes 3 bf16-equivalents per algorithmic flop); achieved uses the whole step time "
                 "(the pack launch included); peak = burst bf16 figure of MEASURED_PEAKS.json, the sustained one "
-                "gives frac_sustained; see DESIGN.md for what bounds the kernel",
+                "gives frac_sustained; see DESIGN.md for what bounds the kernel (tensor-memory read port + issue slots "
+                "of the spline rows, not the tensor pipe)",
         "frac_sustained": (tflops / pk["bf16_sustained"]) if pk.get("bf16_sustained") else None,
-        "tensor_pipe_bf16_equivalent_frac": 6 * tflops / pk["bf16"],
+        "tensor_pipe_bf16_equivalent_frac": 3 * tflops / pk["bf16"],
         "frac_of_fp32_simt_peak": tflops / 74.4, "peak_source": pk["source"]}
 
     cpu_sample = args.cpu_sample or default_cpu_sample(w)

@@ -293,6 +293,11 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line (rank 0): whatever libraries print meanwhile (NCCL's version banner ...)
+    # goes to stderr; the descriptor is restored for the final print
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -542,7 +547,10 @@ def run_gpu(args):
     line.update(extras)
     if train_info:
         line["train_step"] = train_info
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -135,3 +135,24 @@ def test_umma_output_lane_mask(mask_mode):
     kept = slice(64, 128) if mask_mode == 1 else slice(0, 64)
     assert np.abs(got[live] - ref[live]).max() < 1e-5
     assert (got[kept] == 777.0).all()
+
+
+@pytest.mark.parametrize("N,K", [(128, 64), (96, 32), (16, 128)])
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])
+def test_bf16x2_split_with_k_major_and_mn_major_operands(N, K, flags):
+    """The train step's image GEMMs (csrc/zf_img_gemm.cu): kind::f16 on bf16 hi/lo parts, both operands in shared
+    memory, each either K-major or MN-major (flags bit 0 / 1).  For an MN-major operand the descriptor's SBO is the
+    stride between core matrices along MN and its LBO the stride along K; every combination gives the same product,
+    at the 2^-17 relative accuracy of the two-part split."""
+    from zenflow_b200 import _lib
+
+    torch.manual_seed(N * 7 + K + flags)
+    A = torch.randn(128, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    out = torch.full((128, N), float("nan"), device="cuda")
+    _lib.check(_lib.load().zf_selftest_umma_bf16(torch.cuda.current_stream().cuda_stream, A.data_ptr(), B.data_ptr(), N, K,
+                                                 out.data_ptr(), flags), "zf_selftest_umma_bf16")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 3e-5, err

@@ -526,8 +526,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_kernel(const __grid_co
 // (measured: below fp32 sgemm's error) at twice the tensor rate and half the operand bytes of the 3xTF32 split
 // it replaces; a single TF32/BF16 pass would break the rel-1e-5 parity.  Valid while the
 // conditioner's activations and weights stay below 65504 in magnitude (beyond that the event's result is NaN).
-// Tensor memory (512 columns): A_hi [0,64) | A_lo [64,128) as fp16 pairs; hidden layers main [128,256), cross
-// [256,384); last layer, buffer b: main [128 + 192 b, +96), cross 96 columns further.
+// Tensor memory (512 columns): A_hi [0,64) | A_lo [64,128) as fp16 pairs; hidden layers main [256,384), cross
+// [384,512); last layer, buffer b: main [128 + 192 b, +96), cross 96 columns further.
 // =============================================================================================
 #ifdef ZF_TRACE   // developer build only (scripts/trace_chain.py): per-phase clock64 stamps of one steady-state tile
 __device__ long long g_zf_trace[4][64];
@@ -547,7 +547,11 @@ constexpr int UM = 128;
 #endif
 constexpr int URING = ZF_URING;   // <= 8 (barrier numbering below)
 constexpr int URING_FLOATS = 4096;  // 16 KB: one K-chunk (32) of a 128-column unit, fp16 hi|lo
-constexpr uint32_t TC_ALO = 64, TC_HMAIN = 128, TC_HCROSS = 256, TC_XOFF = 96;
+constexpr uint32_t TC_ALO = 64, TC_XOFF = 96;
+// Hidden accumulators.  Single-tile kernel: main [256,384), cross [384,512) - theta buffer 0 = [128,320) then only
+// overlaps the hidden main columns of K-chunks 0 and 1, so the first last-layer unit starts while the hidden epilogue
+// is still draining chunks 2 and 3.  Two-tile kernel: main [128,256), cross [256,384).
+constexpr uint32_t TC_HMAIN = 256, TC_HCROSS = 384, TC_PP_HMAIN = 128, TC_PP_HCROSS = 256;
 __host__ __device__ constexpr uint32_t tc_dmain(int b) { return 128u + 192u * (uint32_t)b; }
 constexpr int UFMAX = 32;           // conditioner inputs handled by the SIMT first layer
 constexpr int UDMAX = 32;           // transformed dims
@@ -971,59 +975,60 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             }
             // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
             // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
-            // the event's first four inputs stay in registers for all chunks (F is 2 on the 2-D flows): the chunk
-            // loop then has no load -> FMA dependency on hs, and its weight / bias loads are issued up front
-            float hreg[4];
+            // FN > 0: exactly F = FN inputs, all of them in registers for all chunks and the rows fully unrolled (the
+            // 16-D flows: F = 8 / 12 / 16): the chunk loop then has no load -> FMA dependency on hs and no predicated-off
+            // rows.  FN = 0: any F, the first four inputs in registers (F is 2 on the 2-D flows), the rest in a loop.
+            auto first_dense = [&](auto ftag) {
+                constexpr int FN = decltype(ftag)::value;
+                constexpr int HR = FN > 0 ? FN : 4;
+                float hreg[HR];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
+                for (int f = 0; f < HR; ++f) hreg[f] = (FN > 0 || f < F) ? hs[f * UM + m] : 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int n0 = c * 32 + half * CW;
-                float acc[CW];
-                uint32_t ahi[CW / 2], alo[CW / 2];
-                {
-                    const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
+                for (int c = 0; c < 4; ++c) {
+                    const int n0 = c * 32 + half * CW;
+                    float acc[CW];
+                    uint32_t ahi[CW / 2], alo[CW / 2];
+                    {
+                        const float4* bv = reinterpret_cast<const float4*>(b0s + n0);
 #pragma unroll
-                    for (int g4 = 0; g4 < CW / 4; ++g4) {
-                        const float4 t = bv[g4];
-                        acc[g4 * 4 + 0] = t.x; acc[g4 * 4 + 1] = t.y; acc[g4 * 4 + 2] = t.z; acc[g4 * 4 + 3] = t.w;
+                        for (int g4 = 0; g4 < CW / 4; ++g4) {
+                            const float4 t = bv[g4];
+                            acc[g4 * 4 + 0] = t.x; acc[g4 * 4 + 1] = t.y; acc[g4 * 4 + 2] = t.z; acc[g4 * 4 + 3] = t.w;
+                        }
                     }
+                    auto fma_row = [&](float h, int f) {
+                        const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
+#pragma unroll
+                        for (int g4 = 0; g4 < CW / 4; ++g4) {
+                            const float4 wv = w[g4];
+                            acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
+                            acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
+                            acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
+                            acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
+                        }
+                    };
+                    if constexpr (FN > 0) {
+#pragma unroll
+                        for (int f = 0; f < FN; ++f) fma_row(hreg[f], f);
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < 4; ++f)
+                            if (f < F) fma_row(hreg[f], f);
+                        for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
+                    }
+                    if (VJP) vjp_activation<CW>(a, 0, tile, m0, m, nm, n0, acc, ahi, alo);
+                    else activation_compute<CW>(acc, ahi, alo);
+                    activation_store<CW>(tb, lane_base, n0, ahi, alo);
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    umma::mbar_arrive(&bars[B_AREADY + c]);
                 }
-                auto fma_row = [&](float h, int f) {
-                    const float4* w = reinterpret_cast<const float4*>(w0s + f * 128 + n0);
-#pragma unroll
-                    for (int g4 = 0; g4 < CW / 4; ++g4) {
-                        const float4 wv = w[g4];
-                        acc[g4 * 4 + 0] = fmaf(h, wv.x, acc[g4 * 4 + 0]);
-                        acc[g4 * 4 + 1] = fmaf(h, wv.y, acc[g4 * 4 + 1]);
-                        acc[g4 * 4 + 2] = fmaf(h, wv.z, acc[g4 * 4 + 2]);
-                        acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
-                    }
-                };
-#pragma unroll
-                for (int f = 0; f < 4; ++f)
-                    if (f < F) fma_row(hreg[f], f);
-                for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
-                if (VJP) vjp_activation<CW>(a, 0, tile, m0, m, nm, n0, acc, ahi, alo);
-                else activation_compute<CW>(acc, ahi, alo);
-#ifdef ZF_TRACE_FINE
-                asm volatile("" :: "f"(ahi[0]), "f"(alo[CW - 1]) : "memory");
-                ZF_TR(trs);
-#endif
-                activation_store<CW>(tb, lane_base, n0, ahi, alo);
-#ifdef ZF_TRACE_FINE
-                ZF_TR(trs);
-#endif
-                umma::wait_st();
-#ifdef ZF_TRACE_FINE
-                ZF_TR(trs);
-#endif
-                umma::fence_before_sync();
-                umma::mbar_arrive(&bars[B_AREADY + c]);
-#ifdef ZF_TRACE_FINE
-                ZF_TR(trs);
-#endif
-            }
+            };
+            if (F == 8) first_dense(std::integral_constant<int, 8>{});
+            else if (F == 12) first_dense(std::integral_constant<int, 12>{});
+            else if (F == 16) first_dense(std::integral_constant<int, 16>{});
+            else first_dense(std::integral_constant<int, 0>{});
             ZF_TR(trs);   // first dense done
             // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
             for (int l = 1; l < L; ++l) {
@@ -1332,7 +1337,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
         // Main and cross products go to separate accumulators (the cross products carry the 2^11 scale of the lo'
         // parts; the tensor core's fp32 accumulator also truncates at every accumulate step - measured -2.3e-8
         // relative per step, tests/test_gpu_umma.py - which the small cross terms would otherwise suffer at the
-        // main product's magnitude): hidden layers main [128,256), cross [256,384); last-layer dim in buffer
+        // main product's magnitude): hidden layers main [256,384), cross [384,512); last-layer dim in buffer
         // b = dim & 1: main [128 + 192 b, +NL), cross 96 columns further.
         // The epilogue publishes a new activation version one 32-column K-chunk at a time (B_AREADY + c), and the
         // MMAs of chunk c are issued as soon as it has arrived, so the layer's GEMM runs underneath the
@@ -1354,9 +1359,9 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
                     ZF_TR(2);
                     const bool newver = hid || u == L - 1;   // this unit reads a new version of the activations
                     // chunks that must have arrived before the first MMA: those whose accumulator columns this unit
-                    // overwrites (u == 0 follows the SIMT first layer: nothing to drain); the last-layer buffers overlap
-                    // all of the hidden accumulators
-                    const int nfree = (u == 0) ? 0 : 4;
+                    // overwrites (u == 0 follows the SIMT first layer: nothing to drain); a hidden unit overwrites all of
+                    // them, the first last-layer unit (theta buffer 0) only the hidden main columns of chunks 0 and 1
+                    const int nfree = (u == 0) ? 0 : (hid ? 4 : 2);
                     int waited = 0;
 #ifdef ZF_TRACE
                     long long w_pend = clock64(), w_full = 0, w_a = 0;
@@ -1620,8 +1625,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         int waited = 0;
                         if (theta_pending) { mbar_wait(&bars[PP_DEMPTY_D], p_ed); p_ed ^= 1u; theta_pending = false; }
                         umma::fence_after_sync();
-                        const uint32_t dmain = hid ? tb + TC_HMAIN : tb + tc_dmain(0);
-                        const uint32_t dcross = hid ? tb + TC_HCROSS : dmain + TC_XOFF;
+                        const uint32_t dmain = hid ? tb + TC_PP_HMAIN : tb + tc_dmain(0);
+                        const uint32_t dcross = hid ? tb + TC_PP_HCROSS : dmain + TC_XOFF;
                         static_assert(URING == 4, "the MMA issuer maps chunk c to ring stage c");
                         auto issue_unit = [&](auto ntag) {
                             constexpr int N = decltype(ntag)::value;
@@ -1772,8 +1777,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         umma::fence_after_sync();
                         const float* bh = bhs + (l - 1) * 128;
                         float vn[CW], wn[CW];
-                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + half * CW), vn);
-                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + half * CW), wn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_PP_HMAIN + half * CW), vn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_PP_HCROSS + half * CW), wn);
 #pragma unroll 1
                         for (int c = 0; c < 4; ++c) {
                             const int n0 = c * 32 + half * CW;
@@ -1792,8 +1797,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                                 }
                             }
                             if (c < 3) {
-                                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + n0 + 32), vn);
-                                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
+                                tmem_load<CW>(umma::taddr(tb, lane_base, TC_PP_HMAIN + n0 + 32), vn);
+                                tmem_load<CW>(umma::taddr(tb, lane_base, TC_PP_HCROSS + n0 + 32), wn);
                             }
                             activation_compute<CW>(v, ahi, alo);
                             activation_store<CW>(tb, lane_base, n0, ahi, alo);

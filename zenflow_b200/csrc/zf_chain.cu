@@ -168,11 +168,17 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
                         if (part == 0) v = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(job.bn_var[f], 1e-5f))) * job.bn_scale[f];
                         else v = part == 1 ? job.bn_mean[f] : job.bn_bias[f];
                     }
-                } else if (i < cl.b0) {                // first Dense kernel [F][128]
-                    const int e = i - cl.w0;
-                    if (e < F * 128) v = job.kernel[0][e];
-                } else if (i < cl.bh) {                // first Dense bias
-                    v = job.bias[0][i - cl.b0];
+                } else if (i < cl.b0) {                // first Dense kernel [F][128] with the BatchNorm scale folded in:
+                    const int e = i - cl.w0;           // the kernels compute sum_f (x_f - mean_f) * (mul_f W0[f][n]) + b0'[n]
+                    if (e < F * 128) {
+                        const int f = e >> 7;
+                        const float mul = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(job.bn_var[f], 1e-5f))) * job.bn_scale[f];
+                        v = __fmul_rn(mul, job.kernel[0][e]);
+                    }
+                } else if (i < cl.bh) {                // first Dense bias + (BatchNorm bias) . W0
+                    const int n = i - cl.b0;
+                    v = job.bias[0][n];
+                    for (int f = 0; f < F; ++f) v = fmaf(job.bn_bias[f], job.kernel[0][f * 128 + n], v);
                 } else if (i < cl.bl) {                // hidden biases, layers 1..L-1
                     const int e = i - cl.bh, l = 1 + (e >> 7);
                     if (l < L) v = job.bias[l][e & 127];
@@ -941,12 +947,17 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh, *bls = cc + cl.bl;
             mbar_wait(&bars[B_CFULL + cb], (ke >> 1) & 1u);
             ZF_TR(trs);   // constants staged
-            // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342); halves share the features
-            for (int f = half; f < F; f += NG) {
-                const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
-                hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+            // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342).  Scale and bias are folded into the first
+            // Dense at pack time, what is left is x - mean: for the input counts the first Dense is specialised on, every
+            // thread takes it straight from the tile (no staging, no barrier); otherwise the halves share the features
+            const bool direct = !VJP && (F == 8 || F == 12 || F == 16);
+            if (!direct) {
+                for (int f = half; f < F; f += NG) {
+                    const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
+                    hs[f * UM + m] = v - bns[F_p + f];
+                }
+                epi_barrier<ET>();
             }
-            epi_barrier<ET>();
             ZF_TR(trs);   // batch norm done
             if (VJP) {
                 // BatchNorm output for the grad-weight GEMM of the first Dense; the conditioning columns' cotangent
@@ -958,7 +969,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int f = g8 * 8 + i;
-                            hv[i] = (m < nm) ? (f < F ? hs[f * UM + m] : (f == F ? 1.0f : 0.f)) : 0.f;
+                            hv[i] = (m < nm) ? (f < F ? fmaf(hs[f * UM + m], bns[f], bns[2 * F_p + f]) : (f == F ? 1.0f : 0.f)) : 0.f;
                         }
                         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -982,8 +993,18 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 constexpr int FN = decltype(ftag)::value;
                 constexpr int HR = FN > 0 ? FN : 4;
                 float hreg[HR];
+                if (FN > 0 && !VJP) {
+                    int col = pmod(d - rot, D);
 #pragma unroll
-                for (int f = 0; f < HR; ++f) hreg[f] = (FN > 0 || f < F) ? hs[f * UM + m] : 0.f;
+                    for (int f = 0; f < HR; ++f) {
+                        const float v = (f < D - d) ? xs[col * UM + m] : cs[(f - (D - d)) * UM + m];
+                        hreg[f] = v - bns[F_p + f];
+                        if (++col == D) col = 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < HR; ++f) hreg[f] = (FN > 0 || f < F) ? hs[f * UM + m] : 0.f;
+                }
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = c * 32 + half * CW;
@@ -1698,7 +1719,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
             mbar_wait(&bars[PP_XSREADY + tbuf], (uint32_t)(((k / PP_TBUF) * ncoup + cj) & 1));
             for (int f = half; f < F; f += 2) {
                 const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
-                hs[f * UM + m] = (v - bns[F_p + f]) * bns[f] + bns[2 * F_p + f];
+                hs[f * UM + m] = v - bns[F_p + f];   // scale and bias are folded into the first Dense (pack_step_kernel)
             }
             bn_done = n;
         };

@@ -59,7 +59,7 @@ struct StepDesc {
 };
 static_assert(sizeof(StepDesc) % 16 == 0, "StepDesc must keep the packed blocks 16-byte aligned");
 
-struct UCst { int bn, w0, b0, bh, bl, total; };   // float offsets inside a constant block (ucst_layout)
+struct UCst { int bn, w0, b0, bh, bl, w0i, total; };   // float offsets inside a constant block (ucst_layout); w0i < 0: no image
 
 struct PackJob {
     StepDesc desc;
@@ -160,7 +160,24 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
         {   // the constant block the producer warp fetches with one bulk copy per coupling
             float* cb = ws + s.off_C;
             const UCst& cl = job.cst;
-            for (int i = gtid; i < cl.total; i += gsz) {
+            const int n_plain = cl.w0i >= 0 ? cl.w0i : cl.total;
+            if (cl.w0i >= 0) {                         // first Dense (BatchNorm scale folded in) as a K = 16 operand image
+                __half* dst = reinterpret_cast<__half*>(cb + cl.w0i);
+                for (int e = gtid; e < 16 * 128; e += gsz) {
+                    const int k = e >> 7, n = e & 127;
+                    float val = 0.f;
+                    if (k < F) {
+                        const float mul = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(job.bn_var[k], 1e-5f))) * job.bn_scale[k];
+                        val = __fmul_rn(mul, job.kernel[0][k * 128 + n]);
+                    }
+                    const __half hi = __float2half_rn(val);
+                    const __half lo = __float2half_rn((val - __half2float(hi)) * umma::kF16LoScale);
+                    const int ii = umma::b_image_index_f16(n, k, 128);
+                    dst[ii] = hi;
+                    dst[16 * 128 + ii] = lo;
+                }
+            }
+            for (int i = gtid; i < n_plain; i += gsz) {
                 float v = 0.f;
                 if (i < cl.w0) {                       // BatchNorm [mul | mean | bias], F_p each
                     const int part = i / F_p, f = i - part * F_p;
@@ -232,6 +249,7 @@ struct ChainArgs {
     float peakness;
     LatentConst lc;
     int u_fmax, u_hmax, u_blmax;   // tensor-core kernel: max conditioner inputs / hidden biases / last-layer bias floats
+    int u_w0img;        // the constant blocks carry the first Dense's operand image (first Dense on the tensor cores)
     int* idx_out;       // (M, n_couplings, d) bin indices of every spline evaluation, or null (parity evidence)
     int n_couplings;
     // kModeVjp (chain_umma_kernel<false, true>, a chain of ONE coupling): conditioner recompute + spline VJP
@@ -558,6 +576,9 @@ constexpr uint32_t TC_ALO = 64, TC_XOFF = 96;
 // overlaps the hidden main columns of K-chunks 0 and 1, so the first last-layer unit starts while the hidden epilogue
 // is still draining chunks 2 and 3.  Two-tile kernel: main [128,256), cross [256,384).
 constexpr uint32_t TC_HMAIN = 256, TC_HCROSS = 384, TC_PP_HMAIN = 128, TC_PP_HCROSS = 256;
+// first Dense on the tensor cores (K = 16): ONE accumulator [128,256) - cross products first, then the main product on
+// top as D = A B + D 2^-11 (scale-input-d); it is drained before the first theta unit overwrites the columns
+constexpr uint32_t TC_FD = 128;
 __host__ __device__ constexpr uint32_t tc_dmain(int b) { return 128u + 192u * (uint32_t)b; }
 constexpr int UFMAX = 32;           // conditioner inputs handled by the SIMT first layer
 constexpr int UDMAX = 32;           // transformed dims
@@ -565,11 +586,14 @@ constexpr int UDMAX = 32;           // transformed dims
 // accumulator columns it was computed from have been read (so they may be overwritten)
 // B_CFULL/B_CEMPTY + b: constant block buffer b;  B_XFULL/B_XEMPTY: the raw rows of the next input tile
 enum UBar : int { B_FULL = 0, B_EMPTY = 8, B_AREADY = 16, B_DFULL_H = 20, B_DFULL_D = 21, B_DEMPTY_D = 23,
-                  B_CFULL = 25, B_CEMPTY = 27, B_XFULL = 29, B_XEMPTY = 30, B_COUNT = 32 };
+                  B_CFULL = 25, B_CEMPTY = 27, B_XFULL = 29, B_XEMPTY = 30, B_A0READY = 31, B_COUNT = 32 };
 
 // per-coupling constants (BatchNorm affine, first Dense, biases), double-buffered: the next coupling's set is
 // fetched with cp.async while the current one computes
-__host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
+// img: the block also carries the first Dense as a 3xFP16 operand image (K = 16 x N = 128: hi 4 KB | lo' 4 KB), for the
+// kernels that run the first Dense on the tensor cores
+constexpr int UW0IMG_FLOATS = 2048;
+__host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax, bool img = false) {
     UCst l;
     l.bn = 0;
     l.w0 = ru(3 * ru(Fmax, KC), 32);
@@ -577,12 +601,15 @@ __host__ __device__ inline UCst ucst_layout(int Fmax, int Hmax, int BLmax) {
     l.bh = l.b0 + 128;
     l.bl = l.bh + Hmax * 128;
     l.total = ru(l.bl + BLmax, 32);
+    l.w0i = -1;
+    if (img) { l.w0i = l.total; l.total += UW0IMG_FLOATS; }
     return l;
 }
 constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer programs read them from global)
 constexpr int VJP_ROW = 97;   // floats per theta row of the VJP kernel (odd: one thread per row without bank conflicts)
-__host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax, bool vjp = false) {
-    return 2 * (size_t)UM * (D + C) + (size_t)Fmax * UM + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax).total + 11 * UM +
+__host__ __device__ inline size_t umma_hs_floats(int Fmax, bool) { return (size_t)Fmax * UM; }   // x - mean, [Fmax][UM]
+__host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax, bool vjp = false, bool img = false) {
+    return 2 * (size_t)UM * (D + C) + umma_hs_floats(Fmax, img) + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax, img).total + 11 * UM +
            (vjp ? 2 * UM * VJP_ROW : 2 * 8 * UM * 4) +
            (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
@@ -950,7 +977,8 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342).  Scale and bias are folded into the first
             // Dense at pack time, what is left is x - mean: for the input counts the first Dense is specialised on, every
             // thread takes it straight from the tile (no staging, no barrier); otherwise the halves share the features
-            const bool direct = !VJP && (F == 8 || F == 12 || F == 16);
+            const bool tcfd = !VJP && a.u_w0img && F <= 16;   // first Dense on the tensor cores (see below)
+            const bool direct = tcfd || (!VJP && (F == 8 || F == 12 || F == 16));
             if (!direct) {
                 for (int f = half; f < F; f += NG) {
                     const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
@@ -1046,23 +1074,53 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     umma::mbar_arrive(&bars[B_AREADY + c]);
                 }
             };
-            if (F == 8) first_dense(std::integral_constant<int, 8>{});
+            if (tcfd) {
+                // ---- first Dense on the tensor cores: x - mean of the event's inputs (3xFP16 split) as a K = 16 A operand
+                // in tensor memory, columns [0, 8) (hi) and [TC_ALO, +8) (lo'); this thread writes inputs [8 half, +8) of
+                // its event = 4 columns of each.  The MMA warp multiplies it with the W0 image of the constant block
+                // into columns [TC_FD, +128); the epilogue below treats the result like a hidden layer.
+                float hv[8];
+                {
+                    const int f0 = 8 * half;
+                    int col = pmod(d + f0 - rot, D);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int f = f0 + i;
+                        float v = 0.f;
+                        if (f < F) v = ((f < D - d) ? xs[col * UM + m] : cs[(f - (D - d)) * UM + m]) - bns[F_p + f];
+                        hv[i] = v;
+                        if (++col == D) col = 0;
+                    }
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) umma::split_f16x2(hv[2 * q2], hv[2 * q2 + 1], hi[q2], lo[q2]);
+                umma::st4u(umma::taddr(tb, lane_base, 4 * half), hi);
+                umma::st4u(umma::taddr(tb, lane_base, TC_ALO + 4 * half), lo);
+                umma::wait_st();
+                umma::fence_before_sync();
+                umma::mbar_arrive(&bars[B_A0READY]);
+            } else if (F == 8) first_dense(std::integral_constant<int, 8>{});
             else if (F == 12) first_dense(std::integral_constant<int, 12>{});
             else if (F == 16) first_dense(std::integral_constant<int, 16>{});
             else first_dense(std::integral_constant<int, 0>{});
             ZF_TR(trs);   // first dense done
             // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
-            for (int l = 1; l < L; ++l) {
+            // FD: the accumulator of the tensor-core first Dense (one merged accumulator, bias b0'); otherwise a hidden
+            // layer's main + cross accumulators
+            auto hidden_epilogue = [&](auto fdtag, int l) {
+                constexpr bool FD = decltype(fdtag)::value;
                 mbar_wait(&bars[B_DFULL_H], p_fh);
                 p_fh ^= 1u;
                 umma::fence_after_sync();
                 ZF_TR(trs);   // hidden accumulator ready
-                const float* bh = bhs + (l - 1) * 128;
+                const float* bh = FD ? b0s : bhs + (l - 1) * 128;
+                constexpr uint32_t cmain = FD ? TC_FD : TC_HMAIN;
                 // chunk c: accumulator columns [32c + CW g, +CW) -> the same columns of the next activations.
                 // The TMEM loads of chunk c+1 are in flight during the arithmetic of chunk c.
-                float vn[CW], wn[CW];
-                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + half * CW), vn);     // main products
-                tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + half * CW), wn);    // cross products (scale 2^11)
+                float vn[CW], wn[FD ? 1 : CW];
+                tmem_load<CW>(umma::taddr(tb, lane_base, cmain + half * CW), vn);     // main products
+                if constexpr (!FD) tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + half * CW), wn);    // cross products (scale 2^11)
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = c * 32 + half * CW;
@@ -1074,15 +1132,22 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
 #pragma unroll
                         for (int g4 = 0; g4 < CW / 4; ++g4) {
                             const float4 t = bv[g4];
-                            v[g4 * 4 + 0] = fmaf(wn[g4 * 4 + 0], umma::kF16LoUnscale, vn[g4 * 4 + 0]) + t.x;
-                            v[g4 * 4 + 1] = fmaf(wn[g4 * 4 + 1], umma::kF16LoUnscale, vn[g4 * 4 + 1]) + t.y;
-                            v[g4 * 4 + 2] = fmaf(wn[g4 * 4 + 2], umma::kF16LoUnscale, vn[g4 * 4 + 2]) + t.z;
-                            v[g4 * 4 + 3] = fmaf(wn[g4 * 4 + 3], umma::kF16LoUnscale, vn[g4 * 4 + 3]) + t.w;
+                            if constexpr (FD) {
+                                v[g4 * 4 + 0] = vn[g4 * 4 + 0] + t.x;
+                                v[g4 * 4 + 1] = vn[g4 * 4 + 1] + t.y;
+                                v[g4 * 4 + 2] = vn[g4 * 4 + 2] + t.z;
+                                v[g4 * 4 + 3] = vn[g4 * 4 + 3] + t.w;
+                            } else {
+                                v[g4 * 4 + 0] = fmaf(wn[g4 * 4 + 0], umma::kF16LoUnscale, vn[g4 * 4 + 0]) + t.x;
+                                v[g4 * 4 + 1] = fmaf(wn[g4 * 4 + 1], umma::kF16LoUnscale, vn[g4 * 4 + 1]) + t.y;
+                                v[g4 * 4 + 2] = fmaf(wn[g4 * 4 + 2], umma::kF16LoUnscale, vn[g4 * 4 + 2]) + t.z;
+                                v[g4 * 4 + 3] = fmaf(wn[g4 * 4 + 3], umma::kF16LoUnscale, vn[g4 * 4 + 3]) + t.w;
+                            }
                         }
                     }
                     if (c < 3) {
-                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HMAIN + n0 + 32), vn);
-                        tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
+                        tmem_load<CW>(umma::taddr(tb, lane_base, cmain + n0 + 32), vn);
+                        if constexpr (!FD) tmem_load<CW>(umma::taddr(tb, lane_base, TC_HCROSS + n0 + 32), wn);
                     }
                     if (VJP) vjp_activation<CW>(a, l, tile, m0, m, nm, n0, v, ahi, alo);
                     else activation_compute<CW>(v, ahi, alo);
@@ -1092,7 +1157,9 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     umma::mbar_arrive(&bars[B_AREADY + c]);
                 }
                 ZF_TR(trs);   // hidden epilogue done
-            }
+            };
+            if (tcfd) hidden_epilogue(std::true_type{}, 0);
+            for (int l = 1; l < L; ++l) hidden_epilogue(std::false_type{}, l);
             // ---- last layer: theta of one transformed dim at a time, read from tensor memory
             float ldc = 0.f;
             if (VJP) {
@@ -1239,12 +1306,12 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int ET = NG * 128, PW = NG * 4, MW = NG * 4 + 1;   // epilogue threads, producer warp, MMA warp
     const int D = a.D, C = a.C;
-    const UCst cl = ucst_layout(a.u_fmax, a.u_hmax, a.u_blmax);
+    const UCst cl = ucst_layout(a.u_fmax, a.u_hmax, a.u_blmax, a.u_w0img != 0);
     float* xs = smem;                         // [D][UM]  the tile, feature-major
     float* cs = xs + D * UM;                  // [C][UM]
     float* xraw = cs + C * UM;                // [UM][D] | [UM][C]  next tile as it lies in global memory (cp.async)
-    float* hs = xraw + UM * (D + C);          // [Fmax][UM]  BatchNorm output
-    float* cst = hs + a.u_fmax * UM;          // [2][cl.total] per-coupling constants
+    float* hs = xraw + UM * (D + C);          // [Fmax][UM]  x - mean (couplings whose first Dense reads it from shared memory)
+    float* cst = hs + umma_hs_floats(a.u_fmax, a.u_w0img != 0);   // [2][cl.total] per-coupling constants
     float* ldx = cst + 2 * cl.total;
     float* pairx = ldx + 3 * UM;              // [7][UM] exchange between the two threads of a shared spline row
     float* scratch = pairx + 8 * UM;          // [2][8][UM] float4: scratch columns of the lean spline rows
@@ -1273,6 +1340,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
         for (int i = 0; i < 2; ++i) { mbar_init(&bars[B_CFULL + i], 1); mbar_init(&bars[B_CEMPTY + i], ET); }
         mbar_init(&bars[B_XFULL], 1);
         mbar_init(&bars[B_XEMPTY], ET);
+        mbar_init(&bars[B_A0READY], ET);
         mbar_fence_init();
     }
     if (warp == MW) umma::tmem_alloc(tmem_slot, 512);
@@ -1365,7 +1433,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
         // bias/swish/split of the chunks behind it.  The arrival of chunk c also says that accumulator columns
         // [32c, 32c+32) of D0 and D1 have been drained, which is what lets the first last-layer unit start
         // before the hidden epilogue has finished (it only needs the columns it overwrites to be free).
-        uint32_t phase = 0, p_ar = 0, p_ed0 = 0, p_ed1 = 0;
+        uint32_t phase = 0, p_ar = 0, p_ed0 = 0, p_ed1 = 0, p_a0 = 0, kcm = 0;
         bool dim_pending0 = false, dim_pending1 = false;
         ZF_TR_DECL;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1374,6 +1442,30 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
                 const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
                 if (s.kind != kStepKindCoupling) continue;
                 const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
+                const bool tcfd = !VJP && a.u_w0img && s.F <= 16;
+                if (tcfd) {
+                    // first Dense: A = the epilogue's (x - mean) operand in tensor memory, B = the W0 image of this
+                    // coupling's constant block; one k-step (K = 16), three products into ONE accumulator [TC_FD, +128):
+                    // the two cross products (scale 2^11) first, then the main product as D = A_hi B_hi + D 2^-11
+                    if (dim_pending0) { mbar_wait(&bars[B_DEMPTY_D + 0], p_ed0); p_ed0 ^= 1u; dim_pending0 = false; }
+                    if (dim_pending1) { mbar_wait(&bars[B_DEMPTY_D + 1], p_ed1); p_ed1 ^= 1u; dim_pending1 = false; }
+                    const uint32_t cbm = kcm & 1u;
+                    mbar_wait(&bars[B_CFULL + cbm], (kcm >> 1) & 1u);
+                    mbar_wait(&bars[B_A0READY], p_a0);
+                    p_a0 ^= 1u;
+                    umma::fence_after_sync();
+                    if (umma::elect_one()) {
+                        const uint32_t w0 = smem_u32(cst + (size_t)cbm * cl.total + cl.w0i);
+                        const uint64_t b_hi = umma::smem_desc_kmajor(w0, 2048u, 128u), b_lo = umma::smem_desc_kmajor(w0 + 4096u, 2048u, 128u);
+                        constexpr uint32_t idesc = umma::instr_desc_f16(128);
+                        umma::mma_f16_ts(tb + TC_FD, tb + TC_ALO, b_hi, idesc, false);
+                        umma::mma_f16_ts(tb + TC_FD, tb, b_lo, idesc, true);
+                        umma::mma_f16_ts_scaled<11>(tb + TC_FD, tb, b_hi, idesc);
+                        umma::commit(&bars[B_DFULL_H]);
+                    }
+                    __syncwarp();
+                }
+                ++kcm;
                 for (int u = 0; u < (L - 1) + s.d; ++u) {
                     const bool hid = u < L - 1;
                     const int b = hid ? 0 : ((u - (L - 1)) & 1);
@@ -1382,7 +1474,8 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
                     // chunks that must have arrived before the first MMA: those whose accumulator columns this unit
                     // overwrites (u == 0 follows the SIMT first layer: nothing to drain); a hidden unit overwrites all of
                     // them, the first last-layer unit (theta buffer 0) only the hidden main columns of chunks 0 and 1
-                    const int nfree = (u == 0) ? 0 : (hid ? 4 : 2);
+                    // (a tensor-core first Dense accumulates in [TC_FD, +128): only a theta unit right behind it overlaps)
+                    const int nfree = (u == 0) ? ((tcfd && !hid) ? 4 : 0) : (hid ? 4 : 2);
                     int waited = 0;
 #ifdef ZF_TRACE
                     long long w_pend = clock64(), w_full = 0, w_a = 0;
@@ -2000,9 +2093,11 @@ struct Plan {
     int n_couplings = 0;
     int Fmax = 1, Hmax = 1, BLmax = 32;   // shared-memory sizing of the two-pipeline kernel
     bool all_d1 = true;                   // every coupling transforms a single dim
+    bool w0img = false;                   // constant blocks carry the first Dense's operand image (tensor-core first Dense)
 };
 
-static int build_plan(const zf_chain* chain, Plan& plan) {
+// for_vjp: the plan of the fused VJP kernel (its shared memory has no room for the first Dense's operand images)
+static int build_plan(const zf_chain* chain, Plan& plan, bool for_vjp = false) {
     ZF_REQUIRE(chain != nullptr, "chain is NULL");
     const int D = chain->dim, C = chain->cdim;
     ZF_REQUIRE(D >= 1 && D <= ZF_MAX_DIM, "dim must be in [1, %d] (got %d)", ZF_MAX_DIM, D);
@@ -2086,6 +2181,9 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
         plan.jobs.push_back(job);
     }
     plan.rot_total = rot;
+    // multi-dim couplings with at most 16 conditioner inputs: first Dense on the tensor cores (single-tile kernel)
+    static const bool simt_fd = [] { const char* e = getenv("ZF_FD_IMPL"); return e && e[0] == 's'; }();   // developer A/B switch
+    plan.w0img = !for_vjp && !simt_fd && plan.umma_ok && plan.n_couplings > 0 && !plan.all_d1 && plan.Fmax <= 16;
 
     // workspace layout: StepDesc array, then per-step blocks (all multiples of 4 floats)
     size_t off = (sizeof(StepDesc) * std::max<size_t>(plan.jobs.size(), 1) + 15) / 16 * 4;
@@ -2113,7 +2211,7 @@ static int build_plan(const zf_chain* chain, Plan& plan) {
                 off = (off + 31) / 32 * 32;  // images are fetched by 16-byte-aligned bulk copies
                 for (int l = 1; l < L; ++l) s.off_U[l] = take((size_t)128 * 128);
                 s.off_U[L] = take((size_t)s.d * NL * 128);
-                job.cst = ucst_layout(plan.Fmax, plan.Hmax, plan.BLmax);
+                job.cst = ucst_layout(plan.Fmax, plan.Hmax, plan.BLmax, plan.w0img);
                 s.off_C = take((size_t)job.cst.total);
             }
         }
@@ -2238,7 +2336,8 @@ static int run_chain(cudaStream_t stream, const zf_chain* chain, int mode, int l
         a.u_fmax = plan.Fmax;
         a.u_hmax = plan.Hmax;
         a.u_blmax = plan.BLmax;
-        const size_t usmem = umma_smem_floats(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax) * sizeof(float);
+        a.u_w0img = plan.w0img ? 1 : 0;
+        const size_t usmem = umma_smem_floats(a.D, a.C, plan.Fmax, plan.Hmax, plan.BLmax, false, plan.w0img) * sizeof(float);
         if (usmem <= (size_t)di.max_smem_optin) {
             const long long tiles = (M + UM - 1) / UM;
             const unsigned ugrid = (unsigned)std::min<long long>(tiles, (long long)di.sm_count);
@@ -2301,7 +2400,7 @@ static int vjp_plan(const zf_coupling* cp, int D, int C, Plan& plan, zf_op& op, 
     op.kind = ZF_OP_COUPLING;
     op.coupling = cp;
     chain = zf_chain{D, C, 1, &op};
-    return build_plan(&chain, plan);
+    return build_plan(&chain, plan, true);
 }
 
 // floats of packed parameters the fused VJP kernel needs, 0 when this coupling / device does not fit it

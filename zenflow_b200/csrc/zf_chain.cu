@@ -579,6 +579,11 @@ constexpr uint32_t TC_HMAIN = 256, TC_HCROSS = 384, TC_PP_HMAIN = 128, TC_PP_HCR
 // first Dense on the tensor cores (K = 16): ONE accumulator [128,256) - cross products first, then the main product on
 // top as D = A B + D 2^-11 (scale-input-d); it is drained before the first theta unit overwrites the columns
 constexpr uint32_t TC_FD = 128;
+// Two-tile kernel, theta columns of the (single) transformed dim.  K = 16 (48 + 48 columns): [384, 480), clear of the
+// hidden accumulators, so the theta unit runs under the hidden epilogue of its own slot and the other slot's hidden
+// GEMM does not have to wait for the row warps.  K = 32 (96 + 96 columns) only fits on top of them: [128, 320).
+__host__ __device__ constexpr uint32_t tc_pp_theta(int NL) { return NL == 48 ? 384u : 128u; }
+__host__ __device__ constexpr uint32_t tc_pp_xoff(int NL) { return NL == 48 ? 48u : 96u; }
 __host__ __device__ constexpr uint32_t tc_dmain(int b) { return 128u + 192u * (uint32_t)b; }
 constexpr int UFMAX = 32;           // conditioner inputs handled by the SIMT first layer
 constexpr int UDMAX = 32;           // transformed dims
@@ -1725,7 +1730,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
 
     auto mma_role = [&]() {
         uint32_t phase = 0, p_ar = 0, p_ed = 0;
-        bool theta_pending = false;   // D0/D1 hold a theta row that the row warps may still be reading
+        bool theta_pending = false;   // the theta columns hold a row that the row warps may still be reading
+        int pending_nl = 0;           // its width (decides whether the hidden accumulators overlap it)
         for (long long p = 0; 2 * p < n_my; ++p) {
             const int nslots = (2 * p + 1 < n_my) ? 2 : 1;
             for (int si = 0; si < a.n_steps; ++si) {
@@ -1735,12 +1741,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                 for (int slot = 0; slot < nslots; ++slot) {
                     for (int u = 0; u < L; ++u) {
                         const bool hid = u < L - 1;
-                        const int nfree = (u == 0) ? 0 : 4;
+                        // a theta row at [384, 480) (K = 16) overlaps nothing but the next theta row
+                        const bool clear = !hid && NL == 48;
+                        const int nfree = (u == 0 || clear) ? 0 : 4;
                         int waited = 0;
-                        if (theta_pending) { mbar_wait(&bars[PP_DEMPTY_D], p_ed); p_ed ^= 1u; theta_pending = false; }
+                        if (theta_pending && (!hid || pending_nl != 48)) {
+                            mbar_wait(&bars[PP_DEMPTY_D], p_ed); p_ed ^= 1u; theta_pending = false;
+                        }
                         umma::fence_after_sync();
-                        const uint32_t dmain = hid ? tb + TC_PP_HMAIN : tb + tc_dmain(0);
-                        const uint32_t dcross = hid ? tb + TC_PP_HCROSS : dmain + TC_XOFF;
+                        const uint32_t dmain = hid ? tb + TC_PP_HMAIN : tb + tc_pp_theta(NL);
+                        const uint32_t dcross = hid ? tb + TC_PP_HCROSS : dmain + tc_pp_xoff(NL);
                         static_assert(URING == 4, "the MMA issuer maps chunk c to ring stage c");
                         auto issue_unit = [&](auto ntag) {
                             constexpr int N = decltype(ntag)::value;
@@ -1781,7 +1791,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         else issue_unit(std::integral_constant<int, 96>{});
                         phase ^= 1u;
                         p_ar ^= 1u;              // every unit reads a new version of the activations (d == 1)
-                        if (!hid) theta_pending = true;
+                        if (!hid) { theta_pending = true; pending_nl = NL; }
                     }
                 }
             }
@@ -2008,7 +2018,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                         mbar_wait(&bars[PP_DFULL_D], p_fd);
                         p_fd ^= 1u;
                         umma::fence_after_sync();
-                        const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(0));
+                        const int NLr = ru(3 * K - 1, 16);
+                        const uint32_t dbase = umma::taddr(tb, lane_base, tc_pp_theta(NLr));
                         float* px = xs + pmod(0 - rot, D) * UM + m;
                         const float v = *px;
                         RqsBin bin;
@@ -2017,8 +2028,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) chain_umma_pp_kernel(const __gr
                             umma::mbar_arrive(&bars[PP_DEMPTY_D]);
                         };
                         float4* scr = reinterpret_cast<float4*>(scratch) + m;
-                        if (K == 16) spline_row_tmem_lean<16, INVERSE>(dbase, TC_XOFF, bls, v, bin, scr, UM, release);
-                        else spline_row_tmem_lean<32, INVERSE>(dbase, TC_XOFF, bls, v, bin, scr, UM, release);
+                        if (K == 16) spline_row_tmem_lean<16, INVERSE>(dbase, tc_pp_xoff(48), bls, v, bin, scr, UM, release);
+                        else spline_row_tmem_lean<32, INVERSE>(dbase, tc_pp_xoff(96), bls, v, bin, scr, UM, release);
                         if (m < nm) put_idx(a, s, m0 + m, 0, bin.idx);
                         umma::mbar_arrive(&bars[PP_CEMPTY + cb]);   // last read of this occurrence's constants by S2
                         if (!INVERSE) {

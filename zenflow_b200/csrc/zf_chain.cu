@@ -614,7 +614,7 @@ constexpr int USTEPS = 40;   // step descriptors kept in shared memory (longer p
 constexpr int VJP_ROW = 97;   // floats per theta row of the VJP kernel (odd: one thread per row without bank conflicts)
 __host__ __device__ inline size_t umma_hs_floats(int Fmax, bool) { return (size_t)Fmax * UM; }   // x - mean, [Fmax][UM]
 __host__ __device__ inline size_t umma_smem_floats(int D, int C, int Fmax, int Hmax, int BLmax, bool vjp = false, bool img = false) {
-    return 2 * (size_t)UM * (D + C) + umma_hs_floats(Fmax, img) + 2 * (size_t)ucst_layout(Fmax, Hmax, BLmax, img).total + 11 * UM +
+    return 2 * (size_t)UM * (D + C) + umma_hs_floats(Fmax, img) + (vjp ? 1 : 2) * (size_t)ucst_layout(Fmax, Hmax, BLmax, img).total + 11 * UM +
            (vjp ? 2 * UM * VJP_ROW : 2 * 8 * UM * 4) +
            (size_t)URING * URING_FLOATS + 2 * B_COUNT + 32 + USTEPS * sizeof(StepDesc) / sizeof(float);
 }
@@ -868,6 +868,7 @@ struct UCtx {
     uint32_t tb;
     long long n_tiles;
     UCst cl;
+    int cst_stride;   // floats between the two constant buffers (0 in the VJP kernel: one coupling, one buffer)
     bool in16;
     uint32_t in_bytes;
 };
@@ -975,15 +976,15 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             const int K = s.K, P = 3 * K - 1, NL = ru(P, 16);
             // ---- this coupling's constants: fetched by the producer warp into buffer ke & 1
             const uint32_t cb = ke & 1u;
-            const float* cc = cst + (size_t)cb * cl.total;
+            const float* cc = cst + (size_t)cb * cx.cst_stride;
             const float *bns = cc + cl.bn, *w0s = cc + cl.w0, *b0s = cc + cl.b0, *bhs = cc + cl.bh, *bls = cc + cl.bl;
             mbar_wait(&bars[B_CFULL + cb], (ke >> 1) & 1u);
             ZF_TR(trs);   // constants staged
             // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342).  Scale and bias are folded into the first
             // Dense at pack time, what is left is x - mean: for the input counts the first Dense is specialised on, every
             // thread takes it straight from the tile (no staging, no barrier); otherwise the halves share the features
-            const bool tcfd = !VJP && a.u_w0img && F <= 16;   // first Dense on the tensor cores (see below)
-            const bool direct = tcfd || (!VJP && (F == 8 || F == 12 || F == 16));
+            const bool tcfd = a.u_w0img && F <= 16;   // first Dense on the tensor cores (see below)
+            const bool direct = !VJP && (tcfd || F == 8 || F == 12 || F == 16);
             if (!direct) {
                 for (int f = half; f < F; f += NG) {
                     const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
@@ -992,7 +993,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 epi_barrier<ET>();
             }
             ZF_TR(trs);   // batch norm done
-            if (VJP) {
+            auto vjp_side_outputs = [&]() {
                 // BatchNorm output for the grad-weight GEMM of the first Dense; the conditioning columns' cotangent
                 // passes through unchanged (d y[:, j] / d x[:, j] = 1, bijectors.py:364)
                 {
@@ -1012,11 +1013,22 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     }
                 }
                 const int nc = D - d;
-                for (int e = tid; e < nm * nc; e += ET) {
-                    const int mm = e / nc, j = d + (e - mm * nc);
-                    a.gx[(m0 + mm) * D + j] = a.gy[(m0 + mm) * D + pmod(j + a.gy_rot, D)];
+                for (int e0 = tid; e0 < nm * nc; e0 += 4 * ET) {   // four loads in flight per thread
+                    float gv[4];
+                    long long go[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = e0 + k * ET;
+                        const int mm = e / nc, j = d + (e - mm * nc);
+                        go[k] = (m0 + mm) * D + j;
+                        gv[k] = e < nm * nc ? a.gy[(m0 + mm) * D + pmod(j + a.gy_rot, D)] : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (e0 + k * ET < nm * nc) a.gx[go[k]] = gv[k];
                 }
-            }
+            };
+            if (VJP && !tcfd) vjp_side_outputs();
             // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
             // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
             // FN > 0: exactly F = FN inputs, all of them in registers for all chunks and the rows fully unrolled (the
@@ -1105,6 +1117,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 umma::wait_st();
                 umma::fence_before_sync();
                 umma::mbar_arrive(&bars[B_A0READY]);
+                if (VJP) vjp_side_outputs();   // under the first Dense's MMAs
             } else if (F == 8) first_dense(std::integral_constant<int, 8>{});
             else if (F == 12) first_dense(std::integral_constant<int, 12>{});
             else if (F == 16) first_dense(std::integral_constant<int, 16>{});
@@ -1181,15 +1194,18 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     mbar_wait(&bars[B_DFULL_D + half], p_fd);
                     p_fd ^= 1u;
                     umma::fence_after_sync();
+                    ZF_TR(trs);   // theta ready
                     const uint32_t dbase = umma::taddr(tb, lane_base, tc_dmain(half));
                     auto release = [&]() {
                         umma::fence_before_sync();
                         umma::mbar_arrive(&bars[B_DEMPTY_D + half]);
+                        ZF_TR(trs);   // released
                     };
                     const float xv = xs[pmod(jj - rot, D) * UM + m];
                     float g_x;
                     if (K == 16) g_x = vjp_row_tmem<16>(dbase, bls + jj * NL, row, xv, gyv, gld, release);
                     else g_x = vjp_row_tmem<32>(dbase, bls + jj * NL, row, xv, gyv, gld, release);
+                    ZF_TR(trs);   // row cotangent done
                     if (m < nm) a.gx[(m0 + m) * D + jj] = g_x;
                     {   // this thread's row -> the event-row image: 16-byte units of 8 columns, hi and lo parts; the 32 lanes of a
                         // warp write 512 contiguous bytes per unit
@@ -1317,7 +1333,9 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
     float* xraw = cs + C * UM;                // [UM][D] | [UM][C]  next tile as it lies in global memory (cp.async)
     float* hs = xraw + UM * (D + C);          // [Fmax][UM]  x - mean (couplings whose first Dense reads it from shared memory)
     float* cst = hs + umma_hs_floats(a.u_fmax, a.u_w0img != 0);   // [2][cl.total] per-coupling constants
-    float* ldx = cst + 2 * cl.total;
+    // the VJP kernel runs ONE coupling: its constants are fetched once and both buffer indices name the same block
+    const int cst_stride = VJP ? 0 : cl.total;
+    float* ldx = cst + (VJP ? 1 : 2) * cl.total;
     float* pairx = ldx + 3 * UM;              // [7][UM] exchange between the two threads of a shared spline row
     float* scratch = pairx + 8 * UM;          // [2][8][UM] float4: scratch columns of the lean spline rows
     float* ring = scratch + (VJP ? 2 * UM * VJP_ROW : 2 * 8 * UM * 4);   // VJP: [2][UM][VJP_ROW] theta rows instead
@@ -1379,8 +1397,12 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
             auto issue_consts = [&](const StepDesc& sn) {   // constant block of the kc-th coupling of this CTA
                 const uint32_t b = kc & 1u;
                 mbar_wait(&bars[B_CEMPTY + b], ((kc >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&bars[B_CFULL + b], (uint32_t)cl.total * 4u);
-                bulk_copy_g2s(cst + (size_t)b * cl.total, wsf + sn.off_C, (uint32_t)cl.total * 4u, &bars[B_CFULL + b]);
+                if (VJP && kc > 0) {
+                    umma::mbar_arrive(&bars[B_CFULL + b]);   // already resident
+                } else {
+                    mbar_arrive_expect_tx(&bars[B_CFULL + b], (uint32_t)cl.total * 4u);
+                    bulk_copy_g2s(cst + (size_t)b * cst_stride, wsf + sn.off_C, (uint32_t)cl.total * 4u, &bars[B_CFULL + b]);
+                }
                 ++kc;
             };
             auto issue_inputs = [&](long long t) {
@@ -1447,7 +1469,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
                 const StepDesc& s = steps[INVERSE ? (a.n_steps - 1 - si) : si];
                 if (s.kind != kStepKindCoupling) continue;
                 const int L = s.n_hidden, NL = ru(3 * s.K - 1, 16);
-                const bool tcfd = !VJP && a.u_w0img && s.F <= 16;
+                const bool tcfd = a.u_w0img && s.F <= 16;
                 if (tcfd) {
                     // first Dense: A = the epilogue's (x - mean) operand in tensor memory, B = the W0 image of this
                     // coupling's constant block; one k-step (K = 16), three products into ONE accumulator [TC_FD, +128):
@@ -1460,7 +1482,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
                     p_a0 ^= 1u;
                     umma::fence_after_sync();
                     if (umma::elect_one()) {
-                        const uint32_t w0 = smem_u32(cst + (size_t)cbm * cl.total + cl.w0i);
+                        const uint32_t w0 = smem_u32(cst + (size_t)cbm * cst_stride + cl.w0i);
                         const uint64_t b_hi = umma::smem_desc_kmajor(w0, 2048u, 128u), b_lo = umma::smem_desc_kmajor(w0 + 4096u, 2048u, 128u);
                         constexpr uint32_t idesc = umma::instr_desc_f16(128);
                         umma::mma_f16_ts(tb + TC_FD, tb + TC_ALO, b_hi, idesc, false);
@@ -1556,7 +1578,7 @@ __global__ void __launch_bounds__(320, 1) chain_umma_kernel(const __grid_constan
         }
     };
     // ------------------------------------------------------------------ role dispatch
-    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, reinterpret_cast<float4*>(scratch), bars, steps, tb, n_tiles, cl, in16, in_bytes};
+    const UCtx cx{a, xs, cs, xraw, hs, cst, ldx, pairx, reinterpret_cast<float4*>(scratch), bars, steps, tb, n_tiles, cl, cst_stride, in16, in_bytes};
     if (warp == PW) producer_role();
     else if (warp == MW) mma_role();
     else umma_epilogue_role<INVERSE, VJP>(cx);
@@ -2107,7 +2129,7 @@ struct Plan {
     bool w0img = false;                   // constant blocks carry the first Dense's operand image (tensor-core first Dense)
 };
 
-// for_vjp: the plan of the fused VJP kernel (its shared memory has no room for the first Dense's operand images)
+// for_vjp: the plan of the fused VJP kernel (a chain of one coupling, multi-dim or not)
 static int build_plan(const zf_chain* chain, Plan& plan, bool for_vjp = false) {
     ZF_REQUIRE(chain != nullptr, "chain is NULL");
     const int D = chain->dim, C = chain->cdim;
@@ -2194,7 +2216,7 @@ static int build_plan(const zf_chain* chain, Plan& plan, bool for_vjp = false) {
     plan.rot_total = rot;
     // multi-dim couplings with at most 16 conditioner inputs: first Dense on the tensor cores (single-tile kernel)
     static const bool simt_fd = [] { const char* e = getenv("ZF_FD_IMPL"); return e && e[0] == 's'; }();   // developer A/B switch
-    plan.w0img = !for_vjp && !simt_fd && plan.umma_ok && plan.n_couplings > 0 && !plan.all_d1 && plan.Fmax <= 16;
+    plan.w0img = !simt_fd && plan.umma_ok && plan.n_couplings > 0 && (for_vjp || !plan.all_d1) && plan.Fmax <= 16;
 
     // workspace layout: StepDesc array, then per-step blocks (all multiples of 4 floats)
     size_t off = (sizeof(StepDesc) * std::max<size_t>(plan.jobs.size(), 1) + 15) / 16 * 4;
@@ -2424,7 +2446,7 @@ size_t coupling_vjp_ws_floats(const zf_coupling* cp, int D, int C) {
     if (vjp_plan(cp, D, C, plan, op, chain) != ZF_OK || !plan.umma_ok || plan.n_couplings != 1) return 0;
     DeviceInfo di;
     if (get_device_info(&di) != ZF_OK) return 0;
-    if (umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true) * sizeof(float) > (size_t)di.max_smem_optin) return 0;
+    if (umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true, plan.w0img) * sizeof(float) > (size_t)di.max_smem_optin) return 0;
     return plan.ws_floats;
 }
 
@@ -2459,7 +2481,7 @@ int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, c
     a.act_rows = plan.act_rows;
     a.mode = kModeVjp;
     a.n_couplings = 1;
-    a.u_fmax = plan.Fmax; a.u_hmax = plan.Hmax; a.u_blmax = plan.BLmax;
+    a.u_fmax = plan.Fmax; a.u_hmax = plan.Hmax; a.u_blmax = plan.BLmax; a.u_w0img = plan.w0img ? 1 : 0;
     a.gy = gy; a.glp = glp; a.gx = gx;
     a.img_h0 = static_cast<char*>(img_h0); a.wh0 = wh0; a.img_dtheta = static_cast<char*>(img_dtheta);
     a.gy_rot = ((gy_rot % D) + D) % D;
@@ -2471,7 +2493,7 @@ int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, c
         ZF_REQUIRE(((reinterpret_cast<uintptr_t>(img_act[l]) | reinterpret_cast<uintptr_t>(act_g[l])) & 15) == 0,
                    "coupling_vjp: images must be 16-byte aligned");
     }
-    const size_t smem = umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true) * sizeof(float);
+    const size_t smem = umma_smem_floats(D, C, plan.Fmax, plan.Hmax, plan.BLmax, true, plan.w0img) * sizeof(float);
     static std::mutex mu;
     static std::map<int, size_t> done;
     {
@@ -2584,7 +2606,10 @@ extern "C" int zf_flow_sample_packed(void* stream, const zf_chain* chain, int32_
 }
 
 #ifdef ZF_TRACE
-extern "C" int zf_debug_trace_read(long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, zf::g_zf_trace, sizeof(long long) * 4 * 64);
+extern "C" int zf_debug_trace_read(long long* out) {   // read and clear
+    int rc = (int)cudaMemcpyFromSymbol(out, zf::g_zf_trace, sizeof(long long) * 4 * 64);
+    static long long zeros[4 * 64];
+    if (rc == 0) rc = (int)cudaMemcpyToSymbol(zf::g_zf_trace, zeros, sizeof(zeros));
+    return rc;
 }
 #endif

@@ -180,10 +180,13 @@ struct ImgTnArgs {
     long long n_tiles;
     int NS;                     // columns per CTA (<= 128, % 16 == 0); gridDim.y slabs
 };
-// Shared memory is a ring of 32 KB slots; a 128-event tile takes four of them in the order A hi, A lo, B hi, B lo, each
-// ONE bulk copy (a whole part of a tile is contiguous in the image: the A part always, the B part for a slab of
-// consecutive feature groups).  Six slots = one and a half tiles in flight.  The products run pass by pass
-// (A lo B hi, then A hi B lo, then A hi B hi) so that the lo parts' slots are handed back early.
+// Shared memory is a ring of 32 KB slots; a 128-event tile takes four of them, each ONE bulk copy (a whole part of a
+// tile is contiguous in the image: the A part always, the B part for a slab of consecutive feature groups).  Six slots =
+// one and a half tiles in flight.  The products run pass by pass in the order A lo B hi, A hi B hi, A hi B lo and the
+// parts are fetched in the order A lo, B hi, A hi, B lo: slots are then handed back in exactly the order they were
+// filled (A lo after pass 1, B hi after pass 2, A hi and B lo after pass 3), so the ring never waits for the END of a
+// tile before it can fetch the next tile's first operands (with the passes ordered lo-hi, hi-lo, hi-hi the B parts of
+// tile t+1 sat behind tile t's A hi slot, released last: one exposed load latency per tile).
 constexpr int TN_SLOTS = 6, TN_SLOT_BYTES = 32768, TN_NS = 128;
 
 __global__ void __launch_bounds__(IG_THREADS, 1) img_tn_kernel(const __grid_constant__ ImgTnArgs g) {
@@ -221,10 +224,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) img_tn_kernel(const __grid_cons
             for (long long t = t0; t < t1; ++t) {
                 const char* at = g.A + (size_t)t * 2 * 128 * 256;
                 const char* bt = g.B + (size_t)t * 2 * g.WB * 256 + (size_t)(n0 >> 3) * 2048;
-                put(at, 32768u);
-                put(at + 32768, 32768u);
-                put(bt, bbytes);
-                put(bt + (size_t)g.WB * 256, bbytes);
+                put(at + 32768, 32768u);                 // A lo
+                put(bt, bbytes);                         // B hi
+                put(at, 32768u);                         // A hi
+                put(bt + (size_t)g.WB * 256, bbytes);    // B lo
             }
         }
         __syncwarp();
@@ -239,31 +242,35 @@ __global__ void __launch_bounds__(IG_THREADS, 1) img_tn_kernel(const __grid_cons
                 sl[i] = slot; ph[i] = phase;
                 if (++slot == TN_SLOTS) { slot = 0; phase ^= 1u; }
             }
-            for (int i = 0; i < 4; ++i) mbar_wait(&full[sl[i]], ph[i]);
+            for (int i = 0; i < 2; ++i) mbar_wait(&full[sl[i]], ph[i]);   // pass 1's operands; the others are awaited by the issuer
             umma::fence_after_sync();
             if (umma::elect_one()) {
-                const uint32_t ahi = smem_u32(smem + sl[0] * TN_SLOT_BYTES), alo = smem_u32(smem + sl[1] * TN_SLOT_BYTES);
-                const uint32_t bhi = smem_u32(smem + sl[2] * TN_SLOT_BYTES), blo = smem_u32(smem + sl[3] * TN_SLOT_BYTES);
+                const uint32_t alo = smem_u32(smem + sl[0] * TN_SLOT_BYTES), bhi = smem_u32(smem + sl[1] * TN_SLOT_BYTES);
+                const uint32_t ahi = smem_u32(smem + sl[2] * TN_SLOT_BYTES), blo = smem_u32(smem + sl[3] * TN_SLOT_BYTES);
                 // MN-major operands: K (events) direction stride 128 B = LBO, MN (features) direction 2048 B = SBO;
                 // one MMA = 16 events = 256 bytes along K
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     umma::mma_f16_ss(tb, ig_desc(alo + ks * 256u, 128u, 2048u), ig_desc(bhi + ks * 256u, 128u, 2048u), idesc, !(first && ks == 0));
                 }
-                umma::commit(&empty[sl[1]]);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    umma::mma_f16_ss(tb, ig_desc(ahi + ks * 256u, 128u, 2048u), ig_desc(blo + ks * 256u, 128u, 2048u), idesc, true);
-                    if (g.colsum) umma::mma_f16_ss(tb + 128u, one_d, ig_desc(blo + ks * 256u, 128u, 2048u), idesc1, !(first && ks == 0));
-                }
-                umma::commit(&empty[sl[3]]);
+                umma::commit(&empty[sl[0]]);
+                mbar_wait(&full[sl[2]], ph[2]);
+                umma::fence_after_sync();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     umma::mma_f16_ss(tb, ig_desc(ahi + ks * 256u, 128u, 2048u), ig_desc(bhi + ks * 256u, 128u, 2048u), idesc, true);
-                    if (g.colsum) umma::mma_f16_ss(tb + 128u, one_d, ig_desc(bhi + ks * 256u, 128u, 2048u), idesc1, true);
+                    if (g.colsum) umma::mma_f16_ss(tb + 128u, one_d, ig_desc(bhi + ks * 256u, 128u, 2048u), idesc1, !(first && ks == 0));
                 }
-                umma::commit(&empty[sl[0]]);
+                umma::commit(&empty[sl[1]]);
+                mbar_wait(&full[sl[3]], ph[3]);
+                umma::fence_after_sync();
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    umma::mma_f16_ss(tb, ig_desc(ahi + ks * 256u, 128u, 2048u), ig_desc(blo + ks * 256u, 128u, 2048u), idesc, true);
+                    if (g.colsum) umma::mma_f16_ss(tb + 128u, one_d, ig_desc(blo + ks * 256u, 128u, 2048u), idesc1, true);
+                }
                 umma::commit(&empty[sl[2]]);
+                umma::commit(&empty[sl[3]]);
             }
             __syncwarp();
             first = false;

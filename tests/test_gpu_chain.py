@@ -34,6 +34,10 @@ CONFIGS = [
     ("cond16", 16, 4, 32, (128, 128), 8, 2, 1500),
     ("one_hidden_k32", 3, 2, 32, (128,), 4, 1, 4099),      # tensor-core kernels with no hidden-layer GEMM
     ("three_hidden", 2, 0, 16, (128, 128, 128), 3, 1, 2500),
+    # multi-dim couplings on the tensor-core kernel: > 16 conditioner inputs (first Dense on the FFMA pipe), K = 16 rows
+    # in both theta buffers; and an odd number of transformed dims with a tensor-core first Dense of 4 inputs
+    ("wide_cond24", 24, 8, 16, (128, 128), 3, 3, 1700),
+    ("odd_dims6", 6, 1, 32, (128, 128), 4, 1, 2100),
     ("odd", 5, 3, 7, (64, 48), None, 1, 2000),
     ("wide", 3, 0, 4, (200,), None, 1, 333),
 ]

@@ -88,6 +88,8 @@ GRAD_CASES = [
     (2, 1, 16, (128, 128), None, 1, 700, 1.5),
     (16, 4, 32, (128, 128), 3, 2, 260, 1.0),
     (3, 0, 5, (40,), None, 1, 515, 1.5),
+    (24, 8, 16, (128, 128), 2, 3, 300, 1.0),   # fused VJP kernel: 20 conditioner inputs (FFMA first Dense), K = 16 rows
+    (6, 1, 32, (128, 128), 2, 1, 400, 1.0),    # fused VJP kernel: 3 transformed dims, tensor-core first Dense of 4 inputs
 ]
 
 

@@ -981,10 +981,10 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             mbar_wait(&bars[B_CFULL + cb], (ke >> 1) & 1u);
             ZF_TR(trs);   // constants staged
             // ---- hstack(xc, c) + eval BatchNorm (bijectors.py:341-342).  Scale and bias are folded into the first
-            // Dense at pack time, what is left is x - mean: for the input counts the first Dense is specialised on, every
-            // thread takes it straight from the tile (no staging, no barrier); otherwise the halves share the features
+            // Dense at pack time, what is left is x - mean: when the first Dense runs on the tensor cores every thread takes
+            // it straight from the tile (no staging, no barrier); otherwise the halves share the features
             const bool tcfd = a.u_w0img && F <= 16;   // first Dense on the tensor cores (see below)
-            const bool direct = !VJP && (tcfd || F == 8 || F == 12 || F == 16);
+            const bool direct = !VJP && tcfd;
             if (!direct) {
                 for (int f = half; f < F; f += NG) {
                     const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
@@ -1029,27 +1029,14 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 }
             };
             if (VJP && !tcfd) vjp_side_outputs();
-            // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory
-            // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them
-            // FN > 0: exactly F = FN inputs, all of them in registers for all chunks and the rows fully unrolled (the
-            // 16-D flows: F = 8 / 12 / 16): the chunk loop then has no load -> FMA dependency on hs and no predicated-off
-            // rows.  FN = 0: any F, the first four inputs in registers (F is 2 on the 2-D flows), the rest in a loop.
-            auto first_dense = [&](auto ftag) {
-                constexpr int FN = decltype(ftag)::value;
-                constexpr int HR = FN > 0 ? FN : 4;
-                float hreg[HR];
-                if (FN > 0 && !VJP) {
-                    int col = pmod(d - rot, D);
+            // ---- first Dense (K = F) on the FFMA pipe, output straight into tensor memory: couplings with more than 16
+            // conditioner inputs, and flows of single-dim couplings run through this kernel (F is 2 or 3 there).
+            // K-chunk c of the next GEMM = columns [32c, 32c+32): this half owns 16 of them.  The event's first four inputs
+            // stay in registers for all chunks, the rest are read from hs in a loop.
+            auto first_dense = [&]() {
+                float hreg[4];
 #pragma unroll
-                    for (int f = 0; f < HR; ++f) {
-                        const float v = (f < D - d) ? xs[col * UM + m] : cs[(f - (D - d)) * UM + m];
-                        hreg[f] = v - bns[F_p + f];
-                        if (++col == D) col = 0;
-                    }
-                } else {
-#pragma unroll
-                    for (int f = 0; f < HR; ++f) hreg[f] = (FN > 0 || f < F) ? hs[f * UM + m] : 0.f;
-                }
+                for (int f = 0; f < 4; ++f) hreg[f] = f < F ? hs[f * UM + m] : 0.f;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int n0 = c * 32 + half * CW;
@@ -1074,15 +1061,10 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                             acc[g4 * 4 + 3] = fmaf(h, wv.w, acc[g4 * 4 + 3]);
                         }
                     };
-                    if constexpr (FN > 0) {
 #pragma unroll
-                        for (int f = 0; f < FN; ++f) fma_row(hreg[f], f);
-                    } else {
-#pragma unroll
-                        for (int f = 0; f < 4; ++f)
-                            if (f < F) fma_row(hreg[f], f);
-                        for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
-                    }
+                    for (int f = 0; f < 4; ++f)
+                        if (f < F) fma_row(hreg[f], f);
+                    for (int f = 4; f < F; ++f) fma_row(hs[f * UM + m], f);
                     if (VJP) vjp_activation<CW>(a, 0, tile, m0, m, nm, n0, acc, ahi, alo);
                     else activation_compute<CW>(acc, ahi, alo);
                     activation_store<CW>(tb, lane_base, n0, ahi, alo);
@@ -1118,10 +1100,9 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 umma::fence_before_sync();
                 umma::mbar_arrive(&bars[B_A0READY]);
                 if (VJP) vjp_side_outputs();   // under the first Dense's MMAs
-            } else if (F == 8) first_dense(std::integral_constant<int, 8>{});
-            else if (F == 12) first_dense(std::integral_constant<int, 12>{});
-            else if (F == 16) first_dense(std::integral_constant<int, 16>{});
-            else first_dense(std::integral_constant<int, 0>{});
+            } else {
+                first_dense();
+            }
             ZF_TR(trs);   // first dense done
             // ---- hidden layers 1..L-1: accumulator -> bias + swish -> next activations
             // FD: the accumulator of the tensor-core first Dense (one merged accumulator, bias b0'); otherwise a hidden
@@ -2215,8 +2196,7 @@ static int build_plan(const zf_chain* chain, Plan& plan, bool for_vjp = false) {
     }
     plan.rot_total = rot;
     // multi-dim couplings with at most 16 conditioner inputs: first Dense on the tensor cores (single-tile kernel)
-    static const bool simt_fd = [] { const char* e = getenv("ZF_FD_IMPL"); return e && e[0] == 's'; }();   // developer A/B switch
-    plan.w0img = !simt_fd && plan.umma_ok && plan.n_couplings > 0 && (for_vjp || !plan.all_d1) && plan.Fmax <= 16;
+    plan.w0img = plan.umma_ok && plan.n_couplings > 0 && (for_vjp || !plan.all_d1) && plan.Fmax <= 16;
 
     // workspace layout: StepDesc array, then per-step blocks (all multiples of 4 floats)
     size_t off = (sizeof(StepDesc) * std::max<size_t>(plan.jobs.size(), 1) + 15) / 16 * 4;

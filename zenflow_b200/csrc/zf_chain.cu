@@ -259,7 +259,7 @@ struct ChainArgs {
     // outputs for the Dense VJPs, as event-row images (bf16 x 2, csrc/zf_img_gemm.cu) of whole 128-event tiles
     char* img_h0;       // width wh0: BatchNorm output, feature F = 1 (the bias column), zero padding
     char* img_act[ZF_MAX_LAYERS];   // width 128: swish of the hidden pre-activations
-    float* act_g[ZF_MAX_LAYERS];    // (M, 128) fp32: swish' of the hidden pre-activations
+    float* act_g[ZF_MAX_LAYERS];    // swish' of the hidden pre-activations, fp32 tile images [tile][n / 4][event % 128][n % 4]
     char* img_dtheta;   // width d NL: cotangent of theta, dim j in columns [j NL, j NL + 3K-1), padding zero
     int wh0, gy_rot;
 };
@@ -799,10 +799,11 @@ __device__ __forceinline__ void vjp_activation(const ChainArgs& a, int layer, lo
     }
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i) umma::split_f16x2(sw[2 * i], sw[2 * i + 1], ahi[i], alo[i]);
-    if (valid) {
-        float4* go = reinterpret_cast<float4*>(a.act_g[layer] + (m0 + m) * 128 + n0);
+    if (valid) {   // fp32 tile image [tile][n / 4][event][n % 4]: a warp writes 512 contiguous bytes per 4-column unit
+        char* go = reinterpret_cast<char*>(a.act_g[layer]) + (size_t)tile * (128 * 128 * 4) + (size_t)(n0 >> 2) * 2048 + (size_t)m * 16;
 #pragma unroll
-        for (int g4 = 0; g4 < CW / 4; ++g4) go[g4] = make_float4(gs[g4 * 4], gs[g4 * 4 + 1], gs[g4 * 4 + 2], gs[g4 * 4 + 3]);
+        for (int g4 = 0; g4 < CW / 4; ++g4)
+            *reinterpret_cast<float4*>(go + (size_t)g4 * 2048) = make_float4(gs[g4 * 4], gs[g4 * 4 + 1], gs[g4 * 4 + 2], gs[g4 * 4 + 3]);
     }
     char* it = a.img_act[layer] + (size_t)tile * 2 * 128 * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16;
 #pragma unroll

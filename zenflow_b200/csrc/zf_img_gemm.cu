@@ -33,7 +33,8 @@ __device__ __forceinline__ uint64_t ig_desc(uint32_t addr, uint32_t lbo, uint32_
 struct ImgNtArgs {
     const char* X; int KW;      // event-row image, KW % 16 == 0
     const char* W; int N;       // [part][k / 8][n / 8][n % 8][k % 8] bf16 x 2, N rows (16 .. 128, % 16 == 0)
-    const float* G; int ldg;    // optional fp32 (M, >= N): the product is multiplied by it (swish' of the pre-activations)
+    const float* G; int ldg;    // optional fp32: the product is multiplied by it (swish' of the pre-activations); (M, ldg >= N) row-major,
+                                // or ldg < 0: tile image [tile][n / 4][event % 128][n % 4] of width 128 (coalesced on both sides)
     char* out_img;              // optional event-row image of width N
     float* out_f32; int ldo, n_valid;   // optional fp32 (M, ldo), the first n_valid columns
     long long M;
@@ -119,6 +120,21 @@ __global__ void __launch_bounds__(IG_THREADS, 1) img_nt_kernel(const __grid_cons
             const uint32_t buf = it & 1u;
             const long long e = t * 128 + m;
             const bool valid = e < g.M;
+            // the multiplier's 16 columns of chunk c0 + 16 are fetched while chunk c0 is processed; the first chunk's
+            // before the accumulator is awaited
+            const bool tiled = g.ldg < 0;
+            const int gq = tiled ? 128 : 1;   // float4 units between consecutive 4-column groups
+            const bool use_g = g.G != nullptr && valid;
+            auto g_ptr = [&](int c0) {
+                return tiled ? reinterpret_cast<const float4*>(g.G + (size_t)t * (128 * 128) + (size_t)(c0 >> 2) * 512 + (size_t)m * 4)
+                             : reinterpret_cast<const float4*>(g.G + e * g.ldg + c0);
+            };
+            float4 gn[4];
+            if (use_g) {
+                const float4* gp = g_ptr(0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gn[q] = gp[q * gq];
+            }
             mbar_wait(&dfull[buf], (it >> 1) & 1u);
             umma::fence_after_sync();
             char* ot = g.out_img ? g.out_img + (size_t)t * 2 * N * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16 : nullptr;
@@ -126,15 +142,21 @@ __global__ void __launch_bounds__(IG_THREADS, 1) img_nt_kernel(const __grid_cons
             for (int c0 = 0; c0 < N; c0 += 16) {
                 float v[16];
                 umma::ld16(umma::taddr(tb, warp * 32, buf * 128u + c0), v);
-                umma::wait_ld();
-                if (g.G) {
-                    if (valid) {
-                        const float4* gp = reinterpret_cast<const float4*>(g.G + e * g.ldg + c0);
+                float4 gc[4];
+                if (use_g) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 gv = gp[q];
-                            v[4 * q] *= gv.x; v[4 * q + 1] *= gv.y; v[4 * q + 2] *= gv.z; v[4 * q + 3] *= gv.w;
-                        }
+                    for (int q = 0; q < 4; ++q) gc[q] = gn[q];
+                    if (c0 + 16 < N) {
+                        const float4* gp = g_ptr(c0 + 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) gn[q] = gp[q * gq];
+                    }
+                }
+                umma::wait_ld();
+                if (use_g) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        v[4 * q] *= gc[q].x; v[4 * q + 1] *= gc[q].y; v[4 * q + 2] *= gc[q].z; v[4 * q + 3] *= gc[q].w;
                     }
                 }
                 if (!valid) {

@@ -727,7 +727,7 @@ static size_t cpl_bwd_batch_bytes(const zf_coupling* cp, const CplBwdLayout& lay
         return (n * (size_t)Mb + 64) * sizeof(float);
     }
     size_t b = up256(zf::img_bytes(Mb, lay.TW)) + up256(zf::img_bytes(Mb, lay.WH)) + 2 * up256(zf::img_bytes(Mb, 128));
-    b += (size_t)L * (up256(zf::img_bytes(Mb, 128)) + up256((size_t)Mb * 128 * 4));
+    b += (size_t)L * (up256(zf::img_bytes(Mb, 128)) + up256(zf::img_bytes(Mb, 128)));   // activation image + swish' tile image (same size)
     return b;
 }
 
@@ -777,7 +777,7 @@ static int coupling_backward_fused(cudaStream_t st, const zf_coupling* cp, const
         float* act_g[ZF_MAX_LAYERS];
         for (int l = 0; l < L; ++l) {
             img_act[l] = take(img_bytes(Mb, 128));
-            act_g[l] = reinterpret_cast<float*>(take((size_t)Mb * 128 * 4));
+            act_g[l] = reinterpret_cast<float*>(take(img_bytes(Mb, 128)));   // fp32 tile image: whole tiles
         }
         // BatchNorm, conditioner (theta in tensor memory), spline VJP: writes gx and the images
         if (int rc = coupling_vjp_run(st, cp, D, C, pack, x_in + m0 * D, c ? c + m0 * C : nullptr, gy + m0 * D, gy_rot, glp + m0, Mb,
@@ -785,12 +785,12 @@ static int coupling_backward_fused(cudaStream_t st, const zf_coupling* cp, const
             return rc;
         // last Dense (padded column space): dW_L, db_L, dZ_L = (dTheta W_L^T) swish'(Z_L)
         if (int rc = launch_img_tn(st, img_act[L - 1], img_dt, TW, gWp, TW, 1, 128, TW, gbp, nullptr, -1, Mb)) return rc;
-        if (int rc = launch_img_nt(st, img_dt, TW, ws + lay.off_wimg[L], 128, act_g[L - 1], 128, img_dz[0], nullptr, 0, 0, Mb)) return rc;
+        if (int rc = launch_img_nt(st, img_dt, TW, ws + lay.off_wimg[L], 128, act_g[L - 1], -1, img_dz[0], nullptr, 0, 0, Mb)) return rc;
         int cur = 0;
         for (int l = L - 1; l >= 1; --l) {   // hidden Dense_l: input swish(Z_l), output cotangent dZ_{l+1}
             if (int rc = launch_img_tn(st, img_act[l - 1], img_dz[cur], 128, gr->kernel[l], 128, 1, 128, 128, gr->bias[l], nullptr, -1, Mb))
                 return rc;
-            if (int rc = launch_img_nt(st, img_dz[cur], 128, ws + lay.off_wimg[l], 128, act_g[l - 1], 128, img_dz[cur ^ 1], nullptr, 0, 0, Mb))
+            if (int rc = launch_img_nt(st, img_dz[cur], 128, ws + lay.off_wimg[l], 128, act_g[l - 1], -1, img_dz[cur ^ 1], nullptr, 0, 0, Mb))
                 return rc;
             cur ^= 1;
         }

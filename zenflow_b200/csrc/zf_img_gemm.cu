@@ -120,43 +120,35 @@ __global__ void __launch_bounds__(IG_THREADS, 1) img_nt_kernel(const __grid_cons
             const uint32_t buf = it & 1u;
             const long long e = t * 128 + m;
             const bool valid = e < g.M;
-            // the multiplier's 16 columns of chunk c0 + 16 are fetched while chunk c0 is processed; the first chunk's
-            // before the accumulator is awaited
+            // The multiplier's whole row of this tile (N <= 128 columns: 32 float4 registers) is requested BEFORE the
+            // accumulator is awaited: one exposed memory latency per tile instead of one per 16-column chunk (the four
+            // epilogue warps are alone on their schedulers, nothing else would hide it).
             const bool tiled = g.ldg < 0;
             const int gq = tiled ? 128 : 1;   // float4 units between consecutive 4-column groups
             const bool use_g = g.G != nullptr && valid;
-            auto g_ptr = [&](int c0) {
-                return tiled ? reinterpret_cast<const float4*>(g.G + (size_t)t * (128 * 128) + (size_t)(c0 >> 2) * 512 + (size_t)m * 4)
-                             : reinterpret_cast<const float4*>(g.G + e * g.ldg + c0);
-            };
-            float4 gn[4];
+            float4 gall[32];
             if (use_g) {
-                const float4* gp = g_ptr(0);
+                const float4* gp = tiled ? reinterpret_cast<const float4*>(g.G + (size_t)t * (128 * 128) + (size_t)m * 4)
+                                         : reinterpret_cast<const float4*>(g.G + e * g.ldg);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) gn[q] = gp[q * gq];
+                for (int q = 0; q < 32; ++q)
+                    if (4 * q < N) gall[q] = gp[q * gq];
             }
             mbar_wait(&dfull[buf], (it >> 1) & 1u);
             umma::fence_after_sync();
             char* ot = g.out_img ? g.out_img + (size_t)t * 2 * N * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16 : nullptr;
-#pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 16) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const int c0 = ci * 16;
+                if (c0 >= N) break;
                 float v[16];
                 umma::ld16(umma::taddr(tb, warp * 32, buf * 128u + c0), v);
-                float4 gc[4];
-                if (use_g) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) gc[q] = gn[q];
-                    if (c0 + 16 < N) {
-                        const float4* gp = g_ptr(c0 + 16);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) gn[q] = gp[q * gq];
-                    }
-                }
                 umma::wait_ld();
                 if (use_g) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        v[4 * q] *= gc[q].x; v[4 * q + 1] *= gc[q].y; v[4 * q + 2] *= gc[q].z; v[4 * q + 3] *= gc[q].w;
+                        const float4 gv = gall[4 * ci + q];
+                        v[4 * q] *= gv.x; v[4 * q + 1] *= gv.y; v[4 * q + 2] *= gv.z; v[4 * q + 3] *= gv.w;
                     }
                 }
                 if (!valid) {

@@ -930,7 +930,23 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
         if (bulk) mbar_wait(&bars[B_XFULL], xk & 1u);
         const float* xsrc = bulk ? xraw : a.x + m0 * D;
         const float* csrc = bulk ? xraw + UM * D : a.c + m0 * C;
-        {   // element e = mm * D + j, advanced by 256 per round without dividing
+        const bool xs16 = (D & 3) == 0 && !a.sample && (reinterpret_cast<uintptr_t>(xsrc) & 15) == 0;
+        const bool cs16 = C > 0 && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(csrc) & 15) == 0;
+        if (xs16) {
+            // this thread: every second group of four columns of its own event, one 16-byte read per group and
+            // conflict-free writes into the feature-major tile
+            const float4* xr = reinterpret_cast<const float4*>(xsrc + (size_t)m * D);
+            for (int q = half; q < (D >> 2); q += NG) {
+                const float4 v = (m < nm) ? xr[q] : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                int col = pmod(4 * q - rot_in, D);
+                const float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    xs[col * UM + m] = o[i];
+                    if (++col == D) col = 0;
+                }
+            }
+        } else {   // element e = mm * D + j, advanced by 256 per round without dividing
             int mm = tid / D, j = tid - mm * D;
             const int dm = ET / D, dj = ET - dm * D;
             for (int e = tid; e < UM * D; e += ET) {
@@ -942,7 +958,14 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 if (j >= D) { j -= D; ++mm; }
             }
         }
-        if (C) {
+        if (cs16) {
+            const float4* cr = reinterpret_cast<const float4*>(csrc + (size_t)m * C);
+            for (int q = half; q < (C >> 2); q += NG) {
+                const float4 v = (m < nm) ? cr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                cs[(4 * q + 0) * UM + m] = v.x; cs[(4 * q + 1) * UM + m] = v.y;
+                cs[(4 * q + 2) * UM + m] = v.z; cs[(4 * q + 3) * UM + m] = v.w;
+            }
+        } else if (C) {
             int mm = tid / C, j = tid - mm * C;
             const int dm = ET / C, dj = ET - dm * C;
             for (int e = tid; e < UM * C; e += ET) {
@@ -985,7 +1008,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             // Dense at pack time, what is left is x - mean: when the first Dense runs on the tensor cores every thread takes
             // it straight from the tile (no staging, no barrier); otherwise the halves share the features
             const bool tcfd = a.u_w0img && F <= 16;   // first Dense on the tensor cores (see below)
-            const bool direct = !VJP && tcfd;
+            const bool direct = tcfd;
             if (!direct) {
                 for (int f = half; f < F; f += NG) {
                     const float v = (f < D - d) ? xs[pmod(d + f - rot, D) * UM + m] : cs[(f - (D - d)) * UM + m];
@@ -1001,10 +1024,17 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     char* ht = a.img_h0 + (size_t)tile * 2 * a.wh0 * 256 + (size_t)(m >> 3) * 128 + (size_t)(m & 7) * 16;
                     for (int g8 = half; g8 < (a.wh0 >> 3); g8 += NG) {
                         float hv[8];
+                        int col = pmod(d + g8 * 8 - rot, D);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int f = g8 * 8 + i;
-                            hv[i] = (m < nm) ? (f < F ? fmaf(hs[f * UM + m], bns[f], bns[2 * F_p + f]) : (f == F ? 1.0f : 0.f)) : 0.f;
+                            float v = f == F ? 1.0f : 0.f;
+                            if (f < F) {
+                                const float xm = ((f < D - d) ? xs[col * UM + m] : cs[(f - (D - d)) * UM + m]) - bns[F_p + f];
+                                v = fmaf(xm, bns[f], bns[2 * F_p + f]);
+                            }
+                            hv[i] = (m < nm) ? v : 0.f;
+                            if (++col == D) col = 0;
                         }
                         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -1013,20 +1043,22 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                         *reinterpret_cast<uint4*>(ht + (size_t)a.wh0 * 256 + (size_t)g8 * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
-                const int nc = D - d;
-                for (int e0 = tid; e0 < nm * nc; e0 += 4 * ET) {   // four loads in flight per thread
-                    float gv[4];
-                    long long go[4];
+                if (m < nm) {   // this thread: every second conditioning column of its own event, four loads in flight
+                    const float* gyr = a.gy + (m0 + m) * D;
+                    float* gxr = a.gx + (m0 + m) * D;
+                    int src = pmod(d + half + a.gy_rot, D);
+                    for (int j0 = d + half; j0 < D; j0 += 8) {
+                        float gv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int e = e0 + k * ET;
-                        const int mm = e / nc, j = d + (e - mm * nc);
-                        go[k] = (m0 + mm) * D + j;
-                        gv[k] = e < nm * nc ? a.gy[(m0 + mm) * D + pmod(j + a.gy_rot, D)] : 0.f;
+                        for (int k = 0; k < 4; ++k) {
+                            gv[k] = (j0 + 2 * k < D) ? gyr[src] : 0.f;
+                            src += 2;
+                            if (src >= D) src -= D;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (j0 + 2 * k < D) gxr[j0 + 2 * k] = gv[k];
                     }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (e0 + k * ET < nm * nc) a.gx[go[k]] = gv[k];
                 }
             };
             if (VJP && !tcfd) vjp_side_outputs();
@@ -1285,9 +1317,27 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
         } else {
             const int rot_out = INVERSE ? 0 : a.rot_total;
             if (a.y) {
-                for (int e = tid; e < nm * D; e += ET) {
-                    const int mm = e / D, j = e - mm * D;
-                    a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * UM + mm];
+                if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+                    // this thread: every second group of four columns of its own event (conflict-free reads of the
+                    // feature-major tile, one 16-byte store per group)
+                    if (m < nm) {
+                        float4* yr = reinterpret_cast<float4*>(a.y + (m0 + m) * D);
+                        for (int q = half; q < (D >> 2); q += NG) {
+                            int col = pmod(4 * q - rot_out, D);
+                            float o[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                o[i] = xs[col * UM + m];
+                                if (++col == D) col = 0;
+                            }
+                            yr[q] = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                } else {
+                    for (int e = tid; e < nm * D; e += ET) {
+                        const int mm = e / D, j = e - mm * D;
+                        a.y[m0 * D + e] = xs[pmod(j - rot_out, D) * UM + mm];
+                    }
                 }
             }
             if (!INVERSE && a.log_det && half == 0 && m < nm)

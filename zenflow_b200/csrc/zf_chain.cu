@@ -930,14 +930,24 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
         if (bulk) mbar_wait(&bars[B_XFULL], xk & 1u);
         const float* xsrc = bulk ? xraw : a.x + m0 * D;
         const float* csrc = bulk ? xraw + UM * D : a.c + m0 * C;
-        const bool xs16 = (D & 3) == 0 && !a.sample && (reinterpret_cast<uintptr_t>(xsrc) & 15) == 0;
+        const bool xs16 = (D & 3) == 0 && (a.sample || (reinterpret_cast<uintptr_t>(xsrc) & 15) == 0);
         const bool cs16 = C > 0 && (C & 3) == 0 && (reinterpret_cast<uintptr_t>(csrc) & 15) == 0;
         if (xs16) {
             // this thread: every second group of four columns of its own event, one 16-byte read per group and
             // conflict-free writes into the feature-major tile
             const float4* xr = reinterpret_cast<const float4*>(xsrc + (size_t)m * D);
             for (int q = half; q < (D >> 2); q += NG) {
-                const float4 v = (m < nm) ? xr[q] : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                float4 v = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                if (m < nm) {
+                    if (a.sample) {   // counter-based draws: the value of (event, column) does not depend on who computes it
+                        float dr[4];
+#pragma unroll 1
+                        for (int i = 0; i < 4; ++i) dr[i] = latent_draw(a.lc.kind, a.peakness, a.seed, m0 + m, 4 * q + i);
+                        v = make_float4(dr[0], dr[1], dr[2], dr[3]);
+                    } else {
+                        v = xr[q];
+                    }
+                }
                 int col = pmod(4 * q - rot_in, D);
                 const float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -975,6 +985,9 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
             }
         }
         if (bulk) { umma::mbar_arrive(&bars[B_XEMPTY]); ++xk; }
+        // the log-det this tile accumulates onto (train forward: one launch per coupling) is requested now, not at the end
+        float ld_prev = 0.f;
+        if (!VJP && !INVERSE && a.mode != kModeLogProb && a.log_det && a.acc_log_det && half == 0 && m < nm) ld_prev = a.log_det[m0 + m];
         epi_barrier<ET>();
         ZF_TR(trs);   // 1: inputs loaded
 
@@ -1341,7 +1354,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 }
             }
             if (!INVERSE && a.log_det && half == 0 && m < nm)
-                a.log_det[m0 + m] = a.acc_log_det ? a.log_det[m0 + m] + ld_acc : ld_acc;
+                a.log_det[m0 + m] = a.acc_log_det ? ld_prev + ld_acc : ld_acc;
         }
         epi_barrier<ET>();
         ZF_TR(trs);   // tile stored

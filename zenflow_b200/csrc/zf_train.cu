@@ -169,7 +169,22 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restric
         const float mu = mean[f];
         const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[f], 1e-5f)));
         double s1 = 0.0, s2 = 0.0;
-        for (long long m = (long long)blockIdx.x * R + r; m < M; m += (long long)gridDim.x * R) {
+        const long long step = (long long)gridDim.x * R;
+        long long m = (long long)blockIdx.x * R + r;
+        for (; m + 3 * step < M; m += 4 * step) {   // four rows in flight per thread (the loads are the whole cost)
+            float h[4], gg[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                h[k] = cond_feature(x, c, m + k * step, f, D, d, C);
+                gg[k] = g[(m + k * step) * F + f];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s1 += (double)gg[k];
+                s2 += (double)gg[k] * (double)((h[k] - mu) * rstd);
+            }
+        }
+        for (; m < M; m += step) {
             const float h = cond_feature(x, c, m, f, D, d, C);
             const float gg = g[m * F + f];
             s1 += (double)gg;
@@ -189,18 +204,42 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ var, const double* __restrict__ sums,
                                                            double count, float* __restrict__ gx, float* __restrict__ gc) {
     const int d = D / 2, F = D - d + C;
-    const long long n = M * F;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const long long m = e / F;
-        const int f = (int)(e - m * F);
-        const float h = cond_feature(x, c, m, f, D, d, C);
+    // per-feature constants once per block: scale * rstd, mean, rstd, sum(g) / count, sum(g xhat) / count
+    extern __shared__ float shc[];
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
         const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[f], 1e-5f)));
-        const float xhat = (h - mean[f]) * rstd;
-        const float s1 = (float)(sums[f] / count), s2 = (float)(sums[F + f] / count);
-        const float dh = scale[f] * rstd * (g[e] - s1 - xhat * s2);
-        if (f < D - d) gx[m * D + d + f] += dh;
-        else if (gc) gc[m * C + (f - (D - d))] += dh;
+        shc[f] = scale[f] * rstd;
+        shc[F + f] = mean[f];
+        shc[2 * F + f] = rstd;
+        shc[3 * F + f] = (float)(sums[f] / count);
+        shc[4 * F + f] = (float)(sums[F + f] / count);
     }
+    __syncthreads();
+    // thread = (row r of the pass, feature f): consecutive threads read consecutive elements of g
+    const int R = blockDim.x / F;
+    const int r = threadIdx.x / F, f = threadIdx.x - r * F;
+    if (r >= R) return;
+    const float a = shc[f], mu = shc[F + f], rstd = shc[2 * F + f], s1 = shc[3 * F + f], s2 = shc[4 * F + f];
+    const bool to_x = f < D - d;
+    const long long step = (long long)gridDim.x * R;
+    auto apply = [&](long long m, float h, float gg) {
+        const float xhat = (h - mu) * rstd;
+        const float dh = a * (gg - s1 - xhat * s2);
+        if (to_x) gx[m * D + d + f] += dh;
+        else if (gc) gc[m * C + (f - (D - d))] += dh;
+    };
+    long long m = (long long)blockIdx.x * R + r;
+    for (; m + 3 * step < M; m += 4 * step) {   // four rows in flight per thread
+        float h[4], gg[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h[k] = cond_feature(x, c, m + k * step, f, D, d, C);
+            gg[k] = g[(m + k * step) * F + f];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) apply(m + k * step, h[k], gg[k]);
+    }
+    for (; m < M; m += step) apply(m, cond_feature(x, c, m, f, D, d, C), g[m * F + f]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -798,7 +837,7 @@ static int coupling_backward_fused(cudaStream_t st, const zf_coupling* cp, const
         if (int rc = launch_img_tn(st, img_dz[cur], img_h0, lay.WH, gr->kernel[0], 1, 128, 128, F, nullptr, gr->bias[0], F, Mb)) return rc;
         if (int rc = launch_img_nt(st, img_dz[cur], 128, ws + lay.off_wimg[0], lay.WF0, nullptr, 0, nullptr, gh0 + m0 * F, F, F, Mb)) return rc;
         const int R = 256 / F;
-        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(
+        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 4), 256, 2 * F * sizeof(double), st>>>(
             x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
         count_launch();
     }
@@ -902,7 +941,7 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             if (int rc = launch_gemm(st, 1, ga)) return rc;
         }
         const int R = 256 / F;
-        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(
+        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 4), 256, 2 * F * sizeof(double), st>>>(
             x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
         count_launch();
     }
@@ -931,7 +970,8 @@ extern "C" int zf_bn_backward_apply(void* stream, const zf_coupling* cp, int32_t
                                     float* gx, float* gc) {
     ZF_REQUIRE(cp && x_in && gh0 && bn_sums && gx && M >= 1 && global_count >= 1, "bn_backward_apply: bad argument");
     const int d = D / 2, F = D - d + C;
-    bn_bwd_apply_kernel<<<grid_for(M * F, 256 * 8, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+    const int R = 256 / F;
+    bn_bwd_apply_kernel<<<grid_for(M, R * 16, 148 * 16), 256, 5 * F * sizeof(float), (cudaStream_t)stream>>>(
         x_in, c, gh0, M, D, C, cp->bn_scale, cp->bn_mean, cp->bn_var, bn_sums, global_count, gx, gc);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());

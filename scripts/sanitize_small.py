@@ -16,7 +16,8 @@ for (M, d, K) in [(1031, 1, 16), (517, 8, 32), (300, 3, 5)]:
 for impl in ("", "simt", "umma2"):
     if impl: os.environ["ZF_CHAIN_IMPL"] = impl
     else: os.environ.pop("ZF_CHAIN_IMPL", None)
-    for (D, C, K, layers, nc, roll, M) in [(2, 1, 16, (128, 128), None, 1, 777), (16, 4, 32, (128, 128), 3, 2, 300), (5, 3, 7, (64, 48), None, 1, 200)]:
+    for (D, C, K, layers, nc, roll, M) in [(2, 1, 16, (128, 128), None, 1, 777), (16, 4, 32, (128, 128), 3, 2, 300), (5, 3, 7, (64, 48), None, 1, 200),
+                                           (24, 8, 16, (128, 128), 2, 3, 390), (6, 1, 32, (128, 128), 2, 1, 270)]:
         ops = zo.make_chain(D, K, layers, n_couplings=nc, roll_shift=roll)
         x = rng.normal(0.3, 1.1, (M, D)).astype(np.float32); c = rng.uniform(0, 1, (M, C)).astype(np.float32) if C else None
         v = trained_variables(ops, x, c)
@@ -27,7 +28,8 @@ for impl in ("", "simt", "umma2"):
 os.environ.pop("ZF_CHAIN_IMPL", None)
 for gemm in ("", "simt"):
     if gemm: os.environ["ZF_GEMM_IMPL"] = gemm
-    for (D, C, K, layers, nc, roll, M) in [(16, 4, 32, (128, 128), 2, 2, 700), (3, 0, 5, (40,), None, 1, 333)]:
+    for (D, C, K, layers, nc, roll, M) in [(16, 4, 32, (128, 128), 2, 2, 700), (3, 0, 5, (40,), None, 1, 333), (24, 8, 16, (128, 128), 2, 3, 390),
+                                           (6, 1, 32, (128, 128), 2, 1, 270)]:
         ops = zo.make_chain(D, K, layers, n_couplings=nc, roll_shift=roll)
         x = rng.normal(0.3, 1.0, (M, D)).astype(np.float32); c = rng.uniform(0, 1, (M, C)).astype(np.float32) if C else None
         v = zo.init_variables(ops, D, C, 2, randomize_bn=True)

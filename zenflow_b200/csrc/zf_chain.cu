@@ -659,9 +659,6 @@ __device__ __forceinline__ float theta_block_finish(int col, const float* __rest
     return nan ? CUDART_INF_F : amax;
 }
 
-// |theta| < 4096 makes the exact fast forms valid without looking at the quotients: squareplus >= 2^-13
-// and the sum <= 2^17, so every s/sum quotient is >= 2^-30, far above the 2^-100 remainder-exactness bound.
-constexpr float kThetaFastBound = 4096.0f;
 
 // Locate the bin from tensor memory.  The three raw blocks are loaded in a software pipeline (the next
 // block's TMEM load is in flight while the current one is processed) and the D buffer is handed back to

@@ -40,7 +40,9 @@ rqs_stage_kernel(const __grid_constant__ StageArgs a) {
     const int P = a.P, R = a.R, S = a.stages, d = a.d;
     const int tile_floats = R * P;  // R % 4 == 0 -> 16-byte multiple
     float* bufs = reinterpret_cast<float*>(smem_raw);
-    float* ldrow = bufs + (size_t)S * tile_floats;
+    // K = 16 / 32: per-thread scratch columns of the lean row ([K / 4][threads] float4)
+    float4* scratch = reinterpret_cast<float4*>(bufs + (size_t)S * tile_floats);
+    float* ldrow = reinterpret_cast<float*>(scratch + (KT > 0 ? (KT / 4) * kStageThreads : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(ldrow + ((R + 3) & ~3));
 
     if (tid == 0) {
@@ -88,23 +90,36 @@ rqs_stage_kernel(const __grid_constant__ StageArgs a) {
             __syncthreads();
         }
 
-        for (int r = tid; r < rows; r += kStageThreads) {
-            const float v = (r == tid) ? v0 : a.v[row0 + r];
-            RqsBin b;
-            rqs_locate<KT>(buf + (size_t)r * P, a.K, !INVERSE, v, a.kn, b);
-            if (!INVERSE) {
-                float y, ld;
-                rqs_eval_forward(v, b, y, ld);
-                a.out[row0 + r] = y;
-                if (d == 1) a.log_det[row0 + r] = ld;
-                else ldrow[r] = ld;
-            } else {
-                a.out[row0 + r] = rqs_eval_inverse(v, b);
+        // d a power of two up to 32: the d rows of a sample sit in d consecutive lanes (tiles and passes start at
+        // multiples of d), their log-dets are summed with shuffles; otherwise through shared memory below
+        const bool shfl_sum = !INVERSE && d > 1 && d <= 32 && (d & (d - 1)) == 0;
+        for (int r0 = 0; r0 < rows; r0 += kStageThreads) {
+            const int r = r0 + tid;
+            const bool active = r < rows;
+            float ld = 0.f;
+            if (active) {
+                const float v = (r == tid) ? v0 : a.v[row0 + r];
+                RqsBin b;
+                if constexpr (KT > 0) rqs_locate_lean<KT>(buf + (size_t)r * P, !INVERSE, v, a.kn, b, scratch + tid, kStageThreads);
+                else rqs_locate<KT>(buf + (size_t)r * P, a.K, !INVERSE, v, a.kn, b);
+                if (!INVERSE) {
+                    float y;
+                    rqs_eval_forward(v, b, y, ld);
+                    a.out[row0 + r] = y;
+                    if (d == 1) a.log_det[row0 + r] = ld;
+                    else if (!shfl_sum) ldrow[r] = ld;
+                } else {
+                    a.out[row0 + r] = rqs_eval_inverse(v, b);
+                }
+                if (a.idx) a.idx[row0 + r] = b.idx;
             }
-            if (a.idx) a.idx[row0 + r] = b.idx;
+            if (shfl_sum) {
+                for (int o = d >> 1; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+                if (active && (r & (d - 1)) == 0) a.log_det[(row0 + r) / d] = ld;
+            }
         }
 
-        if (!INVERSE && d > 1) {  // log_det.sum(axis=1), utils.py:139
+        if (!INVERSE && d > 1 && !shfl_sum) {  // log_det.sum(axis=1), utils.py:139
             __syncthreads();
             const int ns = rows / d;
             for (int s = tid; s < ns; s += kStageThreads) {
@@ -148,7 +163,8 @@ static int launch_stage(cudaStream_t stream, const float* theta, const float* v,
     while (TS > 4 && (size_t)TS * d * row_bytes > 96 * 1024) TS -= 4;
     a.R = TS * d;
     const size_t tile_bytes = (size_t)a.R * row_bytes;
-    const size_t misc = (size_t)((a.R + 3) & ~3) * 4 + 8 * 8 + 128;
+    const size_t lean_scratch = (K == 16 || K == 32) ? (size_t)(K / 4) * kStageThreads * 16 : 0;
+    const size_t misc = (size_t)((a.R + 3) & ~3) * 4 + 8 * 8 + 128 + lean_scratch;
     const size_t budget = (size_t)di.max_smem_optin;
     if (tile_bytes + misc > budget)
         return fail(ZF_ERR_UNSUPPORTED, "rqs: one tile of %d rows x %d params does not fit shared memory", a.R, a.P);

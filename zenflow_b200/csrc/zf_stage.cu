@@ -30,19 +30,19 @@ struct StageArgs {
     KnotNorm kn;
 };
 
-constexpr int kStageThreads = 256;
+constexpr int kStageThreads = 256;   // at most; 128 when that lets two blocks share an SM (see launch_stage)
 
 template <int KT, bool INVERSE>
 __global__ void __launch_bounds__(kStageThreads)
 rqs_stage_kernel(const __grid_constant__ StageArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int P = a.P, R = a.R, S = a.stages, d = a.d;
     const int tile_floats = R * P;  // R % 4 == 0 -> 16-byte multiple
     float* bufs = reinterpret_cast<float*>(smem_raw);
     // K = 16 / 32: per-thread scratch columns of the lean row ([K / 4][threads] float4)
     float4* scratch = reinterpret_cast<float4*>(bufs + (size_t)S * tile_floats);
-    float* ldrow = reinterpret_cast<float*>(scratch + (KT > 0 ? (KT / 4) * kStageThreads : 0));
+    float* ldrow = reinterpret_cast<float*>(scratch + (KT > 0 ? (KT / 4) * nthr : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(ldrow + ((R + 3) & ~3));
 
     if (tid == 0) {
@@ -86,21 +86,21 @@ rqs_stage_kernel(const __grid_constant__ StageArgs a) {
             mbar_wait(&bars[stage], parity);
         } else {  // ragged last tile or unaligned theta: cooperative coalesced load
             const float* src = a.theta + row0 * P;
-            for (int i = tid; i < rows * P; i += kStageThreads) buf[i] = ld_stream(src + i);
+            for (int i = tid; i < rows * P; i += nthr) buf[i] = ld_stream(src + i);
             __syncthreads();
         }
 
         // d a power of two up to 32: the d rows of a sample sit in d consecutive lanes (tiles and passes start at
         // multiples of d), their log-dets are summed with shuffles; otherwise through shared memory below
         const bool shfl_sum = !INVERSE && d > 1 && d <= 32 && (d & (d - 1)) == 0;
-        for (int r0 = 0; r0 < rows; r0 += kStageThreads) {
+        for (int r0 = 0; r0 < rows; r0 += nthr) {
             const int r = r0 + tid;
             const bool active = r < rows;
             float ld = 0.f;
             if (active) {
                 const float v = (r == tid) ? v0 : a.v[row0 + r];
                 RqsBin b;
-                if constexpr (KT > 0) rqs_locate_lean<KT>(buf + (size_t)r * P, !INVERSE, v, a.kn, b, scratch + tid, kStageThreads);
+                if constexpr (KT > 0) rqs_locate_lean<KT>(buf + (size_t)r * P, !INVERSE, v, a.kn, b, scratch + tid, nthr);
                 else rqs_locate<KT>(buf + (size_t)r * P, a.K, !INVERSE, v, a.kn, b);
                 if (!INVERSE) {
                     float y;
@@ -122,7 +122,7 @@ rqs_stage_kernel(const __grid_constant__ StageArgs a) {
         if (!INVERSE && d > 1 && !shfl_sum) {  // log_det.sum(axis=1), utils.py:139
             __syncthreads();
             const int ns = rows / d;
-            for (int s = tid; s < ns; s += kStageThreads) {
+            for (int s = tid; s < ns; s += nthr) {
                 float acc = ldrow[s * d];
                 for (int j = 1; j < d; ++j) acc += ldrow[s * d + j];
                 a.log_det[row0 / d + s] = acc;
@@ -158,23 +158,37 @@ static int launch_stage(cudaStream_t stream, const float* theta, const float* v,
     // tile: TS samples (multiple of 4 so that every full tile is a 16-byte multiple), about
     // one row per thread, at most ~96 KB so that two stages always fit.
     const size_t row_bytes = (size_t)a.P * 4;
-    int TS = (kStageThreads / d) & ~3;
-    if (TS < 4) TS = 4;
-    while (TS > 4 && (size_t)TS * d * row_bytes > 96 * 1024) TS -= 4;
-    a.R = TS * d;
-    const size_t tile_bytes = (size_t)a.R * row_bytes;
-    const size_t lean_scratch = (K == 16 || K == 32) ? (size_t)(K / 4) * kStageThreads * 16 : 0;
-    const size_t misc = (size_t)((a.R + 3) & ~3) * 4 + 8 * 8 + 128 + lean_scratch;
     const size_t budget = (size_t)di.max_smem_optin;
-    if (tile_bytes + misc > budget)
+    int threads = kStageThreads, blocks_per_sm = 1, stages = 1;
+    size_t tile_bytes = 0, misc = 0;
+    auto config = [&](int T) -> bool {   // false: not even one tile fits
+        int TS = (T / d) & ~3;
+        if (TS < 4) TS = 4;
+        while (TS > 4 && (size_t)TS * d * row_bytes > 96 * 1024) TS -= 4;
+        a.R = TS * d;
+        threads = T;
+        tile_bytes = (size_t)a.R * row_bytes;
+        const size_t lean_scratch = (K == 16 || K == 32) ? (size_t)(K / 4) * T * 16 : 0;
+        misc = (size_t)((a.R + 3) & ~3) * 4 + 8 * 8 + 128 + lean_scratch;
+        if (tile_bytes + misc > budget) return false;
+        // two resident blocks of two stages when tiles are small, else one block with up to 4 stages
+        if (2 * (2 * tile_bytes + misc) + 2048 <= budget) { blocks_per_sm = 2; stages = 2; }
+        else {
+            blocks_per_sm = 1;
+            stages = (int)((budget - misc) / tile_bytes);
+            if (stages > 4) stages = 4;
+            if (stages < 1) stages = 1;
+        }
+        return true;
+    };
+    if (!config(kStageThreads))
         return fail(ZF_ERR_UNSUPPORTED, "rqs: one tile of %d rows x %d params does not fit shared memory", a.R, a.P);
-    // two resident blocks of two stages when tiles are small, else one block with up to 4 stages
-    int blocks_per_sm = 1, stages;
-    if (2 * (2 * tile_bytes + misc) + 2048 <= budget) { blocks_per_sm = 2; stages = 2; }
-    else {
-        stages = (int)((budget - misc) / tile_bytes);
-        if (stages > 4) stages = 4;
-        if (stages < 1) stages = 1;
+    // big rows (d = 8, K = 32: 97 KB tiles): two blocks of 128 threads keep four copies in flight per SM instead of two
+    // and decouple the tiles' barriers
+    if (blocks_per_sm == 1 && d <= kStageThreads / 2 / 4) {
+        const int R0 = a.R, st0 = stages;
+        const size_t tb0 = tile_bytes, misc0 = misc;
+        if (!(config(kStageThreads / 2) && blocks_per_sm == 2)) { a.R = R0; threads = kStageThreads; blocks_per_sm = 1; stages = st0; tile_bytes = tb0; misc = misc0; }
     }
     a.stages = stages;
     a.n_tiles = (a.n_rows + a.R - 1) / a.R;
@@ -185,7 +199,7 @@ static int launch_stage(cudaStream_t stream, const float* theta, const float* v,
 
     auto run = [&](auto kernel) -> int {
         ZF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<(unsigned)grid, kStageThreads, smem, stream>>>(a);
+        kernel<<<(unsigned)grid, threads, smem, stream>>>(a);
         count_launch();
         ZF_CUDA_CHECK(cudaGetLastError());
         return ZF_OK;

@@ -40,5 +40,7 @@ def table(name):
 t16 = table("chain16")
 tpp = table("pp")
 table("train")
+if os.path.exists(os.path.join(G, "prof_r02_stage_raw.csv")):
+    table("stage")
 json.dump({"bounded16:16777216": t16[0], "two_moons_conditional:1000000": tpp[0]}, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, "r02_traffic.json")).read())

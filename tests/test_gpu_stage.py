@@ -80,6 +80,37 @@ def test_extreme_parameters_take_the_ieee_path():
     np.testing.assert_allclose(y[good], yo[good], atol=5e-6)
 
 
+@pytest.mark.parametrize("K,d", [(16, 1), (32, 8)])
+def test_nan_inf_and_large_parameters_lean_row(K, d):
+    """The lean row of the stage kernel (K = 16 / 32) tests every searched / other-axis value against the fast-path bound;
+    NaN, inf and |theta| >= 4096 must route the row to the IEEE path: bins bit-exact, NaN pattern as the oracle's, forward
+    and inverse."""
+    from zenflow_b200.utils import rqs_forward_raw, rqs_inverse_raw
+
+    M = 3000
+    rng = np.random.default_rng(K + d)
+    theta = (1.5 * rng.standard_normal((M, d, 3 * K - 1))).astype(np.float32)
+    theta[::5, 0, 3] = 5000.0                 # just above the bound, searched block (forward)
+    theta[1::5, d - 1, K + 2] = -7000.0       # other block (forward) = searched block (inverse)
+    theta[2::11, 0, 1] = np.inf
+    theta[3::13, d - 1, K + 1] = np.nan
+    theta[4::17, 0, 2 * K + 1] = 1e9          # a slope: never decides the path
+    x = rng.uniform(-0.05, 1.05, (M, d)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        yo, ldo, idxo = zo.rqs_forward_theta(x, theta, K, return_idx=True)
+        xo, idxi = zo.rqs_inverse_theta(x, theta, K, return_idx=True)
+    y, ld, idx = rqs_forward_raw(x, theta, K, return_index=True)
+    np.testing.assert_array_equal(idx, idxo)
+    np.testing.assert_array_equal(np.isnan(y), np.isnan(yo))
+    good = np.isfinite(yo)
+    np.testing.assert_allclose(y[good], yo[good], atol=5e-6, rtol=0)
+    xi, idx2 = rqs_inverse_raw(x, theta, K, return_index=True)
+    np.testing.assert_array_equal(idx2, idxi)
+    np.testing.assert_array_equal(np.isnan(xi), np.isnan(xo))
+    good = np.isfinite(xo)
+    np.testing.assert_allclose(xi[good], xo[good], atol=1e-5, rtol=0)
+
+
 def test_reference_kats_on_device():
     """tests/test_utils.py:7-13 (identity spline incl. out of range) through the CUDA path:
     raw parameters 0 give equal bins and squareplus(0)=1 slopes."""

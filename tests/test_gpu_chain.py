@@ -345,6 +345,33 @@ def test_flow_sample_and_steps():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("D,C,K,ncoup,shift", [(16, 4, 32, 3, 2), (2, 4, 16, 2, 1)])
+def test_unnormalised_conditioning_features(D, C, K, ncoup, shift):
+    """Conditioning features of wildly different scales (1e6: x - mean alone would overflow fp16; 1e-6; 3e4 with an offset).  BatchNorm makes the reference
+    invariant to them; the tensor-core first Dense feeds (x - mean) * mul, not x - mean, to the fp16 hi / lo' split, so
+    it neither overflows fp16 nor drops to subnormals: log_prob stays at the float32 oracle's accuracy."""
+    from zenflow_b200 import Flow
+
+    M = 3000
+    ops = zo.make_chain(D, K, (128, 128), n_couplings=ncoup, roll_shift=shift)
+    x, c = _data(M, D, C, seed=21)
+    c = (c.astype(np.float64) * np.array([1e6, 1e-6, 1.0, 3e4]) + np.array([0.0, 0.0, -2.0, 1e3])).astype(np.float32)
+    v = trained_variables(ops, x, c, seed=2)
+    d = D // 2
+    for st in v["batch_stats"].values():   # running statistics of the conditioning features = the data's
+        if "BatchNorm_0" in st:
+            st["BatchNorm_0"]["mean"][D - d:] = c.mean(0)
+            st["BatchNorm_0"]["var"][D - d:] = c.var(0)
+    flow = Flow(product_chain(ops))
+    fv = {"params": {"bijector": v["params"]}, "batch_stats": {"bijector": v["batch_stats"]}}
+    lp = flow.apply(fv, x, c)
+    lp64, _ = zo.flow_log_prob(ops, to64(v), x.astype(np.float64), c.astype(np.float64))
+    lpo, _ = zo.flow_log_prob(ops, v, x, c)
+    print(f"[scaled c, D={D}] lp err gpu={errs(lp, lp64):.2e} oracle32={errs(lpo, lp64):.2e}")
+    assert np.isfinite(lp).all()
+    assert_fp32_parity(lp, lp64, lpo, "log_prob", atol=5e-5, slack=4.0)
+
+
 @pytest.mark.parametrize("D,C,K,layers", [(2, 1, 16, (128, 128)), (5, 2, 8, (32, 16)), (16, 0, 32, (128, 128))])
 def test_steps_match_oracle_steps(D, C, K, layers):
     """Flow._steps (flow.py:80-95): every per-bijector intermediate, forward and inverse, against the oracle's

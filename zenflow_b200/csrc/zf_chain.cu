@@ -161,15 +161,14 @@ __global__ void __launch_bounds__(256) pack_step_kernel(const __grid_constant__ 
             float* cb = ws + s.off_C;
             const UCst& cl = job.cst;
             const int n_plain = cl.w0i >= 0 ? cl.w0i : cl.total;
-            if (cl.w0i >= 0) {                         // first Dense (BatchNorm scale folded in) as a K = 16 operand image
+            if (cl.w0i >= 0) {
+                // first Dense as a K = 16 operand image.  The BatchNorm scale is NOT folded in here: the tensor-core path
+                // multiplies it into the A operand ((x - mean) * mul is O(1) whatever the scale of the raw inputs, so the
+                // fp16 hi / lo' split neither overflows nor goes subnormal on un-normalised conditioning features)
                 __half* dst = reinterpret_cast<__half*>(cb + cl.w0i);
                 for (int e = gtid; e < 16 * 128; e += gsz) {
                     const int k = e >> 7, n = e & 127;
-                    float val = 0.f;
-                    if (k < F) {
-                        const float mul = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(job.bn_var[k], 1e-5f))) * job.bn_scale[k];
-                        val = __fmul_rn(mul, job.kernel[0][k * 128 + n]);
-                    }
+                    const float val = k < F ? job.kernel[0][k * 128 + n] : 0.f;
                     const __half hi = __float2half_rn(val);
                     const __half lo = __float2half_rn((val - __half2float(hi)) * umma::kF16LoScale);
                     const int ii = umma::b_image_index_f16(n, k, 128);
@@ -1117,7 +1116,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                 }
             };
             if (tcfd) {
-                // ---- first Dense on the tensor cores: x - mean of the event's inputs (3xFP16 split) as a K = 16 A operand
+                // ---- first Dense on the tensor cores: (x - mean) * mul of the event's inputs (3xFP16 split) as a K = 16 A operand
                 // in tensor memory, columns [0, 8) (hi) and [TC_ALO, +8) (lo'); this thread writes inputs [8 half, +8) of
                 // its event = 4 columns of each.  The MMA warp multiplies it with the W0 image of the constant block
                 // into columns [TC_FD, +128); the epilogue below treats the result like a hidden layer.
@@ -1129,7 +1128,7 @@ __device__ __forceinline__ void umma_epilogue_role(const UCtx& cx) {
                     for (int i = 0; i < 8; ++i) {
                         const int f = f0 + i;
                         float v = 0.f;
-                        if (f < F) v = ((f < D - d) ? xs[col * UM + m] : cs[(f - (D - d)) * UM + m]) - bns[F_p + f];
+                        if (f < F) v = (((f < D - d) ? xs[col * UM + m] : cs[(f - (D - d)) * UM + m]) - bns[F_p + f]) * bns[f];
                         hv[i] = v;
                         if (++col == D) col = 0;
                     }

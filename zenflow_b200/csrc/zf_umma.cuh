@@ -138,21 +138,8 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
         : "memory");
 }
-// D[tmem] = A[smem] * B[smem] + D * 2^-SCALE (scale-input-d): folds accumulated lo' cross products (scale 2^11) under
-// the main product in ONE accumulator
-template <int SCALE>
-__device__ __forceinline__ void mma_f16_ss_scaled(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-    uint32_t z = 0u;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %5, %6, %7}, p, %8;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(z), "r"(z), "r"(z), "r"(z), "n"(SCALE)
-        : "memory");
-}
-// D[tmem] = A[tmem, fp16 pairs] * B[smem] + D * 2^-SCALE
+// D[tmem] = A[tmem, fp16 pairs] * B[smem] + D * 2^-SCALE (scale-input-d): folds accumulated lo' cross products (scale 2^11)
+// under the main product in ONE accumulator
 template <int SCALE>
 __device__ __forceinline__ void mma_f16_ts_scaled(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
     uint32_t z = 0u;
@@ -169,8 +156,6 @@ __device__ __forceinline__ void st4u(uint32_t a, const uint32_t (&v)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
                  : "memory");
 }
-// generic-proxy shared-memory writes -> visible to the async proxy (an MMA reading them through a descriptor)
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // half-word offset of element (r, k) of an R-row operand in an "event-row" image: [r/8][k/8][k%8][r%8] is the MN-major
 // reading of the same bytes a K-major image of the transposed operand has
 __host__ __device__ inline int mn_image_index_bf16(int r, int k, int Ktile) { return ((r >> 3) * (Ktile >> 3) + (k >> 3)) * 64 + (k & 7) * 8 + (r & 7); }

@@ -42,5 +42,8 @@ tpp = table("pp")
 table("train")
 if os.path.exists(os.path.join(G, "prof_r02_stage_raw.csv")):
     table("stage")
-json.dump({"bounded16:16777216": t16[0], "two_moons_conditional:1000000": tpp[0]}, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
+traffic = {"bounded16:16777216": t16[0], "two_moons_conditional:1000000": tpp[0]}
+if os.path.exists(os.path.join(G, "prof_r02_stage_bench_raw.csv")):   # the bench's own stage leg (d = 8, K = 32, 493,421 events)
+    traffic["rqs_stage:493421"] = table("stage_bench")[0]
+json.dump(traffic, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, "r02_traffic.json")).read())

@@ -48,19 +48,6 @@ struct LatentRng {
         const float u1 = uniform_open(), u2 = uniform();
         return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
     }
-    // Marsaglia & Tsang (2000), shape alpha >= 1
-    __device__ __forceinline__ float gamma(float alpha) {
-        const float d = alpha - (1.0f / 3.0f), c = rsqrtf(9.0f * d);
-        for (int it = 0; it < 64; ++it) {
-            const float x = normal();
-            float v = 1.0f + c * x;
-            if (v <= 0.f) continue;
-            v = v * v * v;
-            const float u = uniform_open();
-            if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return d * v;
-        }
-        return d;  // unreachable in practice (acceptance > 95% per round)
-    }
 };
 
 // one draw of the latent for (event m, column j)
@@ -73,9 +60,14 @@ __device__ __forceinline__ float latent_draw(int kind, float peakness, unsigned 
             for (int it = 0; it < 16 && fabsf(z) > 5.0f; ++it) z = g.normal();
             return 0.5f + 0.1f * fminf(fmaxf(z, -5.0f), 5.0f);
         }
-        case kLatentBeta: {   // Beta(p, p) = G1 / (G1 + G2), the construction jax.random.beta uses
-            const float g1 = g.gamma(peakness), g2 = g.gamma(peakness);
-            return g1 / (g1 + g2);
+        case kLatentBeta: {
+            // Symmetric Beta(p, p), p >= 1 (distributions.py:96-97), without rejection: Ulrich (1984), Devroye IX.4:
+            // 1/2 + 1/2 sqrt(1 - U^(2 / (2p - 1))) cos(2 pi V).  Two uniforms (one Philox block) instead of the ~2.1 rounds of
+            // two Marsaglia-Tsang gammas (jax.random.beta's G1 / (G1 + G2) construction): same distribution, a third of the
+            // instructions, no divergent rejection loop in the tile fill of Flow.sample.
+            const float u = g.uniform_open(), v = g.uniform();
+            const float t = exp2f(log2f(u) * (2.0f / (2.0f * peakness - 1.0f)));
+            return 0.5f + 0.5f * sqrtf(fmaxf(1.0f - t, 0.f)) * cospif(2.0f * v);
         }
         default: return g.uniform();
     }

@@ -12,7 +12,7 @@
 //       ShiftBounds        : 0, D kinds (zf_bound_kind)                      + attribute "bounds" (f64[2 D], lo then hi),
 //                                                                              attribute "margin" (f64)
 //       Roll               : 1, shift
-//       NeuralSplineCoupling: 2, knots, n_hidden, hidden widths...
+//       NeuralSplineCoupling: 2, knots | act << 16, n_hidden, hidden widths...   (act: zf_act_kind, 0 = nn.swish)
 //   operands: x (M, D) [, c (M, C) when cdim > 0], then the FLAX leaves in op order:
 //       ShiftBounds        : xmin (D,), xmax (D,)            (the batch_stats xmin_i / xmax_i packed)
 //       coupling           : BatchNorm scale, bias, mean, var, then kernel_0, bias_0, ..., kernel_L, bias_L
@@ -89,7 +89,8 @@ ffi::Error BuildChainFromLeaves(ffi::Span<const int32_t> program, ffi::Span<cons
             i += 2;
         } else {
             zf_coupling cp{};
-            cp.knots = program[i + 1];
+            cp.knots = program[i + 1] & 0xffff;
+            cp.act = (program[i + 1] >> 16) & 0xff;   // bijectors.py:319
             cp.n_hidden = program[i + 2];
             if (cp.n_hidden < 0 || cp.n_hidden > ZF_MAX_LAYERS) return Invalid("too many hidden layers");
             for (int l = 0; l < cp.n_hidden; ++l) cp.hidden[l] = program[i + 3 + l];

@@ -25,6 +25,8 @@ from typing import Any, Dict, List, Sequence, Tuple
 # zf_op_kind / zf_bound_kind / zf_latent_kind of include/zenflow_b200.h
 OP_SHIFT_BOUNDS, OP_ROLL, OP_COUPLING = 0, 1, 2
 BOUND_NONE, BOUND_BOTH, BOUND_LOWER, BOUND_UPPER = 0, 1, 2, 3
+# zf_act_kind by the name of the jax.nn function (silu is jax's alias of swish)
+ACT_KINDS = {"swish": 0, "silu": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "gelu": 4, "elu": 5, "softplus": 6, "leaky_relu": 7}
 LATENT = {"Beta": 0, "Normal": 1, "TruncatedNormal": 2, "Uniform": 3}
 
 _TARGETS = {
@@ -73,7 +75,7 @@ def encode_program(bijector, dim: int) -> Tuple[List[int], List[float], float]:
     """The ``program`` / ``bounds`` / ``margin`` attributes the handlers take.
 
     One record per bijector: ShiftBounds ``0, kind_0..kind_{D-1}``; Roll ``1, shift``; NeuralSplineCoupling
-    ``2, knots, n_hidden, widths...``.  ``bounds`` = D lower then D upper limits (0 where unset).
+    ``2, knots | act << 16, n_hidden, widths...`` (act: zf_act_kind, 0 = nn.swish).  ``bounds`` = D lower then D upper limits (0 where unset).
     """
     program: List[int] = []
     lo, hi, margin = [0.0] * dim, [0.0] * dim, 0.0
@@ -101,10 +103,13 @@ def encode_program(bijector, dim: int) -> Tuple[List[int], List[float], float]:
         elif name == "Roll":
             program += [OP_ROLL, int(b.shift)]
         elif name == "NeuralSplineCoupling":
-            act = getattr(b.act, "__name__", "")
-            if act not in ("swish", "silu"):
-                raise NotImplementedError("the CUDA conditioner implements act=nn.swish (the reference default)")
-            program += [OP_COUPLING, int(b.knots), len(b.layers)] + [int(w) for w in b.layers]
+            act = ACT_KINDS.get(getattr(b.act, "__name__", ""))  # bijectors.py:319; matched by the jax.nn function's name
+            if act is None:
+                raise NotImplementedError(f"the CUDA conditioner implements act in {sorted(ACT_KINDS)} (jax.nn functions "
+                                          "with their default arguments); nn.swish is the reference default")
+            if not 1 <= int(b.knots) < 1 << 16:
+                raise ValueError("knots must be in [1, 65535]")
+            program += [OP_COUPLING, int(b.knots) | act << 16, len(b.layers)] + [int(w) for w in b.layers]
         else:
             raise NotImplementedError(f"bijector {name} has no CUDA implementation")
     return program, lo + hi, margin

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ZF_ABI_VERSION 2
+#define ZF_ABI_VERSION 3
 #define ZF_MAX_LAYERS 8   /* hidden layers per conditioner */
 #define ZF_MAX_DIM 64     /* columns of x */
 
@@ -69,6 +69,20 @@ typedef struct zf_shift_bounds {
     float* xmax;
 } zf_shift_bounds;
 
+/* bijectors.py:319 NeuralSplineCoupling.act: the conditioner's activation (jax.nn definitions; gelu is the tanh
+ * form, jax's default).  ZF_ACT_SWISH (the reference default, = 0 so a zeroed struct keeps it) runs on the
+ * tensor-core kernels; the others take the fp32 FFMA kernels (eval and train). */
+typedef enum zf_act_kind {
+    ZF_ACT_SWISH = 0,
+    ZF_ACT_RELU = 1,
+    ZF_ACT_TANH = 2,
+    ZF_ACT_SIGMOID = 3,
+    ZF_ACT_GELU = 4,
+    ZF_ACT_ELU = 5,
+    ZF_ACT_SOFTPLUS = 6,
+    ZF_ACT_LEAKY_RELU = 7
+} zf_act_kind;
+
 /* bijectors.py:300-371 NeuralSplineCoupling.  Leaves exactly as FLAX stores them:
  * BatchNorm_0 scale/bias (params), mean/var (batch_stats), all (F,), F = dim - dim/2 + cdim;
  * Dense_j kernel (in,out) row-major and bias (out,), j = 0..n_hidden (the last one has
@@ -83,6 +97,7 @@ typedef struct zf_coupling {
     float* bn_var;
     const float* kernel[ZF_MAX_LAYERS + 1];
     const float* bias[ZF_MAX_LAYERS + 1];
+    int32_t act;   /* zf_act_kind, bijectors.py:319,345 */
 } zf_coupling;
 
 typedef struct zf_op {

@@ -133,6 +133,19 @@ def to_numpy(tree):
     return tree.detach().numpy()
 
 
+# bijectors.py:319 `act` (jax.nn definitions, default arguments)
+_ACT = {
+    "swish": lambda h: h * torch.sigmoid(h),
+    "relu": torch.relu,
+    "tanh": torch.tanh,
+    "sigmoid": torch.sigmoid,
+    "gelu": lambda h: torch.nn.functional.gelu(h, approximate="tanh"),
+    "elu": torch.nn.functional.elu,
+    "softplus": lambda h: torch.logaddexp(h, torch.zeros_like(h)),   # F.softplus switches to x above 20
+    "leaky_relu": lambda h: torch.nn.functional.leaky_relu(h, 0.01),
+}
+
+
 def train_loss(ops, params_t, stats, x, c, *, latent="beta", peakness=12.0, train=True):
     """loss_fn of train.py:64-73: returns (loss, new_batch_stats, lp).  x, c torch float64."""
     new_stats: Dict[str, dict] = {}
@@ -168,7 +181,7 @@ def train_loss(ops, params_t, stats, x, c, *, latent="beta", peakness=12.0, trai
             n_dense = sum(1 for k in p if k.startswith("Dense_"))
             for j in range(n_dense - 1):
                 h = h @ p[f"Dense_{j}"]["kernel"] + p[f"Dense_{j}"]["bias"]
-                h = h * torch.sigmoid(h)
+                h = _ACT[op.get("act", "swish")](h)
             j = n_dense - 1
             theta = (h @ p[f"Dense_{j}"]["kernel"] + p[f"Dense_{j}"]["bias"]).reshape(x.shape[0], d, 3 * K - 1)
             yt, ld = rqs_forward(xt, theta, K)

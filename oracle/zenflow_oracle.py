@@ -370,7 +370,46 @@ def shift_bounds_inverse(z, stats: Dict[str, np.ndarray], *,
     return x
 
 
-def coupling_params(x, c, params, stats, *, knots_: int, train: bool):
+def relu(x):
+    """jax.nn.relu."""
+    return np.maximum(x, x.dtype.type(0))
+
+
+def sigmoid(x):
+    """jax.nn.sigmoid."""
+    dt = x.dtype.type
+    with np.errstate(over="ignore"):
+        return dt(1) / (dt(1) + np.exp(-x))
+
+
+def gelu(x):
+    """jax.nn.gelu(approximate=True) (jax's default): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))."""
+    dt = x.dtype.type
+    return dt(0.5) * x * (dt(1) + np.tanh(dt(math.sqrt(2.0 / math.pi)) * (x + dt(0.044715) * (x * x * x))))
+
+
+def elu(x):
+    """jax.nn.elu(alpha=1)."""
+    with np.errstate(over="ignore"):
+        return np.where(x > 0, x, np.expm1(x)).astype(x.dtype)
+
+
+def softplus(x):
+    """jax.nn.softplus = logaddexp(x, 0)."""
+    return np.logaddexp(x, x.dtype.type(0))
+
+
+def leaky_relu(x):
+    """jax.nn.leaky_relu(negative_slope=0.01)."""
+    return np.where(x >= 0, x, x.dtype.type(0.01) * x).astype(x.dtype)
+
+
+# bijectors.py:319 `act` by the name of the jax.nn function
+ACTIVATIONS = {"swish": swish, "silu": swish, "relu": relu, "tanh": np.tanh, "sigmoid": sigmoid, "gelu": gelu,
+               "elu": elu, "softplus": softplus, "leaky_relu": leaky_relu}
+
+
+def coupling_params(x, c, params, stats, *, knots_: int, train: bool, act: str = "swish"):
     """bijectors.py:329-357  the conditioner.  Returns (xt, xc, theta, new_stats).
 
     params: {"BatchNorm_0": {"scale","bias"}, "Dense_j": {"kernel","bias"}}
@@ -386,7 +425,7 @@ def coupling_params(x, c, params, stats, *, knots_: int, train: bool):
     h, m, v = batchnorm(h, bn_p["scale"], bn_p["bias"], bn_s["mean"], bn_s["var"], train)
     n_dense = sum(1 for k in params if k.startswith("Dense_"))
     for j in range(n_dense - 1):
-        h = swish(dense(h, params[f"Dense_{j}"]["kernel"], params[f"Dense_{j}"]["bias"]))
+        h = ACTIVATIONS[act](dense(h, params[f"Dense_{j}"]["kernel"], params[f"Dense_{j}"]["bias"]))  # :345
     j = n_dense - 1
     h = dense(h, params[f"Dense_{j}"]["kernel"], params[f"Dense_{j}"]["bias"])
     theta = h.reshape(x.shape[0], d, 3 * knots_ - 1)
@@ -395,9 +434,9 @@ def coupling_params(x, c, params, stats, *, knots_: int, train: bool):
 
 
 def coupling_forward(x, c, params, stats, *, knots_: int, train: bool = False,
-                     return_aux: bool = False):
+                     return_aux: bool = False, act: str = "swish"):
     """bijectors.py:359-365."""
-    xt, xc, theta, new_stats = coupling_params(x, c, params, stats, knots_=knots_, train=train)
+    xt, xc, theta, new_stats = coupling_params(x, c, params, stats, knots_=knots_, train=train, act=act)
     yt, log_det, idx = rqs_forward_theta(xt, theta, knots_, return_idx=True)
     y = np.hstack((yt, xc))
     if return_aux:
@@ -405,9 +444,9 @@ def coupling_forward(x, c, params, stats, *, knots_: int, train: bool = False,
     return y, log_det, new_stats
 
 
-def coupling_inverse(y, c, params, stats, *, knots_: int, return_aux: bool = False):
+def coupling_inverse(y, c, params, stats, *, knots_: int, return_aux: bool = False, act: str = "swish"):
     """bijectors.py:367-371 (always eval-mode BatchNorm)."""
-    yt, yc, theta, _ = coupling_params(y, c, params, stats, knots_=knots_, train=False)
+    yt, yc, theta, _ = coupling_params(y, c, params, stats, knots_=knots_, train=False, act=act)
     xt, idx = rqs_inverse_theta(yt, theta, knots_, return_idx=True)
     x = np.hstack((xt, yc))
     if return_aux:
@@ -418,7 +457,7 @@ def coupling_inverse(y, c, params, stats, *, knots_: int, return_aux: bool = Fal
 # A chain is described by a list of dicts, the oracle's stand-in for the FLAX modules:
 #   {"kind": "shift_bounds", "margin": 0.1, "bounds": ()}
 #   {"kind": "roll", "shift": 1}
-#   {"kind": "coupling", "knots": 16, "layers": (128, 128)}
+#   {"kind": "coupling", "knots": 16, "layers": (128, 128)}      (+ "act": a key of ACTIVATIONS; default "swish")
 # and variables use the FLAX naming: params["bijectors_i"], batch_stats["bijectors_i"].
 
 
@@ -503,7 +542,7 @@ def chain_forward(ops, variables, x, c=None, *, train: bool = False, initializin
             x, ld = roll_forward(x, op["shift"]), 0
         elif op["kind"] == "coupling":
             x, ld, ns = coupling_forward(x, c, params[name], stats[name], knots_=op["knots"],
-                                         train=train)
+                                         train=train, act=op.get("act", "swish"))
             if train and not initializing:
                 stats[name] = ns
         else:
@@ -531,7 +570,7 @@ def chain_inverse(ops, variables, z, c=None, *, return_steps: bool = False):
         elif op["kind"] == "roll":
             x = roll_inverse(x, op["shift"])
         elif op["kind"] == "coupling":
-            x = coupling_inverse(x, c, params[name], stats[name], knots_=op["knots"])
+            x = coupling_inverse(x, c, params[name], stats[name], knots_=op["knots"], act=op.get("act", "swish"))
         steps.append(x)
     if return_steps:
         return x, steps

@@ -14,7 +14,8 @@ def product_chain(ops):
         elif op["kind"] == "roll":
             mods.append(bi.Roll(op["shift"]))
         else:
-            mods.append(bi.NeuralSplineCoupling(knots=op["knots"], layers=op["layers"]))
+            mods.append(bi.NeuralSplineCoupling(knots=op["knots"], layers=op["layers"],
+                                                act=getattr(bi, op.get("act", "swish"))))
     return bi.Chain(mods)
 
 

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/zenflow_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in zenflow_b200/_lib.py"
-    assert lib.zf_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.zf_abi_version() == _lib.ABI_VERSION == 3
     assert os.path.dirname(_lib.library_path()).startswith(ROOT)  # in-tree, not site-packages
 
 

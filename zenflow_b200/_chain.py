@@ -55,12 +55,13 @@ class ChainSpec:
         self._ops.append(op)
 
     def add_coupling(self, knots: int, hidden: Sequence[int], bn_scale, bn_bias, bn_mean, bn_var,
-                     kernels: Sequence, biases: Sequence) -> None:
+                     kernels: Sequence, biases: Sequence, act: int = 0) -> None:
         if len(hidden) > _lib.ZF_MAX_LAYERS:
             raise ValueError(f"at most {_lib.ZF_MAX_LAYERS} hidden layers are supported")
         cp = _lib.ZfCoupling()
         cp.knots = int(knots)
         cp.n_hidden = len(hidden)
+        cp.act = int(act)
         for i, w in enumerate(hidden):
             cp.hidden[i] = int(w)
         cp.bn_scale = ptr(self.leaf(bn_scale))

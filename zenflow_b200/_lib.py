@@ -12,13 +12,14 @@ import threading
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DP_UNIQUE_ID_BYTES = 128
 ZF_MAX_LAYERS = 8
 ZF_MAX_DIM = 64
 
 OP_SHIFT_BOUNDS, OP_ROLL, OP_COUPLING = 0, 1, 2
 LATENT_KINDS = {"beta": 0, "normal": 1, "truncnorm": 2, "uniform": 3}
+ACT_KINDS = {"swish": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "gelu": 4, "elu": 5, "softplus": 6, "leaky_relu": 7}
 BOUND_NONE, BOUND_BOTH, BOUND_LOWER, BOUND_UPPER = 0, 1, 2, 3
 
 c_float_p = C.POINTER(C.c_float)
@@ -46,6 +47,7 @@ class ZfCoupling(C.Structure):
         ("bn_var", C.c_void_p),
         ("kernel", C.c_void_p * (ZF_MAX_LAYERS + 1)),
         ("bias", C.c_void_p * (ZF_MAX_LAYERS + 1)),
+        ("act", C.c_int32),
     ]
 
 

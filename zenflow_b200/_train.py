@@ -125,10 +125,13 @@ def _op_roll(shift):
     return op
 
 
-def _coupling_struct(knots, hidden, scale, bias, mean, var, kernels, biases) -> _lib.ZfCoupling:
+def _coupling_struct(mod, scale, bias, mean, var, kernels, biases) -> _lib.ZfCoupling:
+    """zf_coupling of the NeuralSplineCoupling module `mod` over the given leaves."""
+    hidden = mod.layers
     cp = _lib.ZfCoupling()
-    cp.knots = int(knots)
+    cp.knots = int(mod.knots)
     cp.n_hidden = len(hidden)
+    cp.act = int(getattr(mod, "_act_kind", 0))
     for i, w in enumerate(hidden):
         cp.hidden[i] = int(w)
     cp.bn_scale, cp.bn_bias, cp.bn_mean, cp.bn_var = ptr(scale), ptr(bias), ptr(mean), ptr(var)
@@ -227,7 +230,7 @@ def coupling_train_forward(mod, x, c):
     bn.put("batch_stats", "var", _leaf_out(ra_var, var))
     keep = [dl(scale), dl(bias)] + [dl(k) for k in kernels] + [dl(b) for b in biases]
     nl = len(kernels)
-    cp = _coupling_struct(mod.knots, mod.layers, keep[0], keep[1], bmean, bvar, keep[2:2 + nl], keep[2 + nl:])
+    cp = _coupling_struct(mod, keep[0], keep[1], bmean, bvar, keep[2:2 + nl], keep[2 + nl:])
     ch, arr = _chain_struct(D, Cdim, [_op_cp(cp)])
     y = torch.empty_like(xd)
     ld = torch.empty(M, dtype=torch.float32, device=dev)
@@ -349,7 +352,7 @@ class TrainEngine:
             ks = [g["pv"][(f"Dense_{j}", "kernel")] for j in range(nl)]
             bs = [g["pv"][(f"Dense_{j}", "bias")] for j in range(nl)]
             # train forward/backward read the BATCH statistics
-            g["cp"] = _coupling_struct(g["mod"].knots, g["mod"].layers, g["pv"][("BatchNorm_0", "scale")],
+            g["cp"] = _coupling_struct(g["mod"], g["pv"][("BatchNorm_0", "scale")],
                                        g["pv"][("BatchNorm_0", "bias")], g["bmean"], g["bvar"], ks, bs)
             gr = _lib.ZfCouplingGrads()
             gr.bn_scale = ptr(g["gv"][("BatchNorm_0", "scale")])
@@ -391,7 +394,7 @@ class TrainEngine:
                 ops.append(_op_sb(g["sb"]))
             else:
                 nl = len(g["mod"].layers) + 1
-                run = _coupling_struct(g["mod"].knots, g["mod"].layers, g["pv"][("BatchNorm_0", "scale")],
+                run = _coupling_struct(g["mod"], g["pv"][("BatchNorm_0", "scale")],
                                        g["pv"][("BatchNorm_0", "bias")], g["ra_mean"], g["ra_var"],
                                        [g["pv"][(f"Dense_{j}", "kernel")] for j in range(nl)],
                                        [g["pv"][(f"Dense_{j}", "bias")] for j in range(nl)])

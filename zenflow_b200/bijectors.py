@@ -255,9 +255,36 @@ class Roll(Bijector):
         return self._eval_inverse(x, c)
 
 
-def swish(x):
-    """Marker for the default activation (jax.nn.swish); the kernels implement it."""
-    raise RuntimeError("swish is evaluated inside the CUDA kernels")
+def _activation(name: str, doc: str):
+    def marker(x):
+        raise RuntimeError(f"{name} is evaluated inside the CUDA kernels")
+    marker.__name__ = marker.__qualname__ = name
+    marker.__doc__ = doc
+    return marker
+
+
+# Markers for NeuralSplineCoupling.act (bijectors.py:319): the kernels implement the jax.nn function of the same
+# name with its default arguments.  swish (the reference default) runs on the tensor-core kernels, the others on
+# the fp32 FFMA kernels.
+swish = _activation("swish", "jax.nn.swish = x * sigmoid(x) (the default)")
+silu = swish
+relu = _activation("relu", "jax.nn.relu")
+tanh = _activation("tanh", "jax.nn.tanh")
+sigmoid = _activation("sigmoid", "jax.nn.sigmoid")
+gelu = _activation("gelu", "jax.nn.gelu(approximate=True), jax's default")
+elu = _activation("elu", "jax.nn.elu(alpha=1)")
+softplus = _activation("softplus", "jax.nn.softplus")
+leaky_relu = _activation("leaky_relu", "jax.nn.leaky_relu(negative_slope=0.01)")
+
+
+def _act_kind(act) -> int:
+    """zf_act_kind of a marker above, of its name, or of a function named like one (jax.nn.relu, ...)."""
+    name = act if isinstance(act, str) else getattr(act, "__name__", "")
+    name = "swish" if name == "silu" else name
+    if name not in _lib.ACT_KINDS:
+        raise NotImplementedError(f"act={act!r}: the kernels implement {sorted(_lib.ACT_KINDS)} "
+                                  "(jax.nn definitions, default arguments)")
+    return _lib.ACT_KINDS[name]
 
 
 class NeuralSplineCoupling(Bijector):
@@ -271,9 +298,8 @@ class NeuralSplineCoupling(Bijector):
     def __init__(self, knots: int = 16, layers: Sequence[int] = (128, 128), act=swish):
         self.knots = knots
         self.layers = tuple(layers)
-        if act is not swish:
-            raise NotImplementedError("only the default activation (swish) is implemented natively")
         self.act = act
+        self._act_kind = _act_kind(act)
 
     @staticmethod
     def _split(x):
@@ -326,7 +352,7 @@ class NeuralSplineCoupling(Bijector):
     def _emit(self, spec, scope):
         assert spec.dim // 2 > 0 and spec.dim // 2 < spec.dim  # bijectors.py:326
         scale, bias, mean, var, kernels, biases = self._leaves(scope, spec.dim)
-        spec.add_coupling(self.knots, self.layers, scale, bias, mean, var, kernels, biases)
+        spec.add_coupling(self.knots, self.layers, scale, bias, mean, var, kernels, biases, act=self._act_kind)
 
     def __call__(self, x, c=None, train: bool = False):
         D = _shape2(x)[1]

@@ -55,7 +55,8 @@ struct StepDesc {
     int umma_ok;                    // this coupling fits the tensor-core kernel
     int off_C;                      // tensor-core kernel: this coupling's small constants as one contiguous block
     int cidx;                       // ordinal of this coupling among the chain's couplings (bin-index output)
-    int pad[2];
+    int act;                        // zf_act_kind of the hidden layers (the tensor-core kernels take swish only)
+    int pad[1];
 };
 static_assert(sizeof(StepDesc) % 16 == 0, "StepDesc must keep the packed blocks 16-byte aligned");
 
@@ -371,7 +372,7 @@ __device__ __forceinline__ void run_coupling(const ChainArgs& a, long long m0, i
     const int tx = tid & 15, ty = tid >> 4;
     float acc[4][8];
     int Kin_p = F_p;
-    // ---- hidden layers: Dense + swish (bijectors.py:343-345)
+    // ---- hidden layers: Dense + act (swish unless the coupling says otherwise; bijectors.py:343-345)
     for (int l = 0; l < s.n_hidden; ++l) {
         const int N_p = ru(s.hidden[l], KC);
         const float* W = wsf + s.off_W[l];
@@ -385,10 +386,10 @@ __device__ __forceinline__ void run_coupling(const ChainArgs& a, long long m0, i
                 if (n < ncols) {
                     const float bj = bias[n0 + n];
                     float4 o;
-                    o.x = swishf(acc[0][j] + bj);
-                    o.y = swishf(acc[1][j] + bj);
-                    o.z = swishf(acc[2][j] + bj);
-                    o.w = swishf(acc[3][j] + bj);
+                    o.x = act_apply(s.act, acc[0][j] + bj);
+                    o.y = act_apply(s.act, acc[1][j] + bj);
+                    o.z = act_apply(s.act, acc[2][j] + bj);
+                    o.w = act_apply(s.act, acc[3][j] + bj);
                     *reinterpret_cast<float4*>(nxt + (n0 + n) * TM + tx * 4) = o;
                 }
             }
@@ -2217,8 +2218,11 @@ static int build_plan(const zf_chain* chain, Plan& plan, bool for_vjp = false) {
             job.desc.kind = kStepKindCoupling;
             job.desc.cidx = plan.n_couplings;
             plan.n_couplings++;
-            {   // tensor-core kernel: hidden width 128 throughout, K in {16, 32}, small first layer
-                bool ok = cp.n_hidden >= 1 && (cp.knots == 16 || cp.knots == 32) && (D - d + C) <= UFMAX && d <= UDMAX;
+            ZF_REQUIRE(cp.act >= ZF_ACT_SWISH && cp.act <= ZF_ACT_LEAKY_RELU, "op %d: unknown activation %d", i, cp.act);
+            job.desc.act = cp.act;
+            {   // tensor-core kernel: swish, hidden width 128 throughout, K in {16, 32}, small first layer
+                bool ok = cp.n_hidden >= 1 && (cp.knots == 16 || cp.knots == 32) && (D - d + C) <= UFMAX && d <= UDMAX &&
+                          cp.act == ZF_ACT_SWISH;
                 for (int l = 0; l < cp.n_hidden; ++l) ok = ok && cp.hidden[l] == 128;
                 job.desc.umma_ok = ok ? 1 : 0;
                 plan.umma_ok = plan.umma_ok && ok;

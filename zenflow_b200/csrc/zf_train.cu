@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LatentConst lc, const fl
 //   mode 0 (NN): C[m][n]  = sum_k opA(A[m][k]) * B[k][n] + bias[n]
 //   mode 1 (NT): C[m][k]  = (sum_n A[m][n] * B[k][n]) * swish'(Z[m][k])          (Z optional)
 //   mode 2 (TN): C[k][n] += sum_m opA(A[m][k]) * B[m][n];  colsum[n] += sum_m B[m][n]
-// opA = swish when a_swish (the stored pre-activations are re-activated on load).
+// opA = the activation `act` (swish by default) when a_swish: stored pre-activations are re-activated on load.
 // ---------------------------------------------------------------------------------------------
 struct GemmArgs {
     const float* A; long long lda;
@@ -294,21 +294,18 @@ struct GemmArgs {
     const float* bias;
     float* colsum;
     const float* Z; long long ldz;
-    int a_swish;
+    int a_swish;         // apply the activation to A on load
+    int act;             // zf_act_kind (0 = swish) of opA and of the derivative that multiplies mode 1's product
     long long I, J, R;   // output rows, output cols, reduction length
     long long r_slab;    // mode 2: reduction rows per CTA (gridDim.z slabs)
 };
 
 constexpr int GT = 64, GK = 16, GS = 68;
 
-__device__ __forceinline__ float swish_grad(float z) {
-    const float s = 1.0f / (1.0f + expf(-z));
-    return s * (1.0f + z * (1.0f - s));
-}
 
 // pattern T: S[r][t] = X[(t0+t)*ld + r0+r]   (r contiguous in memory)
 __device__ __forceinline__ void load_T(float (*S)[GS], const float* __restrict__ X, long long ld, long long t0,
-                                       long long tmax, long long r0, long long rmax, bool act, int tid) {
+                                       long long tmax, long long r0, long long rmax, int act, int tid) {
 #pragma unroll
     for (int q = 0; q < (GT * GK) / 256; ++q) {
         const int e = tid + q * 256;
@@ -316,14 +313,14 @@ __device__ __forceinline__ void load_T(float (*S)[GS], const float* __restrict__
         float v = 0.f;
         if (t0 + t < tmax && r0 + r < rmax) {
             v = X[(t0 + t) * ld + r0 + r];
-            if (act) v = swishf(v);
+            if (act >= 0) v = act_apply(act, v);
         }
         S[r][t] = v;
     }
 }
 // pattern D: S[r][t] = X[(r0+r)*ld + t0+t]   (t contiguous in memory)
 __device__ __forceinline__ void load_D(float (*S)[GS], const float* __restrict__ X, long long ld, long long t0,
-                                       long long tmax, long long r0, long long rmax, bool act, int tid) {
+                                       long long tmax, long long r0, long long rmax, int act, int tid) {
 #pragma unroll
     for (int q = 0; q < (GT * GK) / 256; ++q) {
         const int e = tid + q * 256;
@@ -331,7 +328,7 @@ __device__ __forceinline__ void load_D(float (*S)[GS], const float* __restrict__
         float v = 0.f;
         if (t0 + t < tmax && r0 + r < rmax) {
             v = X[(r0 + r) * ld + t0 + t];
-            if (act) v = swishf(v);
+            if (act >= 0) v = act_apply(act, v);
         }
         S[r][t] = v;
     }
@@ -357,14 +354,14 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmA
 
     for (long long r0 = rbeg; r0 < rend; r0 += GK) {
         if (MODE == 0) {
-            load_T(As, g.A, g.lda, i0, g.I, r0, rend, g.a_swish != 0, tid);
-            load_D(Bs, g.B, g.ldb, j0, g.J, r0, rend, false, tid);
+            load_T(As, g.A, g.lda, i0, g.I, r0, rend, g.a_swish ? g.act : -1, tid);
+            load_D(Bs, g.B, g.ldb, j0, g.J, r0, rend, -1, tid);
         } else if (MODE == 1) {
-            load_T(As, g.A, g.lda, i0, g.I, r0, rend, false, tid);
-            load_T(Bs, g.B, g.ldb, j0, g.J, r0, rend, false, tid);
+            load_T(As, g.A, g.lda, i0, g.I, r0, rend, -1, tid);
+            load_T(Bs, g.B, g.ldb, j0, g.J, r0, rend, -1, tid);
         } else {
-            load_D(As, g.A, g.lda, i0, g.I, r0, rend, g.a_swish != 0, tid);
-            load_D(Bs, g.B, g.ldb, j0, g.J, r0, rend, false, tid);
+            load_D(As, g.A, g.lda, i0, g.I, r0, rend, g.a_swish ? g.act : -1, tid);
+            load_D(Bs, g.B, g.ldb, j0, g.J, r0, rend, -1, tid);
         }
         __syncthreads();
         if (MODE == 2 && g.colsum && blockIdx.x == 0 && tid < GT) {
@@ -397,7 +394,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmA
                 if (g.bias) v += g.bias[j];
                 g.C[i * g.ldc + j] = v;
             } else if (MODE == 1) {
-                if (g.Z) v *= swish_grad(g.Z[i * g.ldz + j]);
+                if (g.Z) v *= act_grad(g.act, g.Z[i * g.ldz + j]);
                 g.C[i * g.ldc + j] = v;
             } else {
                 atomicAdd(&g.C[i * g.ldc + j], v);
@@ -414,9 +411,10 @@ int launch_umma_gemm(cudaStream_t st, int mode, const float* A, long long lda, c
                      long long I, long long J, long long R, long long r_slab);
 
 static int launch_gemm(cudaStream_t st, int mode, const GemmArgs& g) {
-    // tensor-core (tcgen05, 3xTF32) GEMM by default; ZF_GEMM_IMPL=simt keeps the fp32 FFMA kernel
+    // tensor-core (tcgen05, 3xTF32) GEMM by default; ZF_GEMM_IMPL=simt, or an activation other than swish,
+    // keeps the fp32 FFMA kernel
     const char* impl = impl_switch().gemm;   // read once per process (zf_chain.cu)
-    if (impl[0] != 's')
+    if (impl[0] != 's' && g.act == ZF_ACT_SWISH)
         return launch_umma_gemm(st, mode, g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.bias, g.colsum, g.Z, g.ldz, g.a_swish,
                                 g.I, g.J, g.R, mode == 2 ? 4096 : 0);
     dim3 grid((unsigned)((g.I + GT - 1) / GT), (unsigned)((g.J + GT - 1) / GT), 1);
@@ -907,7 +905,7 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             g.B = cp->kernel[l]; g.ldb = widths[l + 1];
             g.C = act[l + 1]; g.ldc = widths[l + 1];
             g.bias = cp->bias[l];
-            g.a_swish = l > 0;
+            g.a_swish = l > 0; g.act = cp->act;
             g.I = Mb; g.J = widths[l + 1]; g.R = widths[l];
             if (int rc = launch_gemm(st, 0, g)) return rc;
         }
@@ -929,14 +927,14 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             gw.B = act[l + 1]; gw.ldb = widths[l + 1];
             gw.C = gr->kernel[l]; gw.ldc = widths[l + 1];
             gw.colsum = gr->bias[l];
-            gw.a_swish = l > 0;
+            gw.a_swish = l > 0; gw.act = cp->act;
             gw.I = widths[l]; gw.J = widths[l + 1]; gw.R = Mb; gw.r_slab = 2048;
             if (int rc = launch_gemm(st, 2, gw)) return rc;
             GemmArgs ga{};  // dZ_l = (dZ_{l+1} W_l^T) * swish'(Z_l)   (l = 0: d/d(BN output), no activation)
             ga.A = act[l + 1]; ga.lda = widths[l + 1];
             ga.B = cp->kernel[l]; ga.ldb = widths[l + 1];
             ga.C = (l == 0) ? gh0 + m0 * F : act[l]; ga.ldc = widths[l];
-            ga.Z = (l == 0) ? nullptr : act[l]; ga.ldz = widths[l];
+            ga.Z = (l == 0) ? nullptr : act[l]; ga.ldz = widths[l]; ga.act = cp->act;
             ga.I = Mb; ga.J = widths[l]; ga.R = widths[l + 1];
             if (int rc = launch_gemm(st, 1, ga)) return rc;
         }

@@ -119,6 +119,8 @@ int32_t zf_abi_version(void);
 const char* zf_last_error(void);
 /* Number of kernels this library has launched on the calling thread (bench bookkeeping). */
 int64_t zf_launch_count(void);
+/* A host that replays a captured CUDA graph of calls into this library adds the graph's kernel count here. */
+void zf_launch_count_add(int64_t n);
 
 /* ---- spline stage on raw conditioner output --------------------------------------------
  * theta (M, d, 3K-1): raw widths | heights | slopes per transformed dim (bijectors.py:347-355).
@@ -289,6 +291,13 @@ int zf_bn_backward_apply(void* stream, const zf_coupling* cp, int32_t D, int32_t
  * -> add_decayed_weights(weight_decay) -> scale(-lr).  count = number of updates done so far. */
 int zf_nadamw_update(void* stream, int64_t n, float* params, const float* grads, float* mu, float* nu,
                      int64_t count, float lr, float b1, float b2, float eps, float weight_decay, int32_t nesterov);
+
+/* The same update with the step counter in DEVICE memory: count_dev[0] = updates done so far, read for the bias
+ * corrections and then incremented on the stream; bias_scratch: 3 device floats.  No argument changes from step to
+ * step, so a CUDA graph captured around a whole train step (zf_flow_value_and_grad + this) can be replayed. */
+int zf_nadamw_update_dev(void* stream, int64_t n, float* params, const float* grads, float* mu, float* nu,
+                         int64_t* count_dev, float* bias_scratch, float lr, float b1, float b2, float eps,
+                         float weight_decay, int32_t nesterov);
 
 /* ---- train() epoch loop helpers (train.py:101-121) ----------------------------------------------
  * X_perm = X_train[perm] (train.py:104-108): out (N,D) = rows of x (N,D) in a pseudo-random order that

@@ -223,3 +223,71 @@ def test_epoch_shuffle_is_a_permutation():
     lp = torch.randn(100_001, device="cuda")
     _lib.check(lib.zf_neg_sum(st, lp.data_ptr(), lp.numel(), acc.data_ptr()))
     assert abs(acc.item() + lp.double().sum().item()) < 1e-6
+
+
+def test_nadamw_device_counter_matches_host_counter():
+    """zf_nadamw_update_dev (step counter and bias corrections on the device: what lets a train step be replayed as a
+    CUDA graph) against zf_nadamw_update on the same gradients."""
+    from zenflow_b200 import _lib
+
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(5)
+    n = 4099
+    p0 = torch.from_numpy(rng.normal(size=n).astype(np.float32)).cuda()
+    for nesterov in (1, 0):
+        pa, pb = p0.clone(), p0.clone()
+        ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        bias = torch.zeros(4, device="cuda")
+        for it in range(7):
+            g = torch.from_numpy(rng.normal(scale=0.3, size=n).astype(np.float32)).cuda()
+            _lib.check(lib.zf_nadamw_update(st, n, pa.data_ptr(), g.data_ptr(), ma.data_ptr(), va.data_ptr(), it,
+                                            1e-3, 0.9, 0.999, 1e-8, 1e-4, nesterov))
+            _lib.check(lib.zf_nadamw_update_dev(st, n, pb.data_ptr(), g.data_ptr(), mb.data_ptr(), vb.data_ptr(),
+                                                cnt.data_ptr(), bias.data_ptr(), 1e-3, 0.9, 0.999, 1e-8, 1e-4, nesterov))
+            assert int(cnt.item()) == it + 1
+            np.testing.assert_allclose(pb.cpu().numpy(), pa.cpu().numpy(), rtol=3e-7, atol=1e-9)
+
+
+def test_graphed_small_batch_steps_match_eager_steps():
+    """Small single-device steps replay a captured CUDA graph (TrainEngine._step_graphed): same losses, parameters,
+    running statistics and step count as the eager sequence, over full and ragged minibatches with fresh data each
+    step (a stale staging buffer or a frozen step counter would show)."""
+    from zenflow_b200 import Flow, _lib
+    from zenflow_b200._train import TrainEngine
+
+    D, C, K, layers = 2, 1, 16, (128, 128)
+    ops = zo.make_chain(D, K, layers)
+    v = zo.init_variables(ops, D, C, 4, weight_scale=1.0, randomize_bn=True)
+    rng = np.random.default_rng(11)
+    sizes = [256, 256, 100, 256, 256, 100, 256, 256]
+    batches = [(rng.normal(0.2, 1.0, (m, D)).astype(np.float32), rng.uniform(0, 1, (m, C)).astype(np.float32)) for m in sizes]
+    engines = []
+    for graphs in (False, True):
+        flow = Flow(product_chain(ops))
+        flow.latent._latch_dim(D)
+        eng = TrainEngine(flow, _flow_vars(v), D, C)
+        eng.use_graphs = graphs
+        engines.append(eng)
+    losses = [[], []]
+    launches = []
+    for x, c in batches:
+        for i, eng in enumerate(engines):
+            n0 = _lib.launch_count()
+            losses[i].append(-float(eng.step(x, c).item()) / len(x))
+            launches.append(_lib.launch_count() - n0)
+    eager, graphed = engines
+    assert any(e["graph"] is not None for e in graphed._graphs.values()) and not eager._graphs
+    assert launches[0::2] == launches[1::2] and min(launches) > 10   # replays are counted like the eager launches
+    assert graphed.count == eager.count == len(sizes) == int(graphed._count_dev.item()) == int(eager._count_dev.item())
+    np.testing.assert_allclose(losses[1], losses[0], rtol=2e-5, atol=1e-6)
+    assert losses[0][-1] < losses[0][0]
+    pe, pg = eager.P.cpu().numpy(), graphed.P.cpu().numpy()
+    diff = np.abs(pe - pg)
+    # fp32 atomics order the gradient sums differently from run to run: Adam turns a near-zero gradient's noise into
+    # a step of up to lr, so a handful of parameters may differ by that much; everything else agrees
+    assert np.quantile(diff, 0.99) <= 1e-5 and diff.max() <= 1e-3 * len(sizes)
+    ve, vg = eager.variables(as_numpy=True)["batch_stats"], graphed.variables(as_numpy=True)["batch_stats"]
+    flat = lambda t: np.concatenate([np.ravel(x) for x in torch.utils._pytree.tree_leaves(t)])
+    np.testing.assert_allclose(flat(vg), flat(ve), rtol=1e-4, atol=1e-5)

@@ -14,6 +14,7 @@ No arithmetic happens in Python here: torch only owns the buffers, views and col
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -383,6 +384,12 @@ class TrainEngine:
             g["chain"], g["_keep"] = _chain_struct(D, self.C, ops)
         self._bufs: Dict[int, dict] = {}
         self.lp_sum = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        # optimiser step counter in device memory (zf_nadamw_update_dev) + its bias-correction scratch, and the
+        # captured single-device steps of small batches (see _step_graphed)
+        self._count_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._bias = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self._graphs: Dict[tuple, dict] = {}
+        self.use_graphs = os.environ.get("ZF_TRAIN_GRAPHS", "1") != "0"
 
         # ---- the whole flow as ONE native chain for zf_flow_value_and_grad: couplings point at the flat parameter
         # buffer and at the RUNNING statistics (updated in place by the call)
@@ -479,14 +486,64 @@ class TrainEngine:
                 global_count = int(cnt.item())
             else:
                 global_count = M
+        if (self.use_graphs and update and self.world == 1 and lp_cotangent is None and global_count == M
+                and 0 < M <= self.GRAPH_MAX_ROWS):
+            return self._step_graphed(x, c, M, update, want_gc)
+        return self._step_eager(x, c, M, global_count, update, want_gc, lp_cotangent)
+
+    # a step of this many rows or fewer is bound by its ~35 launches per coupling, not by the kernels
+    GRAPH_MAX_ROWS = 1 << 16
+
+    def _step_graphed(self, x, c, M: int, update: bool, want_gc: bool):
+        """Single-device optimiser step of a small batch as ONE CUDA-graph launch: the first step of a shape runs
+        eagerly, the second is captured (inputs staged in fixed buffers; the optimiser's step counter lives on the
+        device, so no kernel argument changes between steps) and every later one replays the graph.  With ``want_gc``
+        the returned d loss / d c is the graph's own buffer: consume it before the next step of the same shape
+        (``value_and_grad`` / ``update=False`` never takes this path).  ZF_TRAIN_GRAPHS=0 turns it off."""
+        lib = _lib.load()
+        key = (M, bool(update), bool(want_gc and self.C))
+        e = self._graphs.get(key)
+        fresh = e is None
+        if fresh:
+            if len(self._graphs) >= 4:   # full + ragged minibatch, with and without update
+                self._graphs.pop(next(iter(self._graphs)))
+            f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=self.dev)
+            e = self._graphs[key] = dict(graph=None, launches=0, x=f32(M, self.D), c=f32(M, self.C) if self.C else None,
+                                         gc=f32(M, self.C) if key[2] else None, ws=self._workspace(M))
+        e["x"].copy_(x)
+        if e["c"] is not None:
+            e["c"].copy_(c)
+        if fresh:
+            self._step_eager(e["x"], e["c"], M, M, update, want_gc, None, gc=e["gc"], ws=e["ws"])
+        else:
+            if e["graph"] is None:
+                graph = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    self._step_eager(e["x"], e["c"], M, M, update, want_gc, None, gc=e["gc"], ws=e["ws"], count=False)
+                e["launches"] = _lib.launch_count() - n0
+                lib.zf_launch_count_add(-e["launches"])   # capturing launched nothing
+                e["graph"] = graph
+            e["graph"].replay()
+            lib.zf_launch_count_add(e["launches"])
+            if update:
+                self.count += 1
+        self._last_gc = e["gc"]
+        return (self.lp_sum, e["gc"]) if want_gc else self.lp_sum
+
+    def _step_eager(self, x, c, M: int, global_count, update: bool, want_gc: bool, lp_cotangent, *, gc=None, ws=None,
+                    count: bool = True):
+        lib = _lib.load()
+        st = stream_ptr()
         self.G.zero_()
         self.lp_sum.zero_()
         if self.world > 1 and not self.use_nccl:
             gc = self._step_phased(x, c, global_count, lp_cotangent)
         else:
-            ws = self._workspace(M)
+            ws = self._workspace(M) if ws is None else ws
             base = (ws.data_ptr() + 255) & ~255
-            gc = torch.empty(M, self.C, dtype=torch.float32, device=self.dev) if (want_gc and self.C) else None
+            if gc is None:
+                gc = torch.empty(M, self.C, dtype=torch.float32, device=self.dev) if (want_gc and self.C) else None
             comm = self.comm
             aux = comm.aux_stream.cuda_stream if comm is not None else None
             ct = None if lp_cotangent is None else to_device_f32(lp_cotangent, self.dev)
@@ -499,10 +556,11 @@ class TrainEngine:
         self._last_gc = gc
         if update:
             h = self.hp
-            _lib.check(lib.zf_nadamw_update(st, self.n_params, ptr(self.P), ptr(self.G), ptr(self.mu), ptr(self.nu),
-                                            self.count, h["lr"], h["b1"], h["b2"], h["eps"], h["weight_decay"],
-                                            h["nesterov"]), "zf_nadamw_update")
-            self.count += 1
+            _lib.check(lib.zf_nadamw_update_dev(st, self.n_params, ptr(self.P), ptr(self.G), ptr(self.mu), ptr(self.nu),
+                                                ptr(self._count_dev), ptr(self._bias), h["lr"], h["b1"], h["b2"], h["eps"],
+                                                h["weight_decay"], h["nesterov"]), "zf_nadamw_update_dev")
+            if count:
+                self.count += 1   # host mirror of the device counter
         return (self.lp_sum, gc) if want_gc else self.lp_sum
 
     def value_and_grad(self, x, c=None, *, global_count: Optional[int] = None):

@@ -56,3 +56,4 @@ int get_device_info(DeviceInfo* out) {
 extern "C" int32_t zf_abi_version(void) { return ZF_ABI_VERSION; }
 extern "C" const char* zf_last_error(void) { return zf::g_err; }
 extern "C" int64_t zf_launch_count(void) { return zf::g_launches; }
+extern "C" void zf_launch_count_add(int64_t n) { zf::g_launches += n; }

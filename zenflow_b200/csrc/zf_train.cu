@@ -560,6 +560,36 @@ __global__ void __launch_bounds__(256) nadamw_kernel(long long n, float* __restr
     }
 }
 
+// The same update with the step counter in device memory: bias corrections from count[0] (updates done so far),
+// then count[0] += 1.  Nothing on the host changes from step to step, so a captured train step can be replayed.
+__global__ void nadamw_bias_kernel(long long* count, float b1, float b2, float* bc) {
+    const double t = (double)count[0] + 1.0;
+    bc[0] = (float)(1.0 - pow((double)b1, t));
+    bc[1] = (float)(1.0 - pow((double)b1, t + 1.0));
+    bc[2] = (float)(1.0 - pow((double)b2, t));
+    count[0] += 1;
+}
+
+__global__ void __launch_bounds__(256) nadamw_dev_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ mu, float* __restrict__ nu, float lr, float b1,
+                                                         float b2, float eps, float wd, const float* __restrict__ bc,
+                                                         int nesterov) {
+    const float bc1_t = bc[0], bc1_t1 = bc[1], bc2_t = bc[2];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float m = b1 * mu[i] + (1.0f - b1) * gi;
+        const float v = b2 * nu[i] + (1.0f - b2) * gi * gi;
+        mu[i] = m;
+        nu[i] = v;
+        float mhat;
+        if (nesterov) mhat = b1 * (m / bc1_t1) + (1.0f - b1) * (gi / bc1_t);
+        else mhat = m / bc1_t;
+        const float vhat = v / bc2_t;
+        const float upd = mhat / (sqrtf(vhat) + eps) + wd * p[i];
+        p[i] = p[i] - lr * upd;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // epoch shuffle (train.py:104-108): X_perm = X_train[perm].  perm is a keyed pseudo-random
 // permutation of [0, N): a 4-round balanced Feistel network on 2h >= log2(N) bits with cycle
@@ -988,6 +1018,21 @@ extern "C" int zf_nadamw_update(void* stream, int64_t n, float* params, const fl
     nadamw_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(n, params, grads, mu, nu, lr, b1, b2, eps,
                                                                                   weight_decay, bc1_t, bc1_t1, bc2_t, nesterov);
     count_launch();
+    ZF_CUDA_CHECK(cudaGetLastError());
+    return ZF_OK;
+}
+
+extern "C" int zf_nadamw_update_dev(void* stream, int64_t n, float* params, const float* grads, float* mu, float* nu,
+                                    int64_t* count_dev, float* bias_scratch, float lr, float b1, float b2, float eps,
+                                    float weight_decay, int32_t nesterov) {
+    ZF_REQUIRE(params && grads && mu && nu && count_dev && bias_scratch && n >= 0, "nadamw_update_dev: bad argument");
+    nadamw_bias_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(count_dev), b1, b2, bias_scratch);
+    count_launch();
+    if (n > 0) {
+        nadamw_dev_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(n, params, grads, mu, nu, lr, b1, b2,
+                                                                                          eps, weight_decay, bias_scratch, nesterov);
+        count_launch();
+    }
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;
 }

@@ -101,6 +101,23 @@ __device__ __forceinline__ float cond_feature(const float* __restrict__ x, const
     return (f < D - d) ? x[m * D + d + f] : c[m * C + (f - (D - d))];
 }
 
+// (s1, s2) of the threads that share feature f -> sh[f], sh[F + f].  Shared-memory double atomics are
+// compare-and-swap loops, so 256 / F threads on one address serialise: when F is a power of two the lanes of a
+// warp that hold the same feature (F apart) are summed with shuffles first.  Every thread of the block must call.
+__device__ __forceinline__ void feature_sums_to_shared(double s1, double s2, int f, int F, bool valid, double* sh) {
+    if (F <= 32 && (F & (F - 1)) == 0) {
+        for (int o = F; o < 32; o <<= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        valid = valid && (threadIdx.x & 31) < F;
+    }
+    if (valid) {
+        atomicAdd(&sh[f], s1);
+        atomicAdd(&sh[F + f], s2);
+    }
+}
+
 // sums[f] += sum_m h, sums[F+f] += sum_m h^2 (double)
 __global__ void __launch_bounds__(256) bn_moments_kernel(const float* __restrict__ x, const float* __restrict__ c,
                                                          long long M, int D, int C, double* sums) {
@@ -110,16 +127,27 @@ __global__ void __launch_bounds__(256) bn_moments_kernel(const float* __restrict
     __syncthreads();
     const int R = blockDim.x / F;  // rows per pass
     const int r = threadIdx.x / F, f = threadIdx.x - r * F;
+    double s1 = 0.0, s2 = 0.0;
     if (r < R) {
-        double s1 = 0.0, s2 = 0.0;
-        for (long long m = (long long)blockIdx.x * R + r; m < M; m += (long long)gridDim.x * R) {
+        const long long step = (long long)gridDim.x * R;
+        long long m = (long long)blockIdx.x * R + r;
+        for (; m + 3 * step < M; m += 4 * step) {   // four rows in flight per thread (the loads are the whole cost)
+            float h[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = cond_feature(x, c, m + k * step, f, D, d, C);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s1 += (double)h[k];
+                s2 += (double)h[k] * (double)h[k];
+            }
+        }
+        for (; m < M; m += step) {
             const float h = cond_feature(x, c, m, f, D, d, C);
             s1 += (double)h;
             s2 += (double)h * (double)h;
         }
-        atomicAdd(&sh[f], s1);
-        atomicAdd(&sh[F + f], s2);
     }
+    feature_sums_to_shared(s1, s2, f, F, r < R, sh);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(&sums[i], sh[i]);
 }
@@ -165,10 +193,10 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restric
     __syncthreads();
     const int R = blockDim.x / F;
     const int r = threadIdx.x / F, f = threadIdx.x - r * F;
+    double s1 = 0.0, s2 = 0.0;
     if (r < R) {
         const float mu = mean[f];
         const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[f], 1e-5f)));
-        double s1 = 0.0, s2 = 0.0;
         const long long step = (long long)gridDim.x * R;
         long long m = (long long)blockIdx.x * R + r;
         for (; m + 3 * step < M; m += 4 * step) {   // four rows in flight per thread (the loads are the whole cost)
@@ -190,9 +218,8 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restric
             s1 += (double)gg;
             s2 += (double)gg * (double)((h - mu) * rstd);
         }
-        atomicAdd(&sh[f], s1);
-        atomicAdd(&sh[F + f], s2);
     }
+    feature_sums_to_shared(s1, s2, f, F, r < R, sh);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(&sums[i], sh[i]);
 }
@@ -649,6 +676,10 @@ static unsigned grid_for(long long n, int per_block, int cap) {
     return (unsigned)b;
 }
 
+// passes per block of the row-strided statistics kernels: the tuned figure for big batches, 4 for the small batches of
+// a reference-style train() (a step of 1,000 rows is latency-bound: one block walking them serially costs ~10 us)
+static int small_batch_rows(long long M, int big) { return M <= (1 << 16) ? 4 : big; }
+
 static void fill_cols(const zf_shift_bounds* sb, int D, SbCols& c) {
     for (int i = 0; i < D; ++i) {
         c.kind[i] = sb->kind[i];
@@ -693,7 +724,7 @@ extern "C" int zf_bn_moments(void* stream, const float* x, const float* c, int64
     cudaStream_t st = (cudaStream_t)stream;
     ZF_CUDA_CHECK(cudaMemsetAsync(sums, 0, 2 * F * sizeof(double), st));
     const int R = 256 / F;
-    bn_moments_kernel<<<grid_for(M, R * 64, 148 * 8), 256, 2 * F * sizeof(double), st>>>(x, c, M, D, C, sums);
+    bn_moments_kernel<<<grid_for(M, R * small_batch_rows(M, 64), 148 * 8), 256, 2 * F * sizeof(double), st>>>(x, c, M, D, C, sums);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;
@@ -865,7 +896,7 @@ static int coupling_backward_fused(cudaStream_t st, const zf_coupling* cp, const
         if (int rc = launch_img_tn(st, img_dz[cur], img_h0, lay.WH, gr->kernel[0], 1, 128, 128, F, nullptr, gr->bias[0], F, Mb)) return rc;
         if (int rc = launch_img_nt(st, img_dz[cur], 128, ws + lay.off_wimg[0], lay.WF0, nullptr, 0, nullptr, gh0 + m0 * F, F, F, Mb)) return rc;
         const int R = 256 / F;
-        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 4), 256, 2 * F * sizeof(double), st>>>(
+        bn_bwd_sums_kernel<<<grid_for(Mb, R * small_batch_rows(Mb, 64), 148 * 4), 256, 2 * F * sizeof(double), st>>>(
             x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
         count_launch();
     }
@@ -969,7 +1000,7 @@ extern "C" int zf_coupling_backward(void* stream, const zf_coupling* cp, const z
             if (int rc = launch_gemm(st, 1, ga)) return rc;
         }
         const int R = 256 / F;
-        bn_bwd_sums_kernel<<<grid_for(Mb, R * 64, 148 * 4), 256, 2 * F * sizeof(double), st>>>(
+        bn_bwd_sums_kernel<<<grid_for(Mb, R * small_batch_rows(Mb, 64), 148 * 4), 256, 2 * F * sizeof(double), st>>>(
             x_in + m0 * D, c ? c + m0 * C : nullptr, gh0 + m0 * F, Mb, D, C, cp->bn_mean, cp->bn_var, bn_sums);
         count_launch();
     }
@@ -999,7 +1030,7 @@ extern "C" int zf_bn_backward_apply(void* stream, const zf_coupling* cp, int32_t
     ZF_REQUIRE(cp && x_in && gh0 && bn_sums && gx && M >= 1 && global_count >= 1, "bn_backward_apply: bad argument");
     const int d = D / 2, F = D - d + C;
     const int R = 256 / F;
-    bn_bwd_apply_kernel<<<grid_for(M, R * 16, 148 * 16), 256, 5 * F * sizeof(float), (cudaStream_t)stream>>>(
+    bn_bwd_apply_kernel<<<grid_for(M, R * small_batch_rows(M, 16), 148 * 16), 256, 5 * F * sizeof(float), (cudaStream_t)stream>>>(
         x_in, c, gh0, M, D, C, cp->bn_scale, cp->bn_mean, cp->bn_var, bn_sums, global_count, gx, gc);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());

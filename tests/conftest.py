@@ -29,3 +29,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _fresh_default_latent():
+    """Flow's default latent is ONE instance shared by every Flow and latches its dim on first use (flow.py:20,
+    distributions.py:31-32 - the reference behaves the same): un-latch it so that tests do not depend on their order."""
+    try:
+        from zenflow_b200 import flow as _flow
+    except Exception:
+        yield
+        return
+    _flow._DEFAULT_LATENT._Distribution__dim = None
+    yield

@@ -496,6 +496,7 @@ def run_gpu(args):
     train_info = bench_train(args, world, rank, dev) if args.train_batch else None
     if rank == 0 and world == 1 and args.deep_set and not args.no_extras:
         extras["deep_set_train_step"] = bench_deep_set(dev)
+        extras["small_batch_train_step"] = bench_small_batch_train(dev)
 
     if rank != 0:
         if world > 1:
@@ -553,6 +554,44 @@ def run_gpu(args):
     os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_small_batch_train(dev, rows=1000, steps=300):
+    """The optimiser step as the reference's train() runs it (train.py:80-86,110-117: minibatches of ~1000 rows) on
+    two_moons_conditional: bound by the step's launches, so TrainEngine replays it as one CUDA graph (eager beside it)."""
+    import torch
+
+    from zenflow_b200 import _lib
+    from zenflow_b200._train import TrainEngine
+
+    w = dict(WORKLOADS["two_moons_conditional"])
+    out = {"config": {"workload": "two_moons_conditional", "rows_per_step": rows, "D": w["D"], "C": w["C"], "K": w["K"],
+                      "optimizer": "nadamw(1e-3)", "data": f"{steps} different minibatches"}}
+    x, c = synth(w, rows * 8, 777)
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
+    for graphs in (False, True):
+        flow, variables = build_flow(w, dev)
+        eng = TrainEngine(flow, variables, w["D"], w["C"])
+        eng.use_graphs = graphs
+        batch = lambda i: (xd[(i % 8) * rows:(i % 8 + 1) * rows], cd[(i % 8) * rows:(i % 8 + 1) * rows])
+        for i in range(5):
+            eng.step(*batch(i))
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            lp_sum = eng.step(*batch(i))
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        key = "graph" if graphs else "eager"
+        out[key] = {"ms_per_step": ms, "samples_per_s": rows / ms * 1e3,
+                    "gpu_launches_per_step": (_lib.launch_count() - n0) / steps,
+                    "loss_last": -float(lp_sum.item()) / rows}
+    out["what"] = ("zf_flow_value_and_grad + zf_nadamw_update_dev per step; 'graph' = the captured step replayed as one "
+                   "CUDA-graph launch (the default for single-device steps of <= 65,536 rows)")
+    return out
 
 
 def bench_deep_set(dev):

@@ -36,6 +36,15 @@ struct DeviceInfo {
 // Cached per device (once-per-device init is the only global mutable state).
 int get_device_info(DeviceInfo* out);
 
+// One weight image of pack_w_images (zf_img_gemm.cu): Wimg(n, k) = W[n * ldw + (k / NL) * P + k % NL] for n < n_valid and
+// k % NL < P, else 0, as the bf16x2 hi | lo operand image of img_nt_kernel.  block0 / blocks are filled by the launcher.
+struct PackWJob {
+    const float* W;
+    void* img;
+    int ldw, n_valid, N, KW, P, NL;
+    int block0, blocks;
+};
+
 // ---- PTX wrappers ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

@@ -328,13 +328,22 @@ __global__ void __launch_bounds__(IG_THREADS, 1) img_tn_kernel(const __grid_cons
 // weight image for img_nt_kernel: Wimg(n, k) = W[n * ldw + (k / NL) * P + k % NL] for n < n_valid and k % NL < P, else 0
 // (Dense kernel leaf (in, out) read as [n = in][k = out]; the last layer's columns padded per transformed dim)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_w_image_kernel(const float* __restrict__ W, int ldw, int n_valid, int N, int KW, int P, int NL,
-                                                           uint16_t* __restrict__ img) {
+constexpr int kMaxPackW = ZF_MAX_LAYERS + 1;
+struct PackWBatch { PackWJob job[kMaxPackW]; int n; };
+
+// all weight images of a coupling in one launch: block b works on the job whose [block0, block0 + blocks) holds it
+__global__ void __launch_bounds__(256) pack_w_images_kernel(const __grid_constant__ PackWBatch b) {
+    int i = 0;
+    while (i + 1 < b.n && (int)blockIdx.x >= b.job[i + 1].block0) ++i;
+    const PackWJob& j = b.job[i];
+    const float* __restrict__ W = j.W;
+    uint16_t* __restrict__ img = static_cast<uint16_t*>(j.img);
+    const int N = j.N, KW = j.KW, NL = j.NL, P = j.P;
     const int total = N * KW;
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    for (int e = ((int)blockIdx.x - j.block0) * 256 + threadIdx.x; e < total; e += j.blocks * 256) {
         const int k = e / N, n = e - k * N;
         const int jj = k / NL, p = k - jj * NL;
-        const float x = (n < n_valid && p < P) ? W[(size_t)n * ldw + jj * P + p] : 0.f;
+        const float x = (n < j.n_valid && p < P) ? W[(size_t)n * j.ldw + jj * P + p] : 0.f;
         uint32_t hi, lo;
         umma::split_bf16x2(x, 0.f, hi, lo);
         const int ii = umma::b_image_index_f16(n, k, N);
@@ -360,12 +369,23 @@ static int set_smem_once(const void* fn, size_t bytes) {
 size_t img_bytes(long long M, int W) { return (size_t)((M + 127) / 128) * 2 * W * 256; }
 size_t w_image_bytes(int N, int KW) { return (size_t)2 * N * KW * 2; }
 
-int pack_w_image(cudaStream_t st, const float* W, int ldw, int n_valid, int N, int KW, int P, int NL, void* img) {
-    pack_w_image_kernel<<<std::min(148 * 2, (N * KW + 255) / 256), 256, 0, st>>>(W, ldw, n_valid, N, KW, P, NL, static_cast<uint16_t*>(img));
+int pack_w_images(cudaStream_t st, const PackWJob* jobs, int n) {
+    ZF_REQUIRE(jobs && n >= 1 && n <= kMaxPackW, "pack_w_images: bad job list");
+    PackWBatch b{};
+    b.n = n;
+    int grid = 0;
+    for (int i = 0; i < n; ++i) {
+        b.job[i] = jobs[i];
+        b.job[i].block0 = grid;
+        b.job[i].blocks = std::max(1, std::min(148, (jobs[i].N * jobs[i].KW + 255) / 256));
+        grid += b.job[i].blocks;
+    }
+    pack_w_images_kernel<<<grid, 256, 0, st>>>(b);
     count_launch();
     ZF_CUDA_CHECK(cudaGetLastError());
     return ZF_OK;
 }
+
 
 int launch_img_nt(cudaStream_t st, const void* X, int KW, const void* Wimg, int N, const float* G, int ldg, void* out_img,
                   float* out_f32, int ldo, int n_valid, long long M) {

@@ -774,7 +774,7 @@ int coupling_vjp_run(cudaStream_t stream, const zf_coupling* cp, int D, int C, c
                      float* const* act_g, void* img_dtheta);
 size_t img_bytes(long long M, int W);
 size_t w_image_bytes(int N, int KW);
-int pack_w_image(cudaStream_t st, const float* W, int ldw, int n_valid, int N, int KW, int P, int NL, void* img);
+int pack_w_images(cudaStream_t st, const PackWJob* jobs, int n);
 int launch_img_nt(cudaStream_t st, const void* X, int KW, const void* Wimg, int N, const float* G, int ldg, void* out_img,
                   float* out_f32, int ldo, int n_valid, long long M);
 int launch_img_tn(cudaStream_t st, const void* A, const void* B, int WB, float* C, long long ldca, long long ldcb, int a_valid,
@@ -855,12 +855,14 @@ static int coupling_backward_fused(cudaStream_t st, const zf_coupling* cp, const
     float* gWp = reinterpret_cast<float*>(ws + lay.off_gwp);
     float* gbp = reinterpret_cast<float*>(ws + lay.off_gbp);
     if (int rc = coupling_vjp_pack(st, cp, D, C, pack)) return rc;
-    for (int l = 0; l <= L; ++l) {   // Dense_l kernel (in, out) as the image [n = in][k = out]
-        int rc;
-        if (l == 0) rc = pack_w_image(st, cp->kernel[0], 128, F, lay.WF0, 128, 128, 128, ws + lay.off_wimg[0]);
-        else if (l == L) rc = pack_w_image(st, cp->kernel[L], d * P, 128, 128, TW, P, NL, ws + lay.off_wimg[L]);
-        else rc = pack_w_image(st, cp->kernel[l], 128, 128, 128, 128, 128, 128, ws + lay.off_wimg[l]);
-        if (rc) return rc;
+    {   // Dense_l kernel (in, out) as the image [n = in][k = out], every layer in one launch
+        PackWJob jobs[ZF_MAX_LAYERS + 1];
+        for (int l = 0; l <= L; ++l) {
+            if (l == 0) jobs[l] = PackWJob{cp->kernel[0], ws + lay.off_wimg[0], 128, F, lay.WF0, 128, 128, 128, 0, 0};
+            else if (l == L) jobs[l] = PackWJob{cp->kernel[L], ws + lay.off_wimg[L], d * P, 128, 128, TW, P, NL, 0, 0};
+            else jobs[l] = PackWJob{cp->kernel[l], ws + lay.off_wimg[l], 128, 128, 128, 128, 128, 128, 0, 0};
+        }
+        if (int rc = pack_w_images(st, jobs, L + 1)) return rc;
     }
     ZF_CUDA_CHECK(cudaMemsetAsync(gWp, 0, lay.fixed_bytes - lay.off_gwp, st));
     char* wb = ws + lay.fixed_bytes;

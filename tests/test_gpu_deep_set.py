@@ -141,3 +141,21 @@ def test_deep_set_flow_joint_step_learns():
     assert min(losses[-10:]) < losses[0] - 0.3, losses[::10]
     lp = tr.log_prob(X, sm, y)
     assert lp.shape == (n_sets,) and bool(torch.isfinite(lp).all())
+
+
+def test_sum_matrix_indices_are_validated():
+    """The kernels index c and h with the COO lists: out-of-range entries must raise on the host, not corrupt memory."""
+    from zenflow_b200.deep_set import Phi, SumMatrix
+
+    sm = SumMatrix(np.array([0, 0, 1, 2]), np.array([0, 1, 2, 3]), 3)   # numpy / int64 input is accepted
+    assert sm.set_idx.dtype == torch.int32 and sm.set_idx.is_cuda and sm.nnz == 4
+    with pytest.raises(ValueError, match="set indices must be in"):
+        SumMatrix(np.array([0, 3]), np.array([0, 1]), 3)
+    with pytest.raises(ValueError, match="negative row index"):
+        SumMatrix(np.array([0, 1]), np.array([0, -1]), 3)
+    with pytest.raises(ValueError, match="row indices"):
+        SumMatrix(np.array([0, 1]), np.array([0]), 3)
+    phi = Phi()
+    x = np.zeros((3, 2), np.float32)   # 3 rows, the matrix refers to row 3
+    with pytest.raises(ValueError, match="out of bounds for 3 rows"):
+        phi.apply(phi.init(0, x), x, sm)

@@ -31,6 +31,29 @@ class SumMatrix:
     row_idx: torch.Tensor
     n_sets: int
 
+    def __post_init__(self):
+        # the kernels index with these: validate once here (an out-of-range entry would write outside c / read outside h)
+        dev = require_cuda()
+        as_i32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.int32).contiguous().reshape(-1)
+        self.set_idx, self.row_idx, self.n_sets = as_i32(self.set_idx), as_i32(self.row_idx), int(self.n_sets)
+        if self.set_idx.numel() != self.row_idx.numel():
+            raise ValueError(f"SumMatrix: {self.set_idx.numel()} set indices but {self.row_idx.numel()} row indices")
+        if self.n_sets < 1:
+            raise ValueError("SumMatrix: n_sets must be at least 1")
+        self._max_row = -1
+        if self.set_idx.numel():
+            s_lo, s_hi = (int(v) for v in torch.aminmax(self.set_idx))
+            r_lo, r_hi = (int(v) for v in torch.aminmax(self.row_idx))
+            if s_lo < 0 or s_hi >= self.n_sets:
+                raise ValueError(f"SumMatrix: set indices must be in [0, {self.n_sets}) (found {s_lo} .. {s_hi})")
+            if r_lo < 0:
+                raise ValueError(f"SumMatrix: negative row index {r_lo}")
+            self._max_row = r_hi
+
+    def check_rows(self, n_rows: int) -> None:
+        if self._max_row >= n_rows:
+            raise ValueError(f"SumMatrix: row index {self._max_row} is out of bounds for {n_rows} rows")
+
     @staticmethod
     def from_sizes(sizes: Sequence[int], device=None) -> "SumMatrix":
         device = device or require_cuda()
@@ -128,6 +151,7 @@ class PhiEngine:
         lib = _lib.load()
         x = to_device_f32(x, self.dev)
         N = x.shape[0]
+        sm.check_rows(N)
         ws = self._workspace(N)
         base = (ws.data_ptr() + 255) & ~255
         mask = None if dropout_mask is None else to_device_f32(dropout_mask, self.dev)

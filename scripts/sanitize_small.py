@@ -13,7 +13,7 @@ rng = np.random.default_rng(0)
 for (M, d, K) in [(1031, 1, 16), (517, 8, 32), (300, 3, 5)]:
     th = rng.standard_normal((M, d, 3 * K - 1)).astype(np.float32); x = rng.uniform(-.1, 1.1, (M, d)).astype(np.float32)
     rqs_forward_raw(x, th, K); rqs_inverse_raw(x, th, K)
-for impl in ("", "simt", "umma2"):
+for impl in ("", "simt", "umma8"):
     if impl: os.environ["ZF_CHAIN_IMPL"] = impl
     else: os.environ.pop("ZF_CHAIN_IMPL", None)
     for (D, C, K, layers, nc, roll, M) in [(2, 1, 16, (128, 128), None, 1, 777), (16, 4, 32, (128, 128), 3, 2, 300), (5, 3, 7, (64, 48), None, 1, 200),

@@ -498,8 +498,8 @@ class TrainEngine:
         """Single-device optimiser step of a small batch as ONE CUDA-graph launch: the first step of a shape runs
         eagerly, the second is captured (inputs staged in fixed buffers; the optimiser's step counter lives on the
         device, so no kernel argument changes between steps) and every later one replays the graph.  With ``want_gc``
-        the returned d loss / d c is the graph's own buffer: consume it before the next step of the same shape
-        (``value_and_grad`` / ``update=False`` never takes this path).  ZF_TRAIN_GRAPHS=0 turns it off."""
+        the returned d loss / d c is a copy of the graph's buffer (``value_and_grad`` / ``update=False`` never takes
+        this path).  ZF_TRAIN_GRAPHS=0 turns it off."""
         lib = _lib.load()
         key = (M, bool(update), bool(want_gc and self.C))
         e = self._graphs.get(key)
@@ -528,8 +528,9 @@ class TrainEngine:
             lib.zf_launch_count_add(e["launches"])
             if update:
                 self.count += 1
-        self._last_gc = e["gc"]
-        return (self.lp_sum, e["gc"]) if want_gc else self.lp_sum
+        gc = None if e["gc"] is None else e["gc"].clone()   # the graph's own buffer is overwritten by the next replay
+        self._last_gc = gc
+        return (self.lp_sum, gc) if want_gc else self.lp_sum
 
     def _step_eager(self, x, c, M: int, global_count, update: bool, want_gc: bool, lp_cotangent, *, gc=None, ws=None,
                     count: bool = True):
